@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the newsched data-parallel block hot path on B200.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+    null_source -> fft(N=4096, Blackman-Harris window) -> complex_to_mag -> null_sink,
+    1 GiB synthetic complex64 stream (32768 vectors) PER GPU, run as ONE fused kernel launch
+    per step (window + FFT + |.|).  A "step" is one pass over that stream.
+`value`    = whole-job Msamples/s with the stream already resident in HBM (CUDA events, max
+             over ranks).
+`e2e`      = the same metric through the C-ABI host-buffer call (b200_chain_run_host): pinned
+             host input -> H2D -> kernel -> D2H -> pinned host output, copies inside the region.
+`roofline` = algorithmic 12 B/sample (8 in + 4 out) x samples per launch / launch duration
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`extras`   = config 1 (fir_filter_ccf, 64 taps, 16 Mi samples) and the other blocks, each with
+             its own roofline, for the record.
+`--impl reference` times the CPU restatement (oracle/, OpenMP over all host threads) of the same
+workload: the reference snapshot has no FFT/FIR block and cannot be built here.
+
+Multi-GPU: independent per-GPU streams (the path shards by stream / time segment), no
+data-path collective; `scaling` = weak.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FFT = 4096
+N_VEC = 32768                       # 32768 x 4096 complex64 = 1 GiB
+SAMPLES = N_FFT * N_VEC
+METRIC = "Msamples/s FIR-ccf & FFT-4096 flowgraph at 1/2/4/8 B200; % of HBM/FP32 roofline"
+CONFIG = {
+    "workload": "configs[1]: null_source -> fft(N=4096, Blackman-Harris) -> complex_to_mag -> null_sink, "
+                "1 GiB synthetic complex64 stream per GPU (32768 vectors), one fused window+FFT+|.| launch per step",
+    "samples_per_gpu_per_step": SAMPLES,
+    "l2": "inputs (1 GiB in, 0.5 GiB out per step) are larger than the 126 MB L2; no flush needed",
+    "parallelism": "one independent stream per GPU (stream / time-segment sharding), no data-path collective",
+}
+
+
+def blackman_harris(n):
+    import numpy as np
+    t = np.arange(n, dtype=np.float64) / (n - 1)
+    return (0.35875 - 0.48829 * np.cos(2 * np.pi * t) + 0.14128 * np.cos(4 * np.pi * t)
+            - 0.01168 * np.cos(6 * np.pi * t)).astype(np.float32)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, torch_dev):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_dev).uuid)
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[torch_dev]) if vis else torch_dev
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self._err = repr(e)
+            self._h = None
+        self._t = None
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+              0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+              0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self._NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self._h is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "note": "no NVML samples"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "n_samples": len(self.samples)}
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_fft_mag_rate(steps, warmup, target_s=0.5):
+    """Times the oracle's fp32 FFT+|.| (OpenMP, all host threads) on a bounded sample."""
+    import numpy as np
+    import oracle as o
+    w = blackman_harris(N_FFT)
+    rng = np.random.default_rng(0x5EED)
+    nv = 256
+    x = (rng.uniform(-1, 1, nv * N_FFT) + 1j * rng.uniform(-1, 1, nv * N_FFT)).astype(np.complex64)
+    o.fft(x, N_FFT, True, w, precise=False, mag=True, mt=True)            # thread pool up
+    t0 = time.perf_counter()
+    o.fft(x, N_FFT, True, w, precise=False, mag=True, mt=True)
+    rate = x.size / (time.perf_counter() - t0)
+    nv_step = int(min(N_VEC, max(256, 2 ** int(np.log2(max(rate * target_s / N_FFT, 256))))))
+    x = np.tile(x, nv_step // nv + 1)[: nv_step * N_FFT]
+    for _ in range(warmup):
+        o.fft(x, N_FFT, True, w, precise=False, mag=True, mt=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.fft(x, N_FFT, True, w, precise=False, mag=True, mt=True)
+    dt = time.perf_counter() - t0
+    return {
+        "value": x.size * steps / dt / 1e6, "unit": "Msamples/s", "cores": o.num_threads(),
+        "kind": "port",
+        "sample": f"{nv_step} vectors x {N_FFT} complex64 ({x.nbytes >> 20} MiB) per step, {steps} steps; "
+                  "oracle.c fp32 radix-2 Stockham + window + |.|, OpenMP static over vectors "
+                  "(CPU restatement, not VOLK/FFTW: the reference snapshot has no FFT block)",
+        "ms_per_step": dt / steps * 1e3,
+    }
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    steps = max(1, args.steps)
+    cb = cpu_fft_mag_rate(steps, max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def timed(torch, fn, steps, warmup, barrier):
+    """W warm-ups, then exactly `steps` calls between CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    import newsched_b200 as nb
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nb.lib()
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    peak_gbs, peak_src, peaks = measured_peaks()
+    w = blackman_harris(N_FFT)
+
+    # ---- synthetic stream, resident in HBM (uniform[-1,1) complex64, seed 0x5EED + rank)
+    g = torch.Generator(device=dev).manual_seed(0x5EED + rank)
+    x = torch.view_as_complex(torch.rand(SAMPLES, 2, device=dev, generator=g) * 2 - 1)
+    out = torch.empty(SAMPLES, dtype=torch.float32, device=dev)
+    fft = nb.FFT(N_FFT, True, w, output=nb.OUT_MAG)
+
+    sampler = ClockSampler(local_rank)
+    l0 = nb.launch_count()
+    for _ in range(warmup):
+        fft.work(x, out)
+    torch.cuda.synchronize()
+    l_warm = nb.launch_count()
+    sampler.start()
+    ms = timed(torch, lambda: fft.work(x, out), steps, 0, barrier)
+    sampler.stop()
+    launches = nb.launch_count() - l_warm
+    ms = max_over_ranks(ms)
+    value = world * SAMPLES * steps / (ms * 1e-3) / 1e6
+    k_ms = ms / steps                                   # one launch per step
+    achieved = 12.0 * SAMPLES / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None,
+                "kernel": "fft4096_kernel<fwd, mag> (window + 3x radix-16 + |.|)",
+                "algorithmic_bytes_per_sample": 12, "peak_source": peak_src,
+                "launch_ms": k_ms}
+    traffic_file = os.path.join(ROOT, "profiles", "r01_fft4096_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through the C-ABI streaming call
+    e2e = None
+    try:
+        chunk = N_FFT * 2048                            # 64 MiB in / 32 MiB out per chunk
+        chain = nb.Chain([fft], in_item_bytes=8, chunk_items=chunk)
+        hx = torch.empty(SAMPLES, dtype=torch.complex64).pin_memory()
+        hx.copy_(x)
+        hy = torch.empty(SAMPLES, dtype=torch.float32).pin_memory()
+        e_steps = max(1, min(steps, 10))
+        for _ in range(2):
+            chain.run_host(hx, hy)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            chain.run_host(hx, hy)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt)
+        ok = bool(torch.equal(hy[-N_FFT:], out[-N_FFT:].cpu()))
+        e2e = {"value": world * SAMPLES * e_steps / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": SAMPLES * 8, "d2h_bytes_per_step": SAMPLES * 4,
+               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "matches_device_run": ok,
+               "api": "b200_chain_run_host (pinned host in/out, 3-stream H2D/compute/D2H overlap)",
+               "pcie_gbs": (SAMPLES * 12 * e_steps) / dt / 1e9}
+        del hx, hy, chain
+    except Exception as e:  # pragma: no cover
+        e2e = {"value": None, "unit": "Msamples/s", "error": repr(e)}
+
+    # ---- extras: the other configs / blocks, each with its own roofline (rank 0 reports)
+    extras = {}
+    try:
+        n1 = 1 << 24                                   # config 1: 16 Mi samples, 64 taps
+        x1 = x[:n1]
+        y1 = torch.empty(n1, dtype=torch.complex64, device=dev)
+        rng = np.random.default_rng(1)
+        fp32_tf, _ = nb.measure_fp32_tflops(8192)
+        fp32_tf, _ = nb.measure_fp32_tflops(8192)
+        for T in (64, 256, 1024):
+            taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+            fir = nb.FirFilter(taps, 1)
+            reps = max(3, min(steps, 20 if T <= 256 else 5))
+            t = timed(torch, lambda: fir.work_segment(x1, None, y1), reps, 3, lambda: None) / reps
+            gs = n1 / (t * 1e-3) / 1e9
+            extras[f"fir_ccf_{T}taps_16Mi"] = {
+                "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 4 * T / 1e3,
+                "frac_of_measured_fp32": gs * 4 * T / 1e3 / fp32_tf,
+                "hbm_gbs": gs * 16, "frac_of_hbm": gs * 16 / peak_gbs}
+        taps = (rng.uniform(-1, 1, 1024) / 1024).astype(np.float32)
+        fir = nb.FirFilter(taps, 4, multiply_const=0.5 - 0.25j)
+        n3 = 1 << 26
+        y3 = torch.empty(n3 // 4, dtype=torch.complex64, device=dev)
+        t = timed(torch, lambda: fir.work_segment(x[:n3], None, y3), 3, 2, lambda: None) / 3
+        gs = n3 / (t * 1e-3) / 1e9
+        extras["fir_ccf_1024taps_decim4_mulc_64Mi"] = {
+            "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 1024 / 1e3,
+            "frac_of_measured_fp32": gs * 1024 / 1e3 / fp32_tf}
+        extras["fp32_fma_tflops_measured"] = fp32_tf
+        yc = torch.empty(SAMPLES, dtype=torch.complex64, device=dev)
+        reps = max(3, min(steps, 20))
+        for name, fn, bps in (
+                ("copy_c64_1Gi", lambda: nb.copy(x, yc), 16),
+                ("multiply_const_cc_1Gi", lambda: nb.multiply_const(x, 0.5 - 0.25j, yc), 16),
+                ("complex_to_mag_1Gi", lambda: nb.complex_to_mag(x, False, out), 12)):
+            t = timed(torch, fn, reps, 3, lambda: None) / reps
+            gbs = SAMPLES * bps / (t * 1e-3) / 1e9
+            extras[name] = {"Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "ms": t, "hbm_gbs": gbs,
+                            "frac_of_hbm": gbs / peak_gbs}
+        fftc = nb.FFT(N_FFT, True, w)
+        t = timed(torch, lambda: fftc.work(x, yc), reps, 3, lambda: None) / reps
+        gbs = SAMPLES * 16 / (t * 1e-3) / 1e9
+        extras["fft4096_window_complex_out_1Gi"] = {"Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "ms": t,
+                                                   "hbm_gbs": gbs, "frac_of_hbm": gbs / peak_gbs}
+        import scipy.signal as sig
+        pt = sig.firwin(64 * 16, 1.0 / 64).astype(np.float32)
+        pfb = nb.PfbChannelizer(pt, 64)
+        yp = yc.view(-1, 64)
+        t = timed(torch, lambda: pfb.work_segment(x, None, yp), reps, 3, lambda: None) / reps
+        gbs = SAMPLES * 16 / (t * 1e-3) / 1e9
+        extras["pfb_channelizer_64ch_16tpc_1Gi"] = {"Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "ms": t,
+                                                   "hbm_gbs": gbs, "frac_of_hbm": gbs / peak_gbs}
+        del yc, y1, y3
+    except Exception as e:  # pragma: no cover
+        extras["error"] = repr(e)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_fft_mag_rate(10, 1, target_s=1.5)
+            cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "error": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "extras": extras,
+            "gpu_name": torch.cuda.get_device_name(dev),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,440 @@
+// fft.cu -- complex64 FFT of vector length N (power of two), forward / reverse, optional real
+// window, optional shift, optional fused complex_to_mag epilogue and fused upstream
+// multiply_const.  Hand-written shared-memory Stockham kernels; cuFFT is not used.
+//
+// Semantics (GNU Radio fft_vcc): t = x*w; X[k] = sum_n t[n] e^{-/+ j 2 pi k n/N};
+// no 1/N scaling; forward+shift = fftshift of the output; reverse+shift = ifftshift of the
+// input.  Both shifts are folded into tables at create time:
+//     forward+shift : w_eff[n] = w[n] * (-1)^n            (X[k+N/2] = FFT{x (-1)^n}[k])
+//     reverse+shift : w_eff[m] = w[(m+N/2) mod N], output * (-1)^k
+// and a fused upstream multiply_const k = |k| e^{j phi} becomes w_eff *= |k| plus a constant
+// output phasor -- so none of them costs a pass over memory.
+//
+// N = 4096 (the BASELINE config): one CTA of 256 threads per vector, three radix-16 passes
+// with 16 points per thread in registers (4096 = 16*16*16):
+//   pass 1  thread L=(n1,n0) loads x[n2*256+L] straight from HBM (coalesced 8 B/thread, 16
+//           loads in flight), window in registers, DFT16 over n2, twiddle W4096^{L k0} from
+//           registers (loaded once per CTA, reused for every vector), store A[k0][n1][n0];
+//   pass 2  thread (k0,n0) DFT16 over n1 IN PLACE, twiddle W256^{n0 k1} from a 2 KB shared
+//           table;
+//   pass 3  thread (k1,k0) DFT16 over n0, writes X[k0+16k1+256k2] (coalesced) or |X|.
+// Exactly one HBM read and one HBM write per sample (16 B, or 12 B with the fused |.|).
+// The exchange buffer uses a row stride of 257 complex so all three access patterns are
+// bank-conflict free.
+// Other N (8..8192): generic radix-2 shared-memory Stockham kernel.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr float C8 = 0.92387953251128674f;  // cos(pi/8)
+constexpr float S8 = 0.38268343236508977f;  // sin(pi/8)
+constexpr float R2 = 0.70710678118654752f;  // sqrt(1/2)
+
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// in: x0..x3 in (a,b,c,d); out: X0..X3 in (a,b,c,d)
+template <bool FWD>
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d)
+{
+    float2 t0 = a + c, t1 = a - c, t2 = b + d, t3 = b - d;
+    a = t0 + t2;
+    c = t0 - t2;
+    if (FWD) {
+        b = make_float2(t1.x + t3.y, t1.y - t3.x);
+        d = make_float2(t1.x - t3.y, t1.y + t3.x);
+    } else {
+        b = make_float2(t1.x - t3.y, t1.y + t3.x);
+        d = make_float2(t1.x + t3.y, t1.y - t3.x);
+    }
+}
+
+// multiply by W16^m (forward: e^{-j 2 pi m/16}; reverse: conjugate), m compile-time
+template <bool FWD, int M>
+__device__ __forceinline__ float2 mul_w16(float2 z)
+{
+    constexpr float cr[10] = { 1.f, C8, R2, S8, 0.f, -S8, -R2, -C8, -1.f, -C8 };
+    constexpr float si[10] = { 0.f, S8, R2, C8, 1.f, C8, R2, S8, 0.f, -S8 };
+    constexpr float wr = cr[M];
+    constexpr float wi = FWD ? -si[M] : si[M];
+    if (M == 0)
+        return z;
+    if (M == 4)
+        return FWD ? make_float2(z.y, -z.x) : make_float2(-z.y, z.x);
+    return make_float2(fmaf(-z.y, wi, z.x * wr), fmaf(z.x, wi, z.y * wr));
+}
+
+// 16-point DFT in registers.  Input natural order v[n]; output X[k] lands in v[pos16(k)].
+__host__ __device__ constexpr int pos16(int k) { return 4 * (k & 3) + (k >> 2); }
+
+template <bool FWD>
+__device__ __forceinline__ void dft16(float2 (&v)[16])
+{
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        dft4<FWD>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    // v[4c+b] = y_b[c]; twiddle by W16^{b c}
+    v[5] = mul_w16<FWD, 1>(v[5]);
+    v[6] = mul_w16<FWD, 2>(v[6]);
+    v[7] = mul_w16<FWD, 3>(v[7]);
+    v[9] = mul_w16<FWD, 2>(v[9]);
+    v[10] = mul_w16<FWD, 4>(v[10]);
+    v[11] = mul_w16<FWD, 6>(v[11]);
+    v[13] = mul_w16<FWD, 3>(v[13]);
+    v[14] = mul_w16<FWD, 6>(v[14]);
+    v[15] = mul_w16<FWD, 9>(v[15]);
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        dft4<FWD>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+constexpr int F4K_STRIDE = 257;
+
+template <bool FWD, int OUT>
+__global__ void __launch_bounds__(256, 2)
+    fft4096_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec,
+                   const float* __restrict__ weff, const float2* __restrict__ tw1,
+                   const float2* __restrict__ tw2)
+{
+    __shared__ float2 sA[16 * F4K_STRIDE];
+    __shared__ float2 sT2[256];
+    const int tid = threadIdx.x;
+
+    // per-thread constants, reused for every vector this CTA transforms
+    float wreg[16];
+    float2 t1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        wreg[i] = __ldg(weff + i * 256 + tid);
+        t1[i] = __ldg(tw1 + i * 256 + tid);
+    }
+    sT2[tid] = __ldg(tw2 + tid);
+    __syncthreads();
+
+    for (long long vec = blockIdx.x; vec < n_vec; vec += gridDim.x) {
+        const float2* x = in + vec * 4096;
+        float2 v[16];
+        // ---- pass 1: over n2, thread = L = n1*16+n0
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            v[i] = __ldcs(x + i * 256 + tid);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            v[i].x *= wreg[i];
+            v[i].y *= wreg[i];
+        }
+        dft16<FWD>(v);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++)
+            sA[k0 * F4K_STRIDE + tid] = cmul(v[pos16(k0)], t1[k0]);
+        __syncthreads();
+        // ---- pass 2: over n1, thread = (k0, n0), in place
+        {
+            const int k0 = tid >> 4, n0 = tid & 15;
+            float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i * 16];
+            dft16<FWD>(v);
+            row[0] = v[pos16(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++)
+                row[k1 * 16] = cmul(v[pos16(k1)], sT2[k1 * 16 + n0]);
+        }
+        __syncthreads();
+        // ---- pass 3: over n0, thread = (k1, k0)
+        {
+            const int k0 = tid & 15, k1 = tid >> 4;
+            const float2* row = sA + k0 * F4K_STRIDE + k1 * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i];
+            dft16<FWD>(v);
+            if (OUT == B200_FFT_OUT_COMPLEX) {
+                float2* y = reinterpret_cast<float2*>(out) + vec * 4096;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++)
+                    __stcs(y + k2 * 256 + tid, v[pos16(k2)]);
+            } else {
+                float* y = reinterpret_cast<float*>(out) + vec * 4096;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    float2 z = v[pos16(k2)];
+                    float p = fmaf(z.x, z.x, z.y * z.y);
+                    __stcs(y + k2 * 256 + tid, OUT == B200_FFT_OUT_MAG ? sqrt_approx(p) : p);
+                }
+            }
+        }
+        __syncthreads(); // pass-3 reads done before the next vector's pass-1 writes
+    }
+}
+
+// ---- generic power-of-two radix-2 Stockham (N = 8 .. 8192) ----------------------------------
+template <bool FWD, int OUT>
+__global__ void __launch_bounds__(512)
+    fft_generic_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec, int N,
+                       int log2n, int vpb, const float* __restrict__ weff,
+                       const float2* __restrict__ tw, float2 post, int flip)
+{
+    extern __shared__ __align__(16) float2 sbuf[];
+    const int per_cta = vpb * N;
+    float2* bx = sbuf;
+    float2* by = sbuf + per_cta;
+    const long long v0 = (long long)blockIdx.x * vpb;
+    const int nv = (int)((n_vec - v0) < vpb ? (n_vec - v0) : vpb);
+    if (nv <= 0)
+        return;
+    const int tot = nv * N;
+    const float2* x = in + v0 * N;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+        float2 t = __ldcs(x + i);
+        float w = __ldg(weff + (i & (N - 1)));
+        bx[i] = make_float2(t.x * w, t.y * w);
+    }
+    __syncthreads();
+    const int half = N >> 1;
+    int s_log = 0;
+    for (int n_log = log2n; n_log >= 1; n_log--, s_log++) {
+        const int m = 1 << (n_log - 1);
+        const int s = 1 << s_log;
+        for (int i = threadIdx.x; i < nv * half; i += blockDim.x) {
+            int vi = i / half;
+            int bi = i - vi * half;
+            int p = bi >> s_log;
+            int q = bi & (s - 1);
+            const float2* xb = bx + vi * N;
+            float2* yb = by + vi * N;
+            float2 a = xb[q + s * p];
+            float2 b = xb[q + s * (p + m)];
+            float2 w = __ldg(tw + (p << (log2n - n_log)));
+            float2 d = a - b;
+            yb[q + s * 2 * p] = a + b;
+            yb[q + s * (2 * p + 1)] = cmul(d, w);
+        }
+        __syncthreads();
+        float2* t = bx;
+        bx = by;
+        by = t;
+    }
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+        float2 z = bx[i];
+        int k = i & (N - 1);
+        if (OUT == B200_FFT_OUT_COMPLEX) {
+            z = cmul(z, post);
+            if (flip && (k & 1))
+                z = make_float2(-z.x, -z.y);
+            __stcs(reinterpret_cast<float2*>(out) + v0 * N + i, z);
+        } else {
+            float pw = fmaf(z.x, z.x, z.y * z.y);
+            __stcs(reinterpret_cast<float*>(out) + v0 * N + i,
+                   OUT == B200_FFT_OUT_MAG ? sqrt_approx(pw) : pw);
+        }
+    }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+struct b200_fft {
+    int N = 0, log2n = 0;
+    int forward = 1, out_mode = 0;
+    int flip = 0;
+    float2 post{ 1.f, 0.f };
+    float* d_weff = nullptr;
+    float2* d_tw1 = nullptr; // 4096 path: [16][256]
+    float2* d_tw2 = nullptr; // 4096 path: [16][16]
+    float2* d_tw = nullptr;  // generic: N/2
+    int vpb = 1;
+    int grid_4k = 296;
+};
+
+template <bool FWD, int OUT>
+static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec, cudaStream_t s)
+{
+    if (h->N == 4096) {
+        long long g = n_vec < h->grid_4k ? n_vec : h->grid_4k;
+        B200_LAUNCH((fft4096_kernel<FWD, OUT>), (unsigned)g, 256, 0, s, (const float2*)d_in, d_out,
+                    n_vec, h->d_weff, h->d_tw1, h->d_tw2);
+    } else {
+        long long blocks = (n_vec + h->vpb - 1) / h->vpb;
+        if (blocks > 0x7fffffffLL)
+            return set_err(B200_ERR_ARG, "fft: too many vectors for one call");
+        int work = h->vpb * h->N / 2;
+        int nt = work < 512 ? (work < 32 ? 32 : work) : 512;
+        size_t smem = sizeof(float2) * 2 * (size_t)h->vpb * h->N;
+        B200_LAUNCH((fft_generic_kernel<FWD, OUT>), (unsigned)blocks, nt, smem, s,
+                    (const float2*)d_in, d_out, n_vec, h->N, h->log2n, h->vpb, h->d_weff, h->d_tw,
+                    h->post, h->flip);
+    }
+    return B200_OK;
+}
+
+template <bool FWD>
+static int fft_run_o(b200_fft* h, const void* d_in, void* d_out, long long n_vec, cudaStream_t s)
+{
+    switch (h->out_mode) {
+    case B200_FFT_OUT_COMPLEX:
+        return fft_run_t<FWD, B200_FFT_OUT_COMPLEX>(h, d_in, d_out, n_vec, s);
+    case B200_FFT_OUT_MAG:
+        return fft_run_t<FWD, B200_FFT_OUT_MAG>(h, d_in, d_out, n_vec, s);
+    default:
+        return fft_run_t<FWD, B200_FFT_OUT_MAG_SQUARED>(h, d_in, d_out, n_vec, s);
+    }
+}
+
+template <bool FWD, int OUT>
+static cudaError_t fft_generic_attr()
+{
+    return cudaFuncSetAttribute(fft_generic_kernel<FWD, OUT>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+}
+
+extern "C" {
+
+int b200_fft_destroy(b200_fft* h)
+{
+    if (!h)
+        return B200_OK;
+    cudaFree(h->d_weff);
+    cudaFree(h->d_tw1);
+    cudaFree(h->d_tw2);
+    cudaFree(h->d_tw);
+    delete h;
+    return B200_OK;
+}
+
+int b200_fft_create(const b200_fft_params* p, b200_fft** out)
+{
+    if (!p || !out)
+        return set_err(B200_ERR_ARG, "fft_create: null argument");
+    *out = nullptr;
+    const int N = p->n;
+    if (N < 8 || N > 8192 || (N & (N - 1)))
+        return set_err(B200_ERR_UNSUPPORTED, "fft_create: N must be a power of two in [8, 8192], got %d", N);
+    if (p->output < 0 || p->output > 2)
+        return set_err(B200_ERR_ARG, "fft_create: bad output mode %d", p->output);
+    b200_fft* h = new b200_fft();
+    h->N = N;
+    while ((1 << h->log2n) < N)
+        h->log2n++;
+    h->forward = p->forward ? 1 : 0;
+    h->out_mode = p->output;
+    const double sgn = h->forward ? -1.0 : 1.0;
+
+    // effective window: window, shift folding, |k| of a fused upstream multiply_const
+    double kmag = 1.0, kph_re = 1.0, kph_im = 0.0;
+    if (p->fuse_pre_multiply_const) {
+        kmag = std::hypot((double)p->k_re, (double)p->k_im);
+        if (kmag > 0.0) {
+            kph_re = p->k_re / kmag;
+            kph_im = p->k_im / kmag;
+        }
+    }
+    std::vector<float> weff(N);
+    for (int n = 0; n < N; n++) {
+        double w;
+        if (!h->forward && p->shift) {
+            // t[n'] = x[(n'+N/2)%N] w[n']  ->  input element n meets w[(n - N/2) mod N]
+            w = p->window ? (double)p->window[(n + N - N / 2) % N] : 1.0;
+        } else {
+            w = p->window ? (double)p->window[n] : 1.0;
+            if (h->forward && p->shift && (n & 1))
+                w = -w;
+        }
+        weff[n] = (float)(w * kmag);
+    }
+    h->flip = (!h->forward && p->shift) ? 1 : 0;
+    h->post = make_float2((float)kph_re, (float)kph_im);
+
+#define FFT_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            b200_fft_destroy(h);                                                         \
+            return set_err(e__ == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA, \
+                           "fft_create: %s -> %s", #call, cudaGetErrorString(e__));      \
+        }                                                                                \
+    } while (0)
+
+    FFT_CUDA(cudaMalloc(&h->d_weff, sizeof(float) * N));
+    FFT_CUDA(cudaMemcpy(h->d_weff, weff.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+    if (N == 4096) {
+        std::vector<float2> t1(16 * 256), t2(256);
+        for (int k0 = 0; k0 < 16; k0++)
+            for (int L = 0; L < 256; L++) {
+                double ang = sgn * 2.0 * M_PI * (double)((L * k0) % 4096) / 4096.0;
+                double wr = std::cos(ang), wi = std::sin(ang);
+                // fold the output phasor and the reverse-shift (-1)^k (k parity = k0 parity)
+                double pr = kph_re, pi = kph_im;
+                if (h->flip && (k0 & 1)) {
+                    pr = -pr;
+                    pi = -pi;
+                }
+                t1[k0 * 256 + L] = make_float2((float)(wr * pr - wi * pi), (float)(wr * pi + wi * pr));
+            }
+        for (int k1 = 0; k1 < 16; k1++)
+            for (int n0 = 0; n0 < 16; n0++) {
+                double ang = sgn * 2.0 * M_PI * (double)(n0 * k1) / 256.0;
+                t2[k1 * 16 + n0] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+            }
+        FFT_CUDA(cudaMalloc(&h->d_tw1, sizeof(float2) * t1.size()));
+        FFT_CUDA(cudaMemcpy(h->d_tw1, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
+        FFT_CUDA(cudaMalloc(&h->d_tw2, sizeof(float2) * t2.size()));
+        FFT_CUDA(cudaMemcpy(h->d_tw2, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
+        h->grid_4k = 2 * sm_count();
+    } else {
+        std::vector<float2> tw(N / 2);
+        for (int j = 0; j < N / 2; j++) {
+            double ang = sgn * 2.0 * M_PI * (double)j / (double)N;
+            tw[j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        FFT_CUDA(cudaMalloc(&h->d_tw, sizeof(float2) * tw.size()));
+        FFT_CUDA(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+        h->vpb = N >= 1024 ? 1 : 1024 / N;
+        FFT_CUDA((fft_generic_attr<true, 0>()));
+        FFT_CUDA((fft_generic_attr<true, 1>()));
+        FFT_CUDA((fft_generic_attr<true, 2>()));
+        FFT_CUDA((fft_generic_attr<false, 0>()));
+        FFT_CUDA((fft_generic_attr<false, 1>()));
+        FFT_CUDA((fft_generic_attr<false, 2>()));
+    }
+#undef FFT_CUDA
+    *out = h;
+    return B200_OK;
+}
+
+int b200_fft_geometry(const b200_fft* h, int* n, int* out_item_bytes)
+{
+    if (!h)
+        return set_err(B200_ERR_ARG, "fft_geometry: null handle");
+    if (n)
+        *n = h->N;
+    if (out_item_bytes)
+        *out_item_bytes = h->out_mode == B200_FFT_OUT_COMPLEX ? 8 : 4;
+    return B200_OK;
+}
+
+int b200_fft_run(b200_fft* h, const void* d_in, void* d_out, int64_t n_vectors, b200_stream_t s)
+{
+    if (!h || n_vectors < 0 || (n_vectors > 0 && (!d_in || !d_out)))
+        return set_err(B200_ERR_ARG, "fft_run: bad argument");
+    if (n_vectors == 0)
+        return B200_OK;
+    if ((uintptr_t)d_in % 8 || (uintptr_t)d_out % (h->out_mode == B200_FFT_OUT_COMPLEX ? 8 : 4))
+        return set_err(B200_ERR_ARG, "fft_run: misaligned buffer");
+    return h->forward ? fft_run_o<true>(h, d_in, d_out, n_vectors, cs(s))
+                      : fft_run_o<false>(h, d_in, d_out, n_vectors, cs(s));
+}
+
+} // extern "C"

@@ -1,0 +1,441 @@
+// fir.cu -- decimating FIR filter, ccf (complex64 stream, real taps) and fff (float stream).
+//
+//   y[m] = sum_{k<T} h[k] x[m*D - k],  m = 0 .. floor(n_in/D)-1      
+//
+// The reference snapshot has no FIR block; the work() contract it plugs
+// into is gr::block::work (runtime/include/gnuradio/block.hpp:81-85) with
+// n_consumed = n_produced*D set by the block (block_work_io.hpp:21,36).
+//
+// Direct-form SIMT kernel (algorithm 1), FP32-pipe bound for T >= 32:
+//   * polyphase split: y = sum_p (h_p * x_p), h_p[q] = h[qD+p], x_p[j] = x[jD-p]; the
+//     input tile is staged once into shared memory de-interleaved by phase, so every phase
+//     is a unit-stride FIR and decimated-away products are never formed;
+//   * each thread owns 32 fp32 accumulators (16 complex / 32 real consecutive outputs) and a
+//     64-float circular register window over x_p; one step = 16 (32) taps = 512 (1024) FFMA
+//     fed by 8 LDS.128 of samples + 4 (8) LDS.128 of taps (warp-uniform broadcast): the inner
+//     loop is > 96 % FFMA issue slots;
+//   * shared layout is padded 16 B per 128 B so that the per-thread 128 B-strided LDS.128
+//     window reads are bank-conflict free;
+//   * outputs go back through shared memory so global stores are fully coalesced.
+// History (the T-1 samples before the next input item) lives in a ping-pong pair of small
+// device buffers owned by the handle; nothing is re-read from the host and the caller may
+// chunk the stream arbitrarily.
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int FIR_NT = 128;  // threads per CTA
+constexpr int FIR_ACC = 32;  // fp32 accumulators per thread
+constexpr int FIR_RING = 64; // register window (floats)
+
+__host__ __device__ __forceinline__ int padf(int f) { return f + ((f >> 5) << 2); }
+
+struct fir_epilogue {
+    int fuse;
+    float kre, kim;
+};
+
+// x value at global sample index g (may be negative -> history, or >= n_in -> 0)
+template <int VEC>
+__device__ __forceinline__ void fir_fetch(const float* __restrict__ x, const float* __restrict__ hist,
+                                          int Tm1, long long g, long long n_in, float* v)
+{
+    const float* src = nullptr;
+    if (g >= 0) {
+        if (g < n_in)
+            src = x + g * VEC;
+    } else if (hist && g >= -(long long)Tm1) {
+        src = hist + ((long long)Tm1 + g) * VEC;
+    }
+    if (VEC == 2) {
+        float2 t = src ? __ldg(reinterpret_cast<const float2*>(src)) : make_float2(0.f, 0.f);
+        v[0] = t.x;
+        v[1] = t.y;
+    } else {
+        v[0] = src ? __ldg(src) : 0.f;
+    }
+}
+
+// One step of CH taps against the register ring.  OFF = ring offset (floats) of output 0.
+template <int VEC, int CH, int OFF>
+__device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)[FIR_RING],
+                                         const float* __restrict__ hs)
+{
+#pragma unroll
+    for (int q4 = 0; q4 < CH; q4 += 4) {
+        float4 h4 = *reinterpret_cast<const float4*>(hs + q4);
+        const float hv[4] = { h4.x, h4.y, h4.z, h4.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int l = 0; l < FIR_ACC; l++)
+                acc[l] = fmaf(hv[u], W[(OFF + (q4 + u) * VEC + l) % FIR_RING], acc[l]);
+        }
+    }
+}
+
+template <int HALF>
+__device__ __forceinline__ void fir_load_half(float (&W)[FIR_RING], const float* __restrict__ p)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+        W[HALF * 32 + 4 * i + 0] = t.x;
+        W[HALF * 32 + 4 * i + 1] = t.y;
+        W[HALF * 32 + 4 * i + 2] = t.z;
+        W[HALF * 32 + 4 * i + 3] = t.w;
+    }
+}
+
+// smem: [taps D*TQ floats][planes D * plane_f floats]
+template <int VEC>
+__global__ void __launch_bounds__(FIR_NT, 3)
+    fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
+                      float* __restrict__ y, const float* __restrict__ taps_pp, int Tm1, int D,
+                      int TQ, int plane_f, long long n_in, long long n_out, fir_epilogue ep)
+{
+    constexpr int R = FIR_ACC / VEC;  // outputs per thread
+    constexpr int CH = FIR_ACC / VEC; // taps per step
+    constexpr int MT = FIR_NT * R;    // outputs per tile
+    extern __shared__ __align__(16) float smem[];
+    float* hs = smem;
+    float* planes = smem + D * TQ;
+
+    const int tid = threadIdx.x;
+    const long long M0 = (long long)blockIdx.x * MT;
+    const int PL = MT + TQ; // samples per plane
+
+    // ---- stage taps and the phase-deinterleaved input tile --------------------------
+    for (int i = tid; i < D * TQ; i += FIR_NT)
+        hs[i] = __ldg(taps_pp + i);
+    {
+        const long long g_lo = (M0 - TQ + 1) * D - (D - 1);
+        const int total = PL * D;
+        if (D == 1) {
+            for (int i = tid; i < total; i += FIR_NT) {
+                float v[2];
+                fir_fetch<VEC>(x, hist, Tm1, g_lo + i, n_in, v);
+                float* dst = planes + padf(i * VEC);
+                if (VEC == 2)
+                    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+                else
+                    dst[0] = v[0];
+            }
+        } else {
+            for (int i = tid; i < total; i += FIR_NT) {
+                int e = i / D;
+                int p = D - 1 - (i - e * D);
+                float v[2];
+                fir_fetch<VEC>(x, hist, Tm1, g_lo + i, n_in, v);
+                float* dst = planes + p * plane_f + padf(e * VEC);
+                if (VEC == 2)
+                    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+                else
+                    dst[0] = v[0];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- register-blocked multiply-accumulate -----------------------------------------
+    float acc[FIR_ACC];
+#pragma unroll
+    for (int l = 0; l < FIR_ACC; l++)
+        acc[l] = 0.f;
+    float W[FIR_RING];
+    const int nsteps = TQ / CH; // even by construction
+    for (int p = 0; p < D; p++) {
+        const float* xp = planes + p * plane_f + 36 * tid;
+        const float* hp = hs + p * TQ;
+        fir_load_half<0>(W, xp);
+        for (int b = 0; b < nsteps; b += 2) {
+            fir_load_half<1>(W, xp + 36 * (b + 1));
+            fir_step<VEC, CH, 0>(acc, W, hp + b * CH);
+            fir_load_half<0>(W, xp + 36 * (b + 2));
+            fir_step<VEC, CH, 32>(acc, W, hp + (b + 1) * CH);
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs: registers -> shared (padded) -> coalesced global -----------------------
+    {
+        float* o = planes + 36 * tid;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            *reinterpret_cast<float4*>(o + 4 * i) =
+                make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < MT; i += FIR_NT) {
+        long long m = M0 + i;
+        if (m >= n_out)
+            break;
+        const float* src = planes + padf(i * VEC);
+        if (VEC == 2) {
+            float2 v = *reinterpret_cast<const float2*>(src);
+            if (ep.fuse)
+                v = cmul_nofma(v, ep.kre, ep.kim);
+            __stcs(reinterpret_cast<float2*>(y) + m, v);
+        } else {
+            float v = src[0];
+            if (ep.fuse)
+                v = __fmul_rn(v, ep.kre);
+            __stcs(y + m, v);
+        }
+    }
+}
+
+// Fallback for parameter combinations the tiled kernel cannot stage (very large D):
+// one thread per output straight from global memory.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    fir_naive_kernel(const float* __restrict__ x, const float* __restrict__ hist,
+                     float* __restrict__ y, const float* __restrict__ taps, int T, int D,
+                     long long n_in, long long n_out, fir_epilogue ep)
+{
+    long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_out)
+        return;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < T; k++) {
+        float v[2];
+        fir_fetch<VEC>(x, hist, T - 1, m * D - k, n_in, v);
+        float h = __ldg(taps + k);
+        a0 = fmaf(h, v[0], a0);
+        if (VEC == 2)
+            a1 = fmaf(h, v[1], a1);
+    }
+    if (VEC == 2) {
+        float2 v = make_float2(a0, a1);
+        if (ep.fuse)
+            v = cmul_nofma(v, ep.kre, ep.kim);
+        reinterpret_cast<float2*>(y)[m] = v;
+    } else {
+        y[m] = ep.fuse ? __fmul_rn(a0, ep.kre) : a0;
+    }
+}
+
+// new_hist[j] = sample (n_consumed - Tm1 + j) of the stream (old history ++ x)
+__global__ void fir_hist_kernel(const float* __restrict__ x, const float* __restrict__ hist_old,
+                                float* __restrict__ hist_new, long long n_consumed, int Tm1, int VEC)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Tm1)
+        return;
+    long long s = n_consumed - Tm1 + j;
+    for (int c = 0; c < VEC; c++)
+        hist_new[j * VEC + c] = (s >= 0) ? x[s * VEC + c] : hist_old[(Tm1 + s) * VEC + c];
+}
+
+} // namespace b200
+
+using namespace b200;
+
+struct b200_fir {
+    int T = 0, D = 1, vec = 2;
+    int TQ = 0;      // taps per phase, padded
+    int plane_f = 0; // floats per phase plane in smem
+    size_t smem = 0;
+    int algorithm = 1;
+    fir_epilogue ep{ 0, 1.f, 0.f };
+    float* d_taps_pp = nullptr; // [D][TQ] reversed per phase
+    float* d_taps = nullptr;    // [T] natural order (naive kernel)
+    float* d_hist[2] = { nullptr, nullptr };
+    int cur = 0;
+    int device = 0;
+};
+
+static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* d_out,
+                      long long n_in, long long n_out, cudaStream_t s)
+{
+    if (n_out <= 0)
+        return B200_OK;
+    const float* x = (const float*)d_in;
+    float* y = (float*)d_out;
+    if (h->algorithm == 1) {
+        const int MT = FIR_NT * (FIR_ACC / h->vec);
+        long long tiles = (n_out + MT - 1) / MT;
+        if (tiles > 0x7fffffffLL)
+            return set_err(B200_ERR_ARG, "fir: too many items for one call");
+        if (h->vec == 2)
+            B200_LAUNCH((fir_direct_kernel<2>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
+                        h->d_taps_pp, h->T - 1, h->D, h->TQ, h->plane_f, n_in, n_out, h->ep);
+        else
+            B200_LAUNCH((fir_direct_kernel<1>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
+                        h->d_taps_pp, h->T - 1, h->D, h->TQ, h->plane_f, n_in, n_out, h->ep);
+    } else {
+        long long blocks = (n_out + 255) / 256;
+        if (h->vec == 2)
+            B200_LAUNCH((fir_naive_kernel<2>), (unsigned)blocks, 256, 0, s, x, d_hist, y, h->d_taps,
+                        h->T, h->D, n_in, n_out, h->ep);
+        else
+            B200_LAUNCH((fir_naive_kernel<1>), (unsigned)blocks, 256, 0, s, x, d_hist, y, h->d_taps,
+                        h->T, h->D, n_in, n_out, h->ep);
+    }
+    return B200_OK;
+}
+
+extern "C" {
+
+int b200_fir_destroy(b200_fir* h)
+{
+    if (!h)
+        return B200_OK;
+    cudaFree(h->d_taps_pp);
+    cudaFree(h->d_taps);
+    cudaFree(h->d_hist[0]);
+    cudaFree(h->d_hist[1]);
+    delete h;
+    return B200_OK;
+}
+
+int b200_fir_create(const b200_fir_params* p, b200_fir** out)
+{
+    if (!p || !out)
+        return set_err(B200_ERR_ARG, "fir_create: null argument");
+    *out = nullptr;
+    if (!p->taps || p->n_taps < 1 || p->decimation < 1)
+        return set_err(B200_ERR_ARG, "fir_create: need n_taps >= 1, decimation >= 1, taps != NULL");
+    if (p->algorithm == 2)
+        return set_err(B200_ERR_UNSUPPORTED, "fir_create: tensor-core algorithm not built yet");
+    b200_fir* h = new b200_fir();
+    h->T = p->n_taps;
+    h->D = p->decimation;
+    h->vec = p->is_complex ? 2 : 1;
+    h->ep = fir_epilogue{ p->fuse_multiply_const ? 1 : 0, p->k_re, p->k_im };
+    cudaGetDevice(&h->device);
+
+    const int CH = FIR_ACC / h->vec;
+    const int MT = FIR_NT * (FIR_ACC / h->vec);
+    int tq = (h->T + h->D - 1) / h->D;
+    h->TQ = (tq + 2 * CH - 1) / (2 * CH) * (2 * CH);
+    int PL = MT + h->TQ;
+    h->plane_f = padf(PL * h->vec) + 8; // +8: keep consecutive planes off the same banks
+    h->plane_f = (h->plane_f + 3) / 4 * 4;
+    h->smem = sizeof(float) * ((size_t)h->D * h->TQ + (size_t)h->D * h->plane_f);
+    h->algorithm = 1;
+    if (h->smem > 200 * 1024 || p->algorithm == 4)
+        h->algorithm = 4; // naive global-memory fallback
+    if (p->algorithm == 3)
+        h->algorithm = 1; // overlap-save not built yet: direct form is always valid
+
+#define FIR_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            b200_fir_destroy(h);                                                         \
+            return set_err(e__ == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA, \
+                           "fir_create: %s -> %s", #call, cudaGetErrorString(e__));      \
+        }                                                                                \
+    } while (0)
+
+    std::vector<float> pp((size_t)h->D * h->TQ, 0.f);
+    for (int ph = 0; ph < h->D; ph++)
+        for (int qr = 0; qr < h->TQ; qr++) {
+            long long k = (long long)(h->TQ - 1 - qr) * h->D + ph;
+            pp[(size_t)ph * h->TQ + qr] = (k < h->T) ? p->taps[k] : 0.f;
+        }
+    FIR_CUDA(cudaMalloc(&h->d_taps_pp, pp.size() * sizeof(float)));
+    FIR_CUDA(cudaMemcpy(h->d_taps_pp, pp.data(), pp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FIR_CUDA(cudaMalloc(&h->d_taps, (size_t)h->T * sizeof(float)));
+    FIR_CUDA(cudaMemcpy(h->d_taps, p->taps, (size_t)h->T * sizeof(float), cudaMemcpyHostToDevice));
+    size_t hb = sizeof(float) * (size_t)h->vec * (size_t)(h->T > 1 ? h->T - 1 : 1);
+    for (int i = 0; i < 2; i++) {
+        FIR_CUDA(cudaMalloc(&h->d_hist[i], hb));
+        FIR_CUDA(cudaMemset(h->d_hist[i], 0, hb));
+    }
+    if (h->algorithm == 1) {
+        if (h->vec == 2)
+            FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else
+            FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<1>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+#undef FIR_CUDA
+    *out = h;
+    return B200_OK;
+}
+
+int b200_fir_algorithm(const b200_fir* h) { return h ? h->algorithm : 0; }
+
+int b200_fir_geometry(const b200_fir* h, int* decimation, int* item_bytes)
+{
+    if (!h)
+        return set_err(B200_ERR_ARG, "fir_geometry: null handle");
+    if (decimation)
+        *decimation = h->D;
+    if (item_bytes)
+        *item_bytes = 4 * h->vec;
+    return B200_OK;
+}
+
+int b200_fir_run(b200_fir* h, const void* d_in, void* d_out, int64_t n_in_items,
+                 int64_t* n_consumed, int64_t* n_produced, b200_stream_t s)
+{
+    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+        return set_err(B200_ERR_ARG, "fir_run: bad argument");
+    long long n_out = n_in_items / h->D;
+    long long n_cons = n_out * h->D;
+    int rc = fir_launch(h, h->d_hist[h->cur], d_in, d_out, n_in_items, n_out, cs(s));
+    if (rc != B200_OK)
+        return rc;
+    if (h->T > 1 && n_cons > 0) {
+        int Tm1 = h->T - 1;
+        B200_LAUNCH(fir_hist_kernel, (Tm1 + 255) / 256, 256, 0, cs(s), (const float*)d_in,
+                    h->d_hist[h->cur], h->d_hist[h->cur ^ 1], n_cons, Tm1, h->vec);
+        h->cur ^= 1;
+    }
+    if (n_consumed)
+        *n_consumed = n_cons;
+    if (n_produced)
+        *n_produced = n_out;
+    return B200_OK;
+}
+
+int b200_fir_run_segment(b200_fir* h, const void* d_halo, const void* d_in, void* d_out,
+                         int64_t n_in_items, int64_t* n_produced, b200_stream_t s)
+{
+    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+        return set_err(B200_ERR_ARG, "fir_run_segment: bad argument");
+    long long n_out = n_in_items / h->D;
+    int rc = fir_launch(h, (const float*)d_halo, d_in, d_out, n_in_items, n_out, cs(s));
+    if (rc == B200_OK && n_produced)
+        *n_produced = n_out;
+    return rc;
+}
+
+int b200_fir_reset(b200_fir* h, b200_stream_t s)
+{
+    if (!h)
+        return set_err(B200_ERR_ARG, "fir_reset: null handle");
+    size_t hb = sizeof(float) * (size_t)h->vec * (size_t)(h->T > 1 ? h->T - 1 : 1);
+    B200_CUDA(cudaMemsetAsync(h->d_hist[h->cur], 0, hb, cs(s)));
+    return B200_OK;
+}
+
+int b200_fir_set_history(b200_fir* h, const void* d_hist, b200_stream_t s)
+{
+    if (!h || !d_hist)
+        return set_err(B200_ERR_ARG, "fir_set_history: null argument");
+    if (h->T > 1)
+        B200_CUDA(cudaMemcpyAsync(h->d_hist[h->cur], d_hist,
+                                  sizeof(float) * (size_t)h->vec * (size_t)(h->T - 1),
+                                  cudaMemcpyDeviceToDevice, cs(s)));
+    return B200_OK;
+}
+
+int b200_fir_get_history(b200_fir* h, void* d_hist, b200_stream_t s)
+{
+    if (!h || !d_hist)
+        return set_err(B200_ERR_ARG, "fir_get_history: null argument");
+    if (h->T > 1)
+        B200_CUDA(cudaMemcpyAsync(d_hist, h->d_hist[h->cur],
+                                  sizeof(float) * (size_t)h->vec * (size_t)(h->T - 1),
+                                  cudaMemcpyDeviceToDevice, cs(s)));
+    return B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,424 @@
+// pfb.cu -- critically sampled polyphase analysis channelizer (M channels, P taps/branch).
+//
+//   u_i[t] = sum_{r<P} h[i + r M] x[(t-r) M + (M-1-i)]
+//   y_c[t] = sum_{i<M} u_i[t] e^{+j 2 pi i c / M}              out[t*M + c]      
+//
+// Absent from the reference snapshot; plugs into gr::block::work
+// (runtime/include/gnuradio/block.hpp:81-85) as a rate-changing block
+// (n_consumed = M * n_produced).
+//
+// Algorithmically 4P + 5 log2 M flop and 16 B per input sample (AI ~ 6 flop/B for M=64,
+// P=16): HBM bound, so the kernel is the polyphase form -- branch FIRs from a shared-memory
+// tile with a register sliding window over time, then an M-point DFT across branches done
+// in shared memory/registers (radix 4 x 16 for M = 64) -- one HBM read and one HBM write
+// per sample.  A dense filterbank*DFT GEMM would execute 8T = 8192 flop/sample and cannot
+// reach the HBM bound of this form, so it is not used here.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// reverse (e^{+j}) 4-point DFT
+__device__ __forceinline__ void idft4(float2& a, float2& b, float2& c, float2& d)
+{
+    float2 t0 = f2add(a, c), t1 = f2sub(a, c), t2 = f2add(b, d), t3 = f2sub(b, d);
+    a = f2add(t0, t2);
+    c = f2sub(t0, t2);
+    b = make_float2(t1.x - t3.y, t1.y + t3.x);
+    d = make_float2(t1.x + t3.y, t1.y - t3.x);
+}
+
+__device__ __forceinline__ float2 cmulc(float2 z, float wr, float wi)
+{
+    return make_float2(fmaf(-z.y, wi, z.x * wr), fmaf(z.x, wi, z.y * wr));
+}
+
+// reverse 16-point DFT, output X[k] in v[4*(k&3) + (k>>2)]
+__device__ __forceinline__ void idft16(float2 (&v)[16])
+{
+    constexpr float C8 = 0.92387953251128674f, S8 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        idft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    v[5] = cmulc(v[5], C8, S8);
+    v[6] = cmulc(v[6], R2, R2);
+    v[7] = cmulc(v[7], S8, C8);
+    v[9] = cmulc(v[9], R2, R2);
+    v[10] = make_float2(-v[10].y, v[10].x);
+    v[11] = cmulc(v[11], -R2, R2);
+    v[13] = cmulc(v[13], S8, C8);
+    v[14] = cmulc(v[14], -R2, R2);
+    v[15] = cmulc(v[15], -C8, -S8);
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        idft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+// stream sample g relative to the new input (g < 0 -> halo of nh samples, oldest first)
+__device__ __forceinline__ float2 pfb_fetch(const float2* __restrict__ x, const float2* __restrict__ halo,
+                                            long long nh, long long g, long long n_in)
+{
+    if (g >= 0)
+        return g < n_in ? __ldcs(x + g) : make_float2(0.f, 0.f);
+    if (halo && g >= -nh)
+        return __ldg(halo + (nh + g));
+    return make_float2(0.f, 0.f);
+}
+
+constexpr int PFB64_TT = 64;  // frames per tile
+constexpr int PFB64_RS = 65;  // u row stride (complex)
+
+// M = 64.  256 threads.  smem: X[(TT+P4-1)][64] | U[TT][65] | taps[P4][64] | tw64[64]
+__global__ void __launch_bounds__(256, 2)
+    pfb64_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
+                 const float* __restrict__ taps_rm /* [P4][64] */, int P4, int Ptrue,
+                 long long n_frames, long long n_in, int ch_begin, int ch_count)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int rows = PFB64_TT + P4 - 1;
+    float2* X = sm;
+    float2* U = X + rows * 64;
+    float* hT = reinterpret_cast<float*>(U + PFB64_TT * PFB64_RS);
+    float2* tw = reinterpret_cast<float2*>(hT + P4 * 64);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P4 * 64; i += 256)
+        hT[i] = __ldg(taps_rm + i);
+    if (tid < 64) {
+        float s, c;
+        sincospif((float)tid / 32.0f, &s, &c); // e^{+j 2 pi tid/64}
+        tw[tid] = make_float2(c, s);
+    }
+    const long long nh = (long long)(Ptrue - 1) * 64;
+    const long long n_tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long f0 = tile * PFB64_TT; // first frame of the tile
+        __syncthreads();                      // previous tile's U/X consumers done
+        // rows: row j holds frame (f0 - (P4-1) + j), col = position within the frame
+        const long long g0 = (f0 - (P4 - 1)) * 64;
+        for (int i = tid; i < rows * 64; i += 256)
+            X[i] = pfb_fetch(x, halo, nh, g0 + i, n_in);
+        __syncthreads();
+
+        // ---- branch filters: thread = (branch i, 16 consecutive frames) ------------------
+        {
+            const int i = tid & 63, tg = tid >> 6;
+            const float2* col = X + (63 - i) + (tg * 16) * 64; // row (tg*16 + j + (P4-1) - r)
+            float2 acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                acc[j] = make_float2(0.f, 0.f);
+            for (int rc = 0; rc < P4; rc += 4) {
+                // taps r = rc..rc+3 ; rows needed: j + (P4-1) - r for j in 0..15 -> base = P4-1-rc-3
+                float h0 = hT[(rc + 0) * 64 + i], h1 = hT[(rc + 1) * 64 + i];
+                float h2 = hT[(rc + 2) * 64 + i], h3 = hT[(rc + 3) * 64 + i];
+                const float2* base = col + (P4 - 1 - rc - 3) * 64;
+                float2 w[19];
+#pragma unroll
+                for (int q = 0; q < 19; q++)
+                    w[q] = base[q * 64];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    // r = rc+u uses row offset j + 3 - u
+                    acc[j].x = fmaf(h0, w[j + 3].x, acc[j].x);
+                    acc[j].y = fmaf(h0, w[j + 3].y, acc[j].y);
+                    acc[j].x = fmaf(h1, w[j + 2].x, acc[j].x);
+                    acc[j].y = fmaf(h1, w[j + 2].y, acc[j].y);
+                    acc[j].x = fmaf(h2, w[j + 1].x, acc[j].x);
+                    acc[j].y = fmaf(h2, w[j + 1].y, acc[j].y);
+                    acc[j].x = fmaf(h3, w[j].x, acc[j].x);
+                    acc[j].y = fmaf(h3, w[j].y, acc[j].y);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                U[(tg * 16 + j) * PFB64_RS + i] = acc[j];
+        }
+        __syncthreads();
+
+        // ---- 64-point reverse DFT across branches: i = 16 i1 + i0, c = c0 + 4 c1 -----------
+        {
+            const int t = tid >> 2, g = tid & 3;
+            float2* row = U + t * PFB64_RS;
+            float2 v[16];
+            // pass A: DFT4 over i1 for i0 = 4g..4g+3 ; v[4*j + i1]
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i1 = 0; i1 < 4; i1++)
+                    v[4 * j + i1] = row[i1 * 16 + 4 * g + j];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                idft4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                const int i0 = 4 * g + j;
+#pragma unroll
+                for (int c0 = 1; c0 < 4; c0++) {
+                    float2 w = tw[(i0 * c0) & 63];
+                    v[4 * j + c0] = cmulc(v[4 * j + c0], w.x, w.y);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int c0 = 0; c0 < 4; c0++)
+                    row[c0 * 16 + 4 * g + j] = v[4 * j + c0];
+            __syncwarp();
+            // pass B: thread (t, c0 = g): DFT16 over i0 -> c1
+#pragma unroll
+            for (int i0 = 0; i0 < 16; i0++)
+                v[i0] = row[g * 16 + i0];
+            idft16(v);
+            const long long f = f0 + t;
+            if (f < n_frames) {
+                float2* y = out + f * ch_count;
+#pragma unroll
+                for (int c1 = 0; c1 < 16; c1++) {
+                    int c = g + 4 * c1 - ch_begin;
+                    if (c >= 0 && c < ch_count)
+                        __stcs(y + c, v[4 * (c1 & 3) + (c1 >> 2)]);
+                }
+            }
+        }
+    }
+}
+
+// generic M (power of two, 4..256): straightforward shared-memory version
+__global__ void __launch_bounds__(256)
+    pfb_generic_kernel(const float2* __restrict__ x, const float2* __restrict__ halo,
+                       float2* __restrict__ out, const float* __restrict__ taps /* [P][M] */, int M,
+                       int P, int TT, long long n_frames, long long n_in, int ch_begin, int ch_count)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const int rows = TT + P - 1;
+    float2* X = sm;
+    float2* U = X + rows * M;
+    float2* tw = U + TT * M;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < M; i += blockDim.x) {
+        float s, c;
+        sincospif(2.0f * (float)i / (float)M, &s, &c);
+        tw[i] = make_float2(c, s);
+    }
+    const long long nh = (long long)(P - 1) * M;
+    const long long f0 = (long long)blockIdx.x * TT;
+    const long long g0 = (f0 - (P - 1)) * M;
+    for (int i = tid; i < rows * M; i += blockDim.x)
+        X[i] = pfb_fetch(x, halo, nh, g0 + i, n_in);
+    __syncthreads();
+    for (int e = tid; e < TT * M; e += blockDim.x) {
+        int t = e / M, i = e - t * M;
+        float2 a = make_float2(0.f, 0.f);
+        for (int r = 0; r < P; r++) {
+            float h = __ldg(taps + r * M + i);
+            float2 v = X[(t + P - 1 - r) * M + (M - 1 - i)];
+            a.x = fmaf(h, v.x, a.x);
+            a.y = fmaf(h, v.y, a.y);
+        }
+        U[e] = a;
+    }
+    __syncthreads();
+    for (int e = tid; e < TT * ch_count; e += blockDim.x) {
+        int t = e / ch_count, cc = e - t * ch_count;
+        int c = cc + ch_begin;
+        long long f = f0 + t;
+        if (f >= n_frames)
+            continue;
+        float2 a = make_float2(0.f, 0.f);
+        for (int i = 0; i < M; i++) {
+            float2 w = tw[(i * c) & (M - 1)];
+            float2 u = U[t * M + i];
+            a.x += u.x * w.x - u.y * w.y;
+            a.y += u.x * w.y + u.y * w.x;
+        }
+        out[f * ch_count + cc] = a;
+    }
+}
+
+// new_tail[j] = sample (n_consumed - nh + j) of (old tail ++ x), complex64
+__global__ void pfb_tail_kernel(const float2* __restrict__ x, const float2* __restrict__ old_tail,
+                                float2* __restrict__ new_tail, long long n_consumed, long long nh)
+{
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nh)
+        return;
+    long long s = n_consumed - nh + j;
+    new_tail[j] = (s >= 0) ? x[s] : old_tail[nh + s];
+}
+
+} // namespace b200
+
+using namespace b200;
+
+struct b200_pfb {
+    int M = 0, P = 0, P4 = 0;
+    int ch_begin = 0, ch_count = 0;
+    float* d_taps_rm = nullptr; // [P4][M], zero padded rows
+    float2* d_tail[2] = { nullptr, nullptr };
+    int cur = 0;
+    size_t smem = 0;
+    int TT = 0;
+    int grid = 296;
+};
+
+static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d_out,
+                      long long n_in, long long n_frames, cudaStream_t s)
+{
+    if (n_frames <= 0)
+        return B200_OK;
+    if (h->M == 64) {
+        long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
+        long long g = tiles < h->grid ? tiles : h->grid;
+        B200_LAUNCH(pfb64_kernel, (unsigned)g, 256, h->smem, s, (const float2*)d_in,
+                    (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,
+                    h->ch_begin, h->ch_count);
+    } else {
+        long long tiles = (n_frames + h->TT - 1) / h->TT;
+        if (tiles > 0x7fffffffLL)
+            return set_err(B200_ERR_ARG, "pfb: too many items for one call");
+        B200_LAUNCH(pfb_generic_kernel, (unsigned)tiles, 256, h->smem, s, (const float2*)d_in,
+                    (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->M, h->P, h->TT, n_frames,
+                    n_in, h->ch_begin, h->ch_count);
+    }
+    return B200_OK;
+}
+
+extern "C" {
+
+int b200_pfb_destroy(b200_pfb* h)
+{
+    if (!h)
+        return B200_OK;
+    cudaFree(h->d_taps_rm);
+    cudaFree(h->d_tail[0]);
+    cudaFree(h->d_tail[1]);
+    delete h;
+    return B200_OK;
+}
+
+int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
+{
+    if (!p || !out)
+        return set_err(B200_ERR_ARG, "pfb_create: null argument");
+    *out = nullptr;
+    const int M = p->n_channels, P = p->taps_per_channel;
+    if (!p->taps || M < 4 || M > 256 || (M & (M - 1)) || P < 1)
+        return set_err(B200_ERR_ARG, "pfb_create: need M power of two in [4,256], P >= 1, taps != NULL");
+    int cb = p->channel_begin, cc = p->channel_count ? p->channel_count : M - p->channel_begin;
+    if (cb < 0 || cc < 1 || cb + cc > M)
+        return set_err(B200_ERR_ARG, "pfb_create: bad channel slice [%d, %d)", cb, cb + cc);
+    b200_pfb* h = new b200_pfb();
+    h->M = M;
+    h->P = P;
+    h->P4 = (P + 3) / 4 * 4;
+    h->ch_begin = cb;
+    h->ch_count = cc;
+#define PFB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            b200_pfb_destroy(h);                                                         \
+            return set_err(e__ == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA, \
+                           "pfb_create: %s -> %s", #call, cudaGetErrorString(e__));      \
+        }                                                                                \
+    } while (0)
+    std::vector<float> rm((size_t)h->P4 * M, 0.f);
+    for (int r = 0; r < P; r++)
+        for (int i = 0; i < M; i++)
+            rm[(size_t)r * M + i] = p->taps[i + r * M];
+    PFB_CUDA(cudaMalloc(&h->d_taps_rm, rm.size() * sizeof(float)));
+    PFB_CUDA(cudaMemcpy(h->d_taps_rm, rm.data(), rm.size() * sizeof(float), cudaMemcpyHostToDevice));
+    size_t nh = (size_t)(P - 1) * M;
+    for (int i = 0; i < 2; i++) {
+        PFB_CUDA(cudaMalloc(&h->d_tail[i], sizeof(float2) * (nh ? nh : 1)));
+        PFB_CUDA(cudaMemset(h->d_tail[i], 0, sizeof(float2) * (nh ? nh : 1)));
+    }
+    if (M == 64) {
+        int rows = PFB64_TT + h->P4 - 1;
+        h->smem = sizeof(float2) * ((size_t)rows * 64 + (size_t)PFB64_TT * PFB64_RS + 64) +
+                  sizeof(float) * (size_t)h->P4 * 64;
+        if (h->smem > 220 * 1024) {
+            b200_pfb_destroy(h);
+            return set_err(B200_ERR_UNSUPPORTED, "pfb_create: taps_per_channel too large for M=64 tile");
+        }
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)h->smem));
+        h->grid = 2 * sm_count();
+    } else {
+        h->TT = 4096 / M;
+        if (h->TT < 1)
+            h->TT = 1;
+        h->smem = sizeof(float2) * ((size_t)(h->TT + P - 1) * M + (size_t)h->TT * M + M);
+        if (h->smem > 220 * 1024) {
+            b200_pfb_destroy(h);
+            return set_err(B200_ERR_UNSUPPORTED, "pfb_create: taps_per_channel too large");
+        }
+        PFB_CUDA(cudaFuncSetAttribute(pfb_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)h->smem));
+    }
+#undef PFB_CUDA
+    *out = h;
+    return B200_OK;
+}
+
+int b200_pfb_run(b200_pfb* h, const void* d_in, void* d_out, int64_t n_in_items,
+                 int64_t* n_consumed, int64_t* n_produced_vectors, b200_stream_t s)
+{
+    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+        return set_err(B200_ERR_ARG, "pfb_run: bad argument");
+    long long n_frames = n_in_items / h->M;
+    long long n_cons = n_frames * h->M;
+    int rc = pfb_launch(h, h->d_tail[h->cur], d_in, d_out, n_in_items, n_frames, cs(s));
+    if (rc != B200_OK)
+        return rc;
+    long long nh = (long long)(h->P - 1) * h->M;
+    if (nh > 0 && n_cons > 0) {
+        B200_LAUNCH(pfb_tail_kernel, (unsigned)((nh + 255) / 256), 256, 0, cs(s), (const float2*)d_in,
+                    h->d_tail[h->cur], h->d_tail[h->cur ^ 1], n_cons, nh);
+        h->cur ^= 1;
+    }
+    if (n_consumed)
+        *n_consumed = n_cons;
+    if (n_produced_vectors)
+        *n_produced_vectors = n_frames;
+    return B200_OK;
+}
+
+int b200_pfb_run_segment(b200_pfb* h, const void* d_halo, const void* d_in, void* d_out,
+                         int64_t n_in_items, int64_t* n_produced_vectors, b200_stream_t s)
+{
+    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+        return set_err(B200_ERR_ARG, "pfb_run_segment: bad argument");
+    long long n_frames = n_in_items / h->M;
+    int rc = pfb_launch(h, d_halo, d_in, d_out, n_in_items, n_frames, cs(s));
+    if (rc == B200_OK && n_produced_vectors)
+        *n_produced_vectors = n_frames;
+    return rc;
+}
+
+int b200_pfb_geometry(const b200_pfb* h, int* n_channels, int* channel_count)
+{
+    if (!h)
+        return set_err(B200_ERR_ARG, "pfb_geometry: null handle");
+    if (n_channels)
+        *n_channels = h->M;
+    if (channel_count)
+        *channel_count = h->ch_count;
+    return B200_OK;
+}
+
+int b200_pfb_reset(b200_pfb* h, b200_stream_t s)
+{
+    if (!h)
+        return set_err(B200_ERR_ARG, "pfb_reset: null handle");
+    size_t nh = (size_t)(h->P - 1) * h->M;
+    B200_CUDA(cudaMemsetAsync(h->d_tail[h->cur], 0, sizeof(float2) * (nh ? nh : 1), cs(s)));
+    return B200_OK;
+}
+
+} // extern "C"

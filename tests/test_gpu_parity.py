@@ -1,0 +1,444 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded
+inputs, against the committed golden vectors, and -- at BASELINE sizes -- through
+size-independent properties.  Bars: bit-exact for copy / integer / indexing / decimation phase /
+multiply_const k=1; <= 1e-6 relative for multiply_const and complex_to_mag (<= 2 ulp);
+<= 1e-5 relative RMS for FIR, FFT and the channelizer (north_star)."""
+import numpy as np
+import pytest
+
+import oracle as o
+from conftest import cplx
+
+pytestmark = pytest.mark.gpu
+
+TOL_RMS = 1e-5   # north_star: FIR / FFT within 1e-5 relative RMS (fp32)
+TOL_EW = 1e-6    # elementwise fp32 ops
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------- copy
+def test_copy_reference_ramp_bit_exact(cuda, golden):
+    import newsched_b200 as nb
+    x = golden["ramp_qa_cuda_copy"]            # qa_scheduler_mt_cuda_copy.cpp:24-28
+    y = host(nb.copy(nb.copy(dev(cuda, x))))   # two chained copies like the reference test
+    assert np.array_equal(y.view(np.uint8), x.view(np.uint8))
+
+
+@pytest.mark.parametrize("nbytes", [0, 1, 15, 16, 17, 4095, 65536 + 3, (1 << 22) + 5])
+@pytest.mark.parametrize("off_in,off_out", [(0, 0), (8, 8), (8, 0), (4, 12), (1, 3), (3, 3), (2, 7)])
+def test_copy_any_alignment_bit_exact(cuda, nbytes, off_in, off_out):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(nbytes + off_in * 31 + off_out)
+    src = rng.integers(0, 256, nbytes + 64, dtype=np.uint8)
+    d_src = dev(cuda, src)
+    d_dst = cuda.full((nbytes + 64,), 0xA5, dtype=cuda.uint8, device="cuda")
+    nb._check(nb.lib().b200_copy(d_dst.data_ptr() + off_out, d_src.data_ptr() + off_in, nbytes,
+                                 nb._stream()))
+    got = host(d_dst)
+    assert np.array_equal(got[off_out:off_out + nbytes], src[off_in:off_in + nbytes])
+    assert (got[:off_out] == 0xA5).all() and (got[off_out + nbytes:] == 0xA5).all()  # no overrun
+
+
+def test_copy_full_size_checksum(cuda):
+    import newsched_b200 as nb
+    n = 1 << 24                                 # config 1 size: 16M complex64
+    x = cuda.randn(n, 2, device="cuda").view(cuda.uint8).flatten()
+    y = nb.copy(x)
+    assert cuda.equal(x, y)
+
+
+# --------------------------------------------------------------------- multiply_const
+def test_multiply_const_k1_exact(cuda, golden):
+    import newsched_b200 as nb
+    x = golden["ramp_qa_scheduler_mt"]          # qa_scheduler_mt.cpp:86-88, k = 1.0 -> exact
+    d = dev(cuda, x)
+    for _ in range(16):                          # qa_block_grouping.cpp chains up to 16 blocks
+        d = nb.multiply_const(d, 1.0 + 0j)
+    assert np.array_equal(host(d), x)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1023, 1 << 16, (1 << 20) + 7])
+def test_multiply_const_cc_matches_oracle(cuda, n):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(n)
+    x = cplx(rng, n + 1)
+    k = 0.5 - 0.25j
+    for off in (0, 1):                           # 16-byte aligned and 8-byte-only aligned
+        xs = x[off:off + n]
+        d = dev(cuda, x)[off:off + n]
+        y = host(nb.multiply_const(d, k))
+        ref = o.multiply_const(xs, k)
+        assert np.array_equal(y, ref), "non-fused fp32 product must be bit-identical to the oracle"
+
+
+def test_multiply_const_ff_ss_ii(cuda):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(11)
+    xf = rng.uniform(-4, 4, 100003).astype(np.float32)
+    assert np.array_equal(host(nb.multiply_const(dev(cuda, xf), 3.25)), o.multiply_const(xf, 3.25))
+    xs = rng.integers(-32768, 32767, 100001, dtype=np.int16)
+    assert np.array_equal(host(nb.multiply_const(dev(cuda, xs), -7)), o.multiply_const(xs, -7))
+    xi = rng.integers(-2**31, 2**31 - 1, 100002, dtype=np.int32)
+    assert np.array_equal(host(nb.multiply_const(dev(cuda, xi), 1000003)), o.multiply_const(xi, 1000003))
+
+
+def test_multiply_const_golden(cuda, golden):
+    import newsched_b200 as nb
+    y = host(nb.multiply_const(dev(cuda, golden["mulc_x"]), complex(golden["mulc_k"][0])))
+    assert o.rel_rms(y, golden["mulc_y64"]) < TOL_EW
+
+
+# --------------------------------------------------------------------- complex_to_mag
+@pytest.mark.parametrize("n", [1, 5, 4096, (1 << 20) + 3])
+def test_complex_to_mag(cuda, n):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(n)
+    x = cplx(rng, n + 1)
+    for off in (0, 1):
+        d = dev(cuda, x)[off:off + n]
+        y = host(nb.complex_to_mag(d))
+        assert np.array_equal(y, o.complex_to_mag(x[off:off + n]))  # same rounding sequence
+        y2 = host(nb.complex_to_mag(d, squared=True))
+        assert np.array_equal(y2, o.complex_to_mag(x[off:off + n], squared=True))
+
+
+def test_complex_to_mag_golden(cuda, golden):
+    import newsched_b200 as nb
+    y = host(nb.complex_to_mag(dev(cuda, golden["mulc_x"])))
+    assert o.rel_rms(y, golden["mag_y64"]) < TOL_EW
+
+
+# ------------------------------------------------------------------------------- FIR
+@pytest.mark.parametrize("name", ["fir_a", "fir_b", "fir_c"])
+def test_fir_golden(cuda, golden, name):
+    import newsched_b200 as nb
+    taps, x, D = golden[name + "_taps"], golden[name + "_x"], int(golden[name + "_D"][0])
+    T = taps.size
+    f = nb.FirFilter(taps, D, is_complex=np.iscomplexobj(x))
+    y, nc = f.work(dev(cuda, x))
+    assert nc == (x.size // D) * D
+    assert o.rel_rms(host(y), golden[name + "_y64"]) < TOL_RMS
+    # preload history, then stream the rest
+    f2 = nb.FirFilter(taps, D, is_complex=np.iscomplexobj(x))
+    f2.set_history(dev(cuda, x[: T - 1]))
+    y2, _ = f2.work(dev(cuda, x[T - 1:]))
+    assert o.rel_rms(host(y2), golden[name + "_y64_hist"]) < TOL_RMS
+
+
+@pytest.mark.parametrize("T,D,cplxin", [(1, 1, True), (2, 1, True), (5, 2, True), (64, 1, True),
+                                        (65, 1, True), (128, 1, True), (256, 3, True),
+                                        (1024, 4, True), (1000, 7, True), (64, 1, False),
+                                        (63, 2, False), (513, 5, False), (64, 16, True), (300, 40, True)])
+def test_fir_matches_oracle(cuda, T, D, cplxin):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T * 100 + D)
+    n = 40000 + 17
+    x = cplx(rng, n) if cplxin else rng.uniform(-1, 1, n).astype(np.float32)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    f = nb.FirFilter(taps, D, is_complex=cplxin)
+    y, nc = f.work(dev(cuda, x))
+    ref = o.fir(x, taps, D)
+    assert y.numel() == n // D and nc == (n // D) * D
+    assert o.rel_rms(host(y), ref) < TOL_RMS
+
+
+def test_fir_impulse_and_decimation_phase_exact(cuda, golden):
+    import newsched_b200 as nb
+    taps = golden["fir_imp_taps"]
+    imp = np.zeros(4096, np.complex64)
+    imp[0] = 1
+    y, _ = nb.FirFilter(taps, 1).work(dev(cuda, imp))
+    y = host(y)
+    assert np.array_equal(y[:48].real, taps) and not y[48:].any() and not y.imag.any()
+    for D in (2, 3, 4, 7):
+        yd, _ = nb.FirFilter(taps, D).work(dev(cuda, imp))
+        yd = host(yd)
+        k = len(taps[::D])
+        assert np.array_equal(yd.real[:k], taps[::D]), "decimation phase 0: y[m] aligned to x[m*D]"
+        assert not yd[k:].any()
+    # an impulse at n0: the response starts at ceil(n0/D) with tap (m*D - n0)
+    n0, D = 37, 4
+    imp2 = np.zeros(4096, np.complex64)
+    imp2[n0] = 1j
+    yd = host(nb.FirFilter(taps, D).work(dev(cuda, imp2))[0])
+    exp = np.zeros(1024, np.complex64)
+    for m in range(1024):
+        kk = m * D - n0
+        if 0 <= kk < taps.size:
+            exp[m] = 1j * taps[kk]
+    assert np.array_equal(yd, exp)
+
+
+@pytest.mark.parametrize("T,D", [(64, 1), (31, 3), (257, 4)])
+def test_fir_streaming_equals_oneshot(cuda, T, D):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(7 + T)
+    n = 30000
+    x = cplx(rng, n)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)
+    ref, _ = nb.FirFilter(taps, D).work(dx)
+    ref = host(ref)
+    for chunk in (1, T - 1 if T > 1 else 1, T, 997, 8192):
+        f = nb.FirFilter(taps, D)
+        step = max(chunk, D)          # the scheduler re-presents unconsumed items with new ones
+        outs, pos = [], 0
+        while n - pos >= D:
+            y, nc = f.work(dx[pos:min(pos + step, n)])
+            assert nc > 0
+            outs.append(host(y))
+            pos += nc
+        got = np.concatenate(outs)
+        assert got.size == n // D
+        assert np.array_equal(got, ref), f"chunk={chunk}: chunked != one-shot"
+
+
+def test_fir_empty_and_short(cuda):
+    import newsched_b200 as nb
+    f = nb.FirFilter(np.ones(8, np.float32), 4)
+    y, nc = f.work(cuda.zeros(0, dtype=cuda.complex64, device="cuda"))
+    assert y.numel() == 0 and nc == 0
+    y, nc = f.work(cuda.ones(3, dtype=cuda.complex64, device="cuda"))
+    assert y.numel() == 0 and nc == 0
+
+
+def test_fir_segment_halo_equals_stream(cuda):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(21)
+    T, D, n = 200, 2, 1 << 16
+    x = cplx(rng, n)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)
+    f = nb.FirFilter(taps, D)
+    ref = host(f.work(dx)[0])
+    segs = 8
+    L = n // segs
+    parts = []
+    for g in range(segs):
+        halo = None if g == 0 else dx[g * L - (T - 1):g * L]
+        parts.append(host(f.work_segment(dx[g * L:(g + 1) * L], halo)))
+    assert np.array_equal(np.concatenate(parts), ref), "time-segment sharding must equal one stream"
+
+
+def test_fir_fused_multiply_const(cuda):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(9)
+    x = cplx(rng, 50000)
+    taps = (rng.uniform(-1, 1, 100) / 100).astype(np.float32)
+    k = 0.5 - 0.25j
+    dx = dev(cuda, x)
+    a = nb.multiply_const(nb.FirFilter(taps, 4).work(dx)[0], k)
+    b = nb.FirFilter(taps, 4, multiply_const=k).work(dx)[0]
+    assert cuda.equal(a, b), "fused epilogue must equal the two-block chain bit for bit"
+
+
+def test_fir_config1_size_linearity(cuda):
+    """BASELINE config 1 size (16M samples, 64 taps): linearity + spot check vs the oracle."""
+    import newsched_b200 as nb
+    n = 1 << 24
+    g = cuda.Generator(device="cuda").manual_seed(1)
+    x1 = cuda.view_as_complex(cuda.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    x2 = cuda.view_as_complex(cuda.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    rng = np.random.default_rng(1)
+    taps = (rng.uniform(-1, 1, 64) / 64).astype(np.float32)
+    y1 = nb.FirFilter(taps).work(x1)[0]
+    y2 = nb.FirFilter(taps).work(x2)[0]
+    y12 = nb.FirFilter(taps).work(x1 + x2)[0]
+    err = (y12 - (y1 + y2)).abs().pow(2).mean().sqrt() / y12.abs().pow(2).mean().sqrt()
+    assert float(err) < TOL_RMS
+    for s in (0, 5_000_000, n - 4096):
+        seg = host(x1[max(s - 63, 0):s + 4096])
+        ref = o.fir(seg, taps, 1)[(63 if s else 0):]
+        assert o.rel_rms(host(y1[s:s + 4096]), ref) < TOL_RMS
+
+
+# ------------------------------------------------------------------------------- FFT
+@pytest.mark.parametrize("key,fwd,shift", [("fft_fwd", True, False), ("fft_fwd_shift", True, True),
+                                           ("fft_rev", False, False), ("fft_rev_shift", False, True)])
+def test_fft4096_golden(cuda, golden, key, fwd, shift):
+    import newsched_b200 as nb
+    x, w = golden["fft_x"], golden["bh4096"].astype(np.float32)
+    y = host(nb.FFT(4096, fwd, w, shift).work(dev(cuda, x)))
+    for v in range(2):
+        assert o.rel_rms(y[v * 4096:(v + 1) * 4096], golden[key][v * 4096:(v + 1) * 4096]) < TOL_RMS
+
+
+@pytest.mark.parametrize("N", [8, 16, 64, 256, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("fwd", [True, False])
+def test_fft_matches_oracle(cuda, N, fwd):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(N)
+    nv = 37 if N <= 1024 else 5
+    x = cplx(rng, nv * N)
+    w = rng.uniform(0.1, 1, N).astype(np.float32)
+    for shift in (False, True):
+        y = host(nb.FFT(N, fwd, w, shift).work(dev(cuda, x)))
+        ref = o.fft(x, N, fwd, w, shift)
+        for v in range(nv):
+            assert o.rel_rms(y[v * N:(v + 1) * N], ref[v * N:(v + 1) * N]) < TOL_RMS
+    y = host(nb.FFT(N, fwd).work(dev(cuda, x)))      # no window
+    assert o.rel_rms(y, o.fft(x, N, fwd)) < TOL_RMS
+
+
+def test_fft_impulse_tone_exact_structure(cuda):
+    import newsched_b200 as nb
+    N = 4096
+    imp = np.zeros(N, np.complex64)
+    imp[0] = 1
+    y = host(nb.FFT(N).work(dev(cuda, imp)))
+    assert np.abs(y - 1).max() < 1e-6                 # flat spectrum
+    k0 = 1234
+    tone = np.exp(2j * np.pi * k0 * np.arange(N) / N).astype(np.complex64)
+    y = host(nb.FFT(N).work(dev(cuda, tone)))
+    assert int(np.argmax(np.abs(y))) == k0            # bin index exact
+    ys = host(nb.FFT(N, shift=True).work(dev(cuda, tone)))
+    assert int(np.argmax(np.abs(ys))) == (k0 + N // 2) % N   # DC lands on N/2
+
+
+@pytest.mark.parametrize("N", [64, 4096])
+def test_fft_mag_fused_and_premultiply(cuda, golden, N):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(N + 1)
+    x = cplx(rng, 9 * N)
+    w = o.window_blackmanharris(N)
+    dx = dev(cuda, x)
+    ref = o.fft(x, N, True, w)
+    m = host(nb.FFT(N, True, w, output=nb.OUT_MAG).work(dx))
+    assert o.rel_rms(m, np.abs(ref.astype(np.complex128))) < TOL_RMS
+    m2 = host(nb.FFT(N, True, w, output=nb.OUT_MAG_SQUARED).work(dx))
+    assert o.rel_rms(m2, np.abs(ref.astype(np.complex128)) ** 2) < 2 * TOL_RMS
+    k = 0.5 - 0.25j
+    y = host(nb.FFT(N, True, w, pre_multiply_const=k).work(dx))
+    ref2 = o.fft(o.multiply_const(x, k), N, True, w)
+    assert o.rel_rms(y, ref2) < TOL_RMS
+
+
+def test_fft_config2_size_roundtrip(cuda):
+    """BASELINE config 2 size (1 GiB = 32768 x 4096): reverse(forward(x)) == N x, and Parseval."""
+    import newsched_b200 as nb
+    N, nv = 4096, 32768
+    g = cuda.Generator(device="cuda").manual_seed(2)
+    x = cuda.view_as_complex(cuda.rand(nv * N, 2, device="cuda", generator=g) * 2 - 1)
+    X = nb.FFT(N, True).work(x)
+    e_t = x[: 64 * N].abs().pow(2).sum().double()
+    e_f = X[: 64 * N].abs().pow(2).sum().double() / N
+    assert abs(float(e_t / e_f) - 1) < 1e-5
+    xr = nb.FFT(N, False).work(X)
+    err = (xr / N - x).abs().pow(2).mean().sqrt() / x.abs().pow(2).mean().sqrt()
+    assert float(err) < TOL_RMS
+    # last vector against the oracle (tail handling at full size)
+    ref = o.fft(host(x[-N:]), N)
+    assert o.rel_rms(host(X[-N:]), ref) < TOL_RMS
+
+
+# ------------------------------------------------------------------------ channelizer
+@pytest.mark.parametrize("name", ["pfb_a", "pfb_b"])
+def test_pfb_golden(cuda, golden, name):
+    import newsched_b200 as nb
+    taps, x, M = golden[name + "_taps"], golden[name + "_x"], int(golden[name + "_M"][0])
+    y, nc = nb.PfbChannelizer(taps, M).work(dev(cuda, x))
+    assert nc == x.size
+    assert o.rel_rms(host(y), golden[name + "_y64"]) < TOL_RMS
+
+
+@pytest.mark.parametrize("M,P", [(64, 16), (64, 3), (64, 32), (16, 8), (256, 4), (4, 7)])
+def test_pfb_matches_oracle_and_streams(cuda, M, P):
+    import scipy.signal as sig
+    import newsched_b200 as nb
+    rng = np.random.default_rng(M + P)
+    taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
+    x = cplx(rng, M * 333 + 5)
+    dx = dev(cuda, x)
+    ref = o.pfb_channelizer(x, taps, M)
+    y, nc = nb.PfbChannelizer(taps, M).work(dx)
+    assert nc == M * 333 and o.rel_rms(host(y), ref) < TOL_RMS
+    ch = nb.PfbChannelizer(taps, M)
+    outs, pos = [], 0
+    for n_fr in (1, 2, 64, 100, 166):
+        yy, c = ch.work(dx[pos:pos + n_fr * M])
+        outs.append(host(yy))
+        pos += c
+    assert np.array_equal(np.concatenate(outs), host(y)), "chunked channelizer != one-shot"
+    # channel slice == the same columns of the full output
+    part, _ = nb.PfbChannelizer(taps, M, channel_begin=M // 4, channel_count=M // 2).work(dx)
+    assert np.array_equal(host(part), host(y)[:, M // 4:M // 4 + M // 2])
+
+
+def test_pfb_tone(cuda):
+    import scipy.signal as sig
+    import newsched_b200 as nb
+    M, P, c0 = 64, 16, 5
+    taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
+    x = np.exp(2j * np.pi * c0 / M * np.arange(M * 300)).astype(np.complex64)
+    y = host(nb.PfbChannelizer(taps, M).work(dev(cuda, x))[0])
+    p = (np.abs(y[P:]) ** 2).mean(axis=0)
+    assert int(np.argmax(p)) == c0 and p[c0] > 1e3 * np.delete(p, c0).max()
+
+
+# ------------------------------------------------------------------------ ring / chain
+def test_ring_double_mapping(cuda):
+    import newsched_b200 as nb
+    ring = nb.DeviceRing(1 << 20)
+    assert ring.size >= 1 << 20 and ring.size % (1 << 16) == 0
+    n = ring.size
+    src = cuda.arange(n // 4, dtype=cuda.int32, device="cuda")
+    L = nb.lib()
+    # write through the low mapping, read the same bytes through the high mapping
+    nb._check(L.b200_copy(ring.base, src.data_ptr(), n, nb._stream()))
+    dst = cuda.empty_like(src)
+    nb._check(L.b200_copy(dst.data_ptr(), ring.base + n, n, nb._stream()))
+    assert cuda.equal(src, dst)
+    # a window that wraps: write starting at 3/4 n for n/2 bytes, read back via wrapped offsets
+    half = src[: n // 8]
+    nb._check(L.b200_copy(ring.base + 3 * n // 4, half.data_ptr(), n // 2, nb._stream()))
+    back = cuda.empty(n // 16, dtype=cuda.int32, device="cuda")
+    nb._check(L.b200_copy(back.data_ptr(), ring.base, n // 4, nb._stream()))
+    assert cuda.equal(back, half[n // 16:]), "bytes written past the end must appear at the start"
+
+
+def test_chain_device_and_host_equal_blocks(cuda):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(33)
+    N = 4096
+    n = N * 64 * 4
+    x = cplx(rng, n)
+    taps = (rng.uniform(-1, 1, 128) / 128).astype(np.float32)
+    w = o.window_blackmanharris(N)
+    k = 0.5 - 0.25j
+    dx = dev(cuda, x)
+    # config-3 style chain, block by block
+    a = nb.FirFilter(taps, 4).work(dx)[0]
+    a = nb.multiply_const(a, k)
+    a = nb.FFT(N, True, w).work(a)
+    # the same through the chain driver (unfused ops), chunked
+    ch = nb.Chain([nb.FirFilter(taps, 4), ("multiply_const_cc", k), nb.FFT(N, True, w)],
+                  in_item_bytes=8, chunk_items=N * 4 * 8)
+    out = cuda.empty(n // 4, dtype=cuda.complex64, device="cuda")
+    nbytes = ch.run(dx, out)
+    assert nbytes == out.numel() * 8 and cuda.equal(out, a)
+    # host-resident streaming: pinned in, pinned out
+    ch2 = nb.Chain([nb.FirFilter(taps, 4), ("multiply_const_cc", k), nb.FFT(N, True, w)],
+                   in_item_bytes=8, chunk_items=N * 4 * 8)
+    hx = cuda.from_numpy(x).pin_memory()
+    hy = cuda.empty(n // 4, dtype=cuda.complex64).pin_memory()
+    assert ch2.run_host(hx, hy) == hy.numel() * 8
+    assert cuda.equal(hy, a.cpu())
+    # fused form (FIR epilogue k, nothing else) stays within tolerance of the oracle
+    ref = o.fft(o.multiply_const(o.fir(x, taps, 4), k), N, True, w)
+    assert o.rel_rms(host(a), ref) < TOL_RMS
+    fused = nb.FFT(N, True, w, pre_multiply_const=k).work(nb.FirFilter(taps, 4).work(dx)[0])
+    assert o.rel_rms(host(fused), ref) < TOL_RMS
+
+
+def test_launch_counter_moves(cuda):
+    import newsched_b200 as nb
+    before = nb.launch_count()
+    nb.copy(cuda.zeros(1024, device="cuda"))
+    assert nb.launch_count() > before
