@@ -375,7 +375,7 @@ int b200_fir_geometry(const b200_fir* h, int* decimation, int* item_bytes)
 int b200_fir_run(b200_fir* h, const void* d_in, void* d_out, int64_t n_in_items,
                  int64_t* n_consumed, int64_t* n_produced, b200_stream_t s)
 {
-    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+    if (!h || n_in_items < 0 || (n_in_items > 0 && !d_in) || (n_in_items >= h->D && !d_out))
         return set_err(B200_ERR_ARG, "fir_run: bad argument");
     long long n_out = n_in_items / h->D;
     long long n_cons = n_out * h->D;
@@ -398,7 +398,7 @@ int b200_fir_run(b200_fir* h, const void* d_in, void* d_out, int64_t n_in_items,
 int b200_fir_run_segment(b200_fir* h, const void* d_halo, const void* d_in, void* d_out,
                          int64_t n_in_items, int64_t* n_produced, b200_stream_t s)
 {
-    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+    if (!h || n_in_items < 0 || (n_in_items > 0 && !d_in) || (n_in_items >= h->D && !d_out))
         return set_err(B200_ERR_ARG, "fir_run_segment: bad argument");
     long long n_out = n_in_items / h->D;
     int rc = fir_launch(h, (const float*)d_halo, d_in, d_out, n_in_items, n_out, cs(s));

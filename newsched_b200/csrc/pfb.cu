@@ -369,7 +369,7 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
 int b200_pfb_run(b200_pfb* h, const void* d_in, void* d_out, int64_t n_in_items,
                  int64_t* n_consumed, int64_t* n_produced_vectors, b200_stream_t s)
 {
-    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+    if (!h || n_in_items < 0 || (n_in_items > 0 && !d_in) || (n_in_items >= h->M && !d_out))
         return set_err(B200_ERR_ARG, "pfb_run: bad argument");
     long long n_frames = n_in_items / h->M;
     long long n_cons = n_frames * h->M;
@@ -392,7 +392,7 @@ int b200_pfb_run(b200_pfb* h, const void* d_in, void* d_out, int64_t n_in_items,
 int b200_pfb_run_segment(b200_pfb* h, const void* d_halo, const void* d_in, void* d_out,
                          int64_t n_in_items, int64_t* n_produced_vectors, b200_stream_t s)
 {
-    if (!h || n_in_items < 0 || (n_in_items > 0 && (!d_in || !d_out)))
+    if (!h || n_in_items < 0 || (n_in_items > 0 && !d_in) || (n_in_items >= h->M && !d_out))
         return set_err(B200_ERR_ARG, "pfb_run_segment: bad argument");
     long long n_frames = n_in_items / h->M;
     int rc = pfb_launch(h, d_halo, d_in, d_out, n_in_items, n_frames, cs(s));

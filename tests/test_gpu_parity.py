@@ -358,7 +358,7 @@ def test_pfb_matches_oracle_and_streams(cuda, M, P):
     dx = dev(cuda, x)
     ref = o.pfb_channelizer(x, taps, M)
     y, nc = nb.PfbChannelizer(taps, M).work(dx)
-    assert nc == M * 333 and o.rel_rms(host(y), ref) < TOL_RMS
+    assert nc == (x.size // M) * M and o.rel_rms(host(y), ref) < TOL_RMS
     ch = nb.PfbChannelizer(taps, M)
     outs, pos = [], 0
     for n_fr in (1, 2, 64, 100, 166):
