@@ -1,0 +1,330 @@
+// gnuradio/schedulers/mt/scheduler_mt.hpp -- thread-per-block(-group) scheduler.
+//
+// Host harness with the API and the per-iteration contract of the reference `mt` scheduler
+// (schedulers/mt/include/gnuradio/schedulers/mt/scheduler_mt.hpp:11-75, lib/scheduler_mt.cpp:24-84,
+// lib/thread_wrapper.cpp:77-191, lib/graph_executor.cpp:7-222, lib/buffer_management.cpp:8-148):
+//   * one buffer per edge: the edge's custom factory if set, else the scheduler default
+//     (vmcirc), num_items = 2 * fixed_buf_size / itemsize (buffer_management.cpp:117);
+//   * one std::thread per block group, then per remaining block;
+//   * per iteration and block: read_info on every input (blocked if < 1 item), min write_info
+//     over all buffers of every output port (blocked if < 1), do_work(), then post_read /
+//     fan-out copy_items / post_write and neighbour notification, tag propagation per policy.
+// It exists because the reference runtime cannot be compiled in this image; it
+// is a caller of the hot path, not part of it.  Two deliberate differences, both called out in
+// SURVEY.md 7.3 as defects of the reference:
+//   * end of stream is a real drain: WORK_DONE marks the block's output edges writer_done, and
+//     a block finishes once its inputs are exhausted and their writers are done (the reference
+//     sleeps 100 ms and drops what is in flight, flowgraph_monitor.cpp:27);
+//     and in the other direction a finished consumer marks its input edges reader_done so an
+//     endless source upstream (null_source -> head) stops;
+//   * a work() call that neither consumes nor produces counts as blocked instead of spinning.
+#pragma once
+#include <gnuradio/scheduler.hpp>
+#include <gnuradio/vmcircbuf.hpp>
+
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <thread>
+
+namespace gr {
+namespace schedulers {
+
+class buffer_manager
+{
+    std::map<edge*, buffer_sptr> _edge_buf;
+    std::map<port_base*, buffer_sptr> _in_buf;
+    std::map<port_base*, std::vector<buffer_sptr>> _out_bufs;
+    int _fixed_buf_size;
+
+public:
+    typedef std::shared_ptr<buffer_manager> sptr;
+    explicit buffer_manager(int fixed_buf_size) : _fixed_buf_size(fixed_buf_size) {}
+    void initialize_buffers(flat_graph_sptr fg, buffer_factory_function def_factory,
+                            std::shared_ptr<buffer_properties> def_props)
+    {
+        for (auto& e : fg->edges()) {
+            size_t itemsize = e->itemsize();
+            size_t num_items = std::max<size_t>(2, 2 * (size_t)_fixed_buf_size / itemsize);
+            buffer_sptr b = e->has_custom_buffer() ? e->buffer_factory()(num_items, itemsize, e->buf_properties())
+                                                   : def_factory(num_items, itemsize, def_props);
+            b->set_name(e->identifier());
+            _edge_buf[e.get()] = b;
+            _in_buf[e->dst().port().get()] = b;
+            _out_bufs[e->src().port().get()].push_back(b);
+        }
+    }
+    buffer_sptr get_input_buffer(port_sptr p)
+    {
+        auto it = _in_buf.find(p.get());
+        return it == _in_buf.end() ? nullptr : it->second;
+    }
+    std::vector<buffer_sptr>& get_output_buffers(port_sptr p) { return _out_bufs[p.get()]; }
+};
+
+enum class executor_iteration_status { READY, BLKD_IN, BLKD_OUT, DONE };
+
+class thread_wrapper : public neighbor_interface
+{
+    std::vector<block_sptr> _blocks;
+    std::vector<bool> _finished;
+    buffer_manager::sptr _bufman;
+    std::thread _thread;
+    std::mutex _m;
+    std::condition_variable _cv;
+    bool _notified = false;
+    std::atomic<bool> _stop{ false }, _started{ false };
+
+    void finish_block(size_t bi)
+    {
+        _finished[bi] = true;
+        auto& b = _blocks[bi];
+        for (auto& p : b->output_stream_ports())
+            for (auto& buf : _bufman->get_output_buffers(p))
+                buf->set_writer_done();
+        for (auto& p : b->input_stream_ports())
+            if (auto buf = _bufman->get_input_buffer(p))
+                buf->set_reader_done();
+        for (auto& p : b->output_stream_ports())
+            p->notify_connected_ports(std::make_shared<scheduler_action>(scheduler_action_t::NOTIFY_INPUT));
+        for (auto& p : b->input_stream_ports())
+            p->notify_connected_ports(std::make_shared<scheduler_action>(scheduler_action_t::NOTIFY_OUTPUT));
+        b->done();
+    }
+
+    // one block, one iteration: graph_executor.cpp:17-218
+    executor_iteration_status run_block(size_t bi)
+    {
+        auto& b = _blocks[bi];
+        std::vector<block_work_input> work_input;
+        std::vector<block_work_output> work_output;
+        auto in_ports = b->input_stream_ports();
+        auto out_ports = b->output_stream_ports();
+
+        bool blocked = false, exhausted = false, all_upstream_done = !in_ports.empty();
+        for (auto& p : in_ports) {
+            auto buf = _bufman->get_input_buffer(p);
+            if (!buf)
+                throw std::runtime_error("unconnected input port on " + b->alias());
+            // sample the flag BEFORE read_info: the writer posts its last items, then sets it
+            bool wd = buf->writer_done();
+            buffer_info_t ri;
+            buf->read_info(ri);
+            if (ri.n_items < 1) {
+                if (wd)
+                    exhausted = true; // nothing left and nothing more will come
+                else
+                    blocked = true;
+            }
+            if (!wd)
+                all_upstream_done = false;
+            work_input.emplace_back(ri.n_items, buf);
+        }
+        if (blocked)
+            return executor_iteration_status::BLKD_IN;
+        if (exhausted) {
+            finish_block(bi);
+            return executor_iteration_status::DONE;
+        }
+        // nobody downstream is listening any more (e.g. a head block finished): stop producing
+        for (auto& p : out_ports) {
+            auto& bufs = _bufman->get_output_buffers(p);
+            bool all_gone = !bufs.empty();
+            for (auto& buf : bufs)
+                all_gone &= buf->reader_done();
+            if (all_gone) {
+                finish_block(bi);
+                return executor_iteration_status::DONE;
+            }
+        }
+        for (auto& p : out_ports) {
+            int space = std::numeric_limits<int>::max();
+            buffer_sptr first = nullptr;
+            for (auto& buf : _bufman->get_output_buffers(p)) {
+                buffer_info_t wi;
+                buf->write_info(wi);
+                space = std::min(space, wi.n_items);
+                if (!first)
+                    first = buf;
+            }
+            if (!first)
+                throw std::runtime_error("unconnected output port on " + b->alias());
+            if (space < 1)
+                return executor_iteration_status::BLKD_OUT;
+            work_output.emplace_back(space, first);
+        }
+
+        work_return_code_t ret = b->do_work(work_input, work_output);
+        if (ret != work_return_code_t::WORK_OK && ret != work_return_code_t::WORK_DONE)
+            throw std::runtime_error("block " + b->alias() + " returned an error from work()");
+
+        bool progress = false;
+        for (size_t i = 0; i < in_ports.size(); i++) {
+            auto& w = work_input[i];
+            int nc = std::max(0, w.n_consumed);
+            if (!w.buffer->tags().empty()) {
+                auto pol = b->tag_propagation_policy();
+                for (size_t o = 0; o < out_ports.size(); o++)
+                    if (pol == tag_propagation_policy_t::TPP_ALL_TO_ALL ||
+                        (pol == tag_propagation_policy_t::TPP_ONE_TO_ONE && o == i))
+                        for (auto& ob : _bufman->get_output_buffers(out_ports[o]))
+                            ob->propagate_tags(w.buffer, nc);
+                w.buffer->prune_tags(nc);
+            }
+            if (nc > 0) {
+                w.buffer->post_read(nc);
+                progress = true;
+                in_ports[i]->notify_connected_ports(
+                    std::make_shared<scheduler_action>(scheduler_action_t::NOTIFY_OUTPUT));
+            }
+        }
+        for (size_t o = 0; o < out_ports.size(); o++) {
+            int np = std::max(0, work_output[o].n_produced);
+            if (np > 0) {
+                auto& bufs = _bufman->get_output_buffers(out_ports[o]);
+                for (size_t j = 1; j < bufs.size(); j++)
+                    bufs[j]->copy_items(bufs[0], np);
+                for (auto& buf : bufs)
+                    buf->post_write(np);
+                progress = true;
+                out_ports[o]->notify_connected_ports(
+                    std::make_shared<scheduler_action>(scheduler_action_t::NOTIFY_INPUT));
+            }
+        }
+        if (ret == work_return_code_t::WORK_DONE) {
+            finish_block(bi);
+            return executor_iteration_status::DONE;
+        }
+        if (!progress) {
+            // 0/0 work: blocked, unless nothing more can ever arrive
+            if (all_upstream_done) {
+                finish_block(bi);
+                return executor_iteration_status::DONE;
+            }
+            return executor_iteration_status::BLKD_IN;
+        }
+        return executor_iteration_status::READY;
+    }
+
+    void thread_body()
+    {
+        while (!_stop.load()) {
+            bool any_ready = false, all_finished = true;
+            for (size_t bi = 0; bi < _blocks.size(); bi++) {
+                if (_finished[bi])
+                    continue;
+                auto st = run_block(bi);
+                if (st == executor_iteration_status::READY)
+                    any_ready = true;
+                if (!_finished[bi])
+                    all_finished = false;
+            }
+            if (all_finished)
+                break;
+            if (!any_ready) {
+                std::unique_lock<std::mutex> lk(_m);
+                _cv.wait_for(lk, std::chrono::milliseconds(2), [this] { return _notified || _stop.load(); });
+                _notified = false;
+            }
+        }
+    }
+
+public:
+    typedef std::shared_ptr<thread_wrapper> sptr;
+    thread_wrapper(std::vector<block_sptr> blocks, buffer_manager::sptr bufman)
+        : _blocks(std::move(blocks)), _finished(_blocks.size(), false), _bufman(std::move(bufman))
+    {
+    }
+    void push_message(scheduler_message_sptr) override
+    {
+        {
+            std::lock_guard<std::mutex> lk(_m);
+            _notified = true;
+        }
+        _cv.notify_one();
+    }
+    void start()
+    {
+        _started = true;
+        _thread = std::thread([this] { thread_body(); });
+    }
+    void stop()
+    {
+        _stop = true;
+        push_message(nullptr);
+        for (auto& b : _blocks)
+            b->stop();
+    }
+    void wait()
+    {
+        if (_thread.joinable())
+            _thread.join();
+    }
+};
+
+class scheduler_mt : public scheduler
+{
+    const int s_fixed_buf_size;
+    std::vector<std::vector<block_sptr>> _block_groups;
+    std::vector<thread_wrapper::sptr> _threads;
+    buffer_manager::sptr _bufman;
+
+public:
+    typedef std::shared_ptr<scheduler_mt> sptr;
+    static sptr make(const std::string name = "multi_threaded", const unsigned int fixed_buf_size = 32768)
+    {
+        return std::make_shared<scheduler_mt>(name, fixed_buf_size);
+    }
+    scheduler_mt(const std::string name = "multi_threaded", const unsigned int fixed_buf_size = 32768)
+        : scheduler(name), s_fixed_buf_size((int)fixed_buf_size)
+    {
+        _default_buf_factory = vmcirc_buffer::make;
+        _default_buf_properties = vmcirc_buffer_properties::make(vmcirc_buffer_type::AUTO);
+    }
+    void add_block_group(const std::vector<block_sptr>& blocks, const std::string& = "",
+                         const std::vector<unsigned int>& = {})
+    {
+        _block_groups.push_back(blocks);
+    }
+    buffer_manager::sptr buffers() { return _bufman; }
+
+    void initialize(flat_graph_sptr fg) override
+    {
+        _bufman = std::make_shared<buffer_manager>(s_fixed_buf_size);
+        _bufman->initialize_buffers(fg, _default_buf_factory, _default_buf_properties);
+        auto blocks = fg->calc_used_blocks();
+        std::vector<block_sptr> grouped;
+        auto make_thread = [&](const std::vector<block_sptr>& grp) {
+            auto t = std::make_shared<thread_wrapper>(grp, _bufman);
+            for (auto& b : grp)
+                for (auto& p : b->all_ports())
+                    p->set_parent_intf(t);
+            _threads.push_back(t);
+        };
+        for (auto& grp : _block_groups) {
+            make_thread(grp);
+            grouped.insert(grouped.end(), grp.begin(), grp.end());
+        }
+        for (auto& b : blocks)
+            if (std::find(grouped.begin(), grouped.end(), b) == grouped.end())
+                make_thread({ b });
+    }
+    void start() override
+    {
+        for (auto& t : _threads)
+            t->start();
+    }
+    void stop() override
+    {
+        for (auto& t : _threads)
+            t->stop();
+    }
+    void wait() override
+    {
+        for (auto& t : _threads)
+            t->wait();
+    }
+};
+
+} // namespace schedulers
+} // namespace gr
