@@ -59,6 +59,8 @@ B200_API int64_t b200_launch_count(void);        /* kernels launched by this lib
 /* measurement helper: runs a pure-FFMA kernel (iters x 256 FFMA per thread, 8 CTAs/SM) and
  * reports the FP32 FMA rate in TFLOP/s -- the denominator of the FP32-bound FIR roofline. */
 B200_API int b200_measure_fp32_tflops(int iters, float* tflops, float* ms);
+/* same probe written with the packed fma.rn.f32x2 (FFMA2) form that the FIR kernel uses */
+B200_API int b200_measure_fp32x2_tflops(int iters, float* tflops, float* ms);
 
 /* ---- memory / stream / event plumbing (so hosts need no CUDA headers) ------------ */
 B200_API int b200_malloc(void** dptr, size_t bytes);

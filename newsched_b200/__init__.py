@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_device_synchronize": (_I, []),
     "b200_launch_count": (_I64, []),
     "b200_measure_fp32_tflops": (_I, [_I, C.POINTER(_F), C.POINTER(_F)]),
+    "b200_measure_fp32x2_tflops": (_I, [_I, C.POINTER(_F), C.POINTER(_F)]),
     "b200_malloc": (_I, [C.POINTER(_V), _SZ]),
     "b200_free": (_I, [_V]),
     "b200_host_alloc": (_I, [C.POINTER(_V), _SZ]),
@@ -163,6 +164,12 @@ def launch_count() -> int:
 def measure_fp32_tflops(iters: int = 4096):
     t, ms = C.c_float(), C.c_float()
     _check(lib().b200_measure_fp32_tflops(int(iters), C.byref(t), C.byref(ms)))
+    return float(t.value), float(ms.value)
+
+
+def measure_fp32x2_tflops(iters: int = 4096):
+    t, ms = C.c_float(), C.c_float()
+    _check(lib().b200_measure_fp32x2_tflops(int(iters), C.byref(t), C.byref(ms)))
     return float(t.value), float(ms.value)
 
 

@@ -23,6 +23,7 @@
 // bank-conflict free.
 // Other N (8..8192): generic radix-2 shared-memory Stockham kernel.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -179,6 +180,104 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// Same three passes, but the NEXT vector is prefetched by the TMA engine (1-D bulk copy, 32 KiB,
+// completion on an mbarrier) into a dedicated shared buffer while passes 2-3 of the current one
+// run: global-load latency is off the critical path and costs no registers or issue slots.
+// smem: sIn 32 KiB | sA 16*257*8 B | sT2 2 KiB | mbarrier  (~67 KiB -> 2-3 CTAs/SM).
+constexpr size_t F4K_TMA_SMEM = 4096 * 8 + 16 * F4K_STRIDE * 8 + 256 * 8 + 16;
+
+template <bool FWD, int OUT>
+__global__ void __launch_bounds__(256, 2)
+    fft4096_tma_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec,
+                       const float* __restrict__ weff, const float2* __restrict__ tw1,
+                       const float2* __restrict__ tw2)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sIn = reinterpret_cast<float2*>(smem_raw);
+    float2* sA = sIn + 4096;
+    float2* sT2 = sA + 16 * F4K_STRIDE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + 256);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    float wreg[16];
+    float2 t1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        wreg[i] = __ldg(weff + i * 256 + tid);
+        t1[i] = __ldg(tw1 + i * 256 + tid);
+    }
+    sT2[tid] = __ldg(tw2 + tid);
+    __syncthreads();
+    long long vec = blockIdx.x;
+    if (tid == 0 && vec < n_vec) {
+        mbar_arrive_expect_tx(bar, 4096 * 8);
+        bulk_copy_g2s(sIn, in + vec * 4096, 4096 * 8, bar);
+    }
+    uint32_t phase = 0;
+    for (; vec < n_vec; vec += gridDim.x) {
+        float2 v[16];
+        mbar_wait(bar, phase);
+        phase ^= 1;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            v[i] = sIn[i * 256 + tid];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            v[i].x *= wreg[i];
+            v[i].y *= wreg[i];
+        }
+        dft16<FWD>(v);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++)
+            sA[k0 * F4K_STRIDE + tid] = cmul(v[pos16(k0)], t1[k0]);
+        __syncthreads(); // sA complete; every thread is done reading sIn
+        if (tid == 0 && vec + gridDim.x < n_vec) {
+            mbar_arrive_expect_tx(bar, 4096 * 8);
+            bulk_copy_g2s(sIn, in + (vec + gridDim.x) * 4096, 4096 * 8, bar);
+        }
+        {
+            const int k0 = tid >> 4, n0 = tid & 15;
+            float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i * 16];
+            dft16<FWD>(v);
+            row[0] = v[pos16(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++)
+                row[k1 * 16] = cmul(v[pos16(k1)], sT2[k1 * 16 + n0]);
+        }
+        __syncthreads();
+        {
+            const int k0 = tid & 15, k1 = tid >> 4;
+            const float2* row = sA + k0 * F4K_STRIDE + k1 * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i];
+            dft16<FWD>(v);
+            if (OUT == B200_FFT_OUT_COMPLEX) {
+                float2* y = reinterpret_cast<float2*>(out) + vec * 4096;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++)
+                    __stcs(y + k2 * 256 + tid, v[pos16(k2)]);
+            } else {
+                float* y = reinterpret_cast<float*>(out) + vec * 4096;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    float2 z = v[pos16(k2)];
+                    float p = fmaf(z.x, z.x, z.y * z.y);
+                    __stcs(y + k2 * 256 + tid, OUT == B200_FFT_OUT_MAG ? sqrt_approx(p) : p);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- generic power-of-two radix-2 Stockham (N = 8 .. 8192) ----------------------------------
 template <bool FWD, int OUT>
 __global__ void __launch_bounds__(512)
@@ -257,6 +356,7 @@ struct b200_fft {
     float2* d_tw = nullptr;  // generic: N/2
     int vpb = 1;
     int grid_4k = 296;
+    int use_tma = 1; // TMA-prefetch kernel for N = 4096 when the input is 16-byte aligned
 };
 
 template <bool FWD, int OUT>
@@ -264,8 +364,12 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
 {
     if (h->N == 4096) {
         long long g = n_vec < h->grid_4k ? n_vec : h->grid_4k;
-        B200_LAUNCH((fft4096_kernel<FWD, OUT>), (unsigned)g, 256, 0, s, (const float2*)d_in, d_out,
-                    n_vec, h->d_weff, h->d_tw1, h->d_tw2);
+        if (h->use_tma && (uintptr_t)d_in % 16 == 0)
+            B200_LAUNCH((fft4096_tma_kernel<FWD, OUT>), (unsigned)g, 256, F4K_TMA_SMEM, s,
+                        (const float2*)d_in, d_out, n_vec, h->d_weff, h->d_tw1, h->d_tw2);
+        else
+            B200_LAUNCH((fft4096_kernel<FWD, OUT>), (unsigned)g, 256, 0, s, (const float2*)d_in, d_out,
+                        n_vec, h->d_weff, h->d_tw1, h->d_tw2);
     } else {
         long long blocks = (n_vec + h->vpb - 1) / h->vpb;
         if (blocks > 0x7fffffffLL)
@@ -291,6 +395,13 @@ static int fft_run_o(b200_fft* h, const void* d_in, void* d_out, long long n_vec
     default:
         return fft_run_t<FWD, B200_FFT_OUT_MAG_SQUARED>(h, d_in, d_out, n_vec, s);
     }
+}
+
+template <bool FWD, int OUT>
+static cudaError_t fft_tma_attr()
+{
+    return cudaFuncSetAttribute(fft4096_tma_kernel<FWD, OUT>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F4K_TMA_SMEM);
 }
 
 template <bool FWD, int OUT>
@@ -393,6 +504,16 @@ int b200_fft_create(const b200_fft_params* p, b200_fft** out)
         FFT_CUDA(cudaMalloc(&h->d_tw2, sizeof(float2) * t2.size()));
         FFT_CUDA(cudaMemcpy(h->d_tw2, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
         h->grid_4k = 2 * sm_count();
+        if (const char* e = getenv("B200_FFT_TMA"))
+            h->use_tma = atoi(e);
+        if (const char* e = getenv("B200_FFT_GRID_PER_SM"))
+            h->grid_4k = atoi(e) * sm_count();
+        FFT_CUDA((fft_tma_attr<true, 0>()));
+        FFT_CUDA((fft_tma_attr<true, 1>()));
+        FFT_CUDA((fft_tma_attr<true, 2>()));
+        FFT_CUDA((fft_tma_attr<false, 0>()));
+        FFT_CUDA((fft_tma_attr<false, 1>()));
+        FFT_CUDA((fft_tma_attr<false, 2>()));
     } else {
         std::vector<float2> tw(N / 2);
         for (int j = 0; j < N / 2; j++) {

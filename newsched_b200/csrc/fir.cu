@@ -20,6 +20,9 @@
 // History (the T-1 samples before the next input item) lives in a ping-pong pair of small
 // device buffers owned by the handle; nothing is re-read from the host and the caller may
 // chunk the stream arbitrarily.
+#include <cuda.h>
+
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -30,11 +33,29 @@ constexpr int FIR_NT = 128;  // threads per CTA
 constexpr int FIR_ACC = 32;  // fp32 accumulators per thread
 constexpr int FIR_RING = 64; // register window (floats)
 
-__host__ __device__ __forceinline__ int padf(int f) { return f + ((f >> 5) << 2); }
+// Shared-memory tile layout = what TMA SWIZZLE_128B produces: rows of 32 floats (128 B), the
+// 16-byte chunk c of row r stored at chunk position c ^ (r & 7).  Thread t's window starts at
+// row t, so the 8 lanes of a quarter-warp hit 8 different chunk positions: the per-thread
+// 128 B-strided LDS.128 reads are bank-conflict free without padding.
+__host__ __device__ __forceinline__ int swz(int f)
+{
+    const int row = f >> 5, c = (f >> 2) & 7;
+    return (row << 5) | ((c ^ (row & 7)) << 2) | (f & 3);
+}
 
 struct fir_epilogue {
     int fuse;
     float kre, kim;
+};
+
+struct fir_geom {
+    int Tm1, D, TQ;
+    int plane_rows;   // rows (of 32 floats) per phase plane
+    int box_rows;     // rows per TMA box
+    int n_boxes;      // TMA boxes per tile (D == 1 only)
+    int tma_ok;       // tensor map valid (input 16-byte aligned, enough full rows)
+    long long full_rows; // rows of the input that are completely inside [0, n_in)
+    long long n_in, n_out;
 };
 
 // x value at global sample index g (may be negative -> history, or >= n_in -> 0)
@@ -55,6 +76,7 @@ __device__ __forceinline__ void fir_fetch(const float* __restrict__ x, const flo
         v[1] = t.y;
     } else {
         v[0] = src ? __ldg(src) : 0.f;
+        v[1] = 0.f;
     }
 }
 
@@ -69,75 +91,129 @@ __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)
         const float hv[4] = { h4.x, h4.y, h4.z, h4.w };
 #pragma unroll
         for (int u = 0; u < 4; u++) {
+            if (VEC == 2) {
+                // complex sample x real tap = one packed FFMA2 (fma.rn.f32x2, tap broadcast):
+                // half the issue slots of two FFMAs, so staging / epilogue instructions of the
+                // other resident warps issue underneath the FMA pipe
+                const float2 h2 = make_float2(hv[u], hv[u]);
 #pragma unroll
-            for (int l = 0; l < FIR_ACC; l++)
-                acc[l] = fmaf(hv[u], W[(OFF + (q4 + u) * VEC + l) % FIR_RING], acc[l]);
+                for (int l = 0; l < FIR_ACC; l += 2) {
+                    const int i = (OFF + (q4 + u) * VEC + l) % FIR_RING;
+                    float2 a = __ffma2_rn(make_float2(W[i], W[i + 1]), h2, make_float2(acc[l], acc[l + 1]));
+                    acc[l] = a.x;
+                    acc[l + 1] = a.y;
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < FIR_ACC; l++)
+                    acc[l] = fmaf(hv[u], W[(OFF + (q4 + u) * VEC + l) % FIR_RING], acc[l]);
+            }
         }
     }
 }
 
+// 32 floats of row `row` of a swizzled plane into one half of the register ring
 template <int HALF>
-__device__ __forceinline__ void fir_load_half(float (&W)[FIR_RING], const float* __restrict__ p)
+__device__ __forceinline__ void fir_load_half(float (&W)[FIR_RING], const float* __restrict__ plane, int row)
 {
+    const float* rb = plane + (row << 5);
+    const int s = (row & 7) << 2;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
-        W[HALF * 32 + 4 * i + 0] = t.x;
-        W[HALF * 32 + 4 * i + 1] = t.y;
-        W[HALF * 32 + 4 * i + 2] = t.z;
-        W[HALF * 32 + 4 * i + 3] = t.w;
+    for (int j = 0; j < 8; j++) {
+        float4 t = *reinterpret_cast<const float4*>(rb + ((j << 2) ^ s));
+        W[HALF * 32 + 4 * j + 0] = t.x;
+        W[HALF * 32 + 4 * j + 1] = t.y;
+        W[HALF * 32 + 4 * j + 2] = t.z;
+        W[HALF * 32 + 4 * j + 3] = t.w;
     }
 }
 
-// smem: [taps D*TQ floats][planes D * plane_f floats]
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1,
+                                            uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Tile k produces outputs [k*MT - 1, (k+1)*MT - 1): the one-sample shift makes every thread's
+// window start on a 128-byte row of the input (rows are counted from the first input sample),
+// which is what lets interior tiles be staged by ONE TMA tensor copy (D == 1).
+// smem: [mbarrier 16 B][taps D*TQ floats][pad to 1024 B][D planes of plane_rows*32 floats]
 template <int VEC>
-__global__ void __launch_bounds__(FIR_NT, 3)
+__global__ void __launch_bounds__(FIR_NT, 5)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
-                      float* __restrict__ y, const float* __restrict__ taps_pp, int Tm1, int D,
-                      int TQ, int plane_f, long long n_in, long long n_out, fir_epilogue ep)
+                      float* __restrict__ y, const float* __restrict__ taps_pp,
+                      const __grid_constant__ CUtensorMap tmap, fir_geom gm, fir_epilogue ep)
 {
     constexpr int R = FIR_ACC / VEC;  // outputs per thread
     constexpr int CH = FIR_ACC / VEC; // taps per step
     constexpr int MT = FIR_NT * R;    // outputs per tile
-    extern __shared__ __align__(16) float smem[];
-    float* hs = smem;
-    float* planes = smem + D * TQ;
-
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* hs = reinterpret_cast<float*>(smem_raw + 16);
+    const int D = gm.D, TQ = gm.TQ;
+    float* planes;
+    {
+        uint32_t a = smem_u32(hs + D * TQ);
+        uint32_t aligned = (a + 1023u) & ~1023u;
+        planes = hs + D * TQ + (aligned - a) / 4;
+    }
+    const int plane_f = gm.plane_rows << 5;
     const int tid = threadIdx.x;
-    const long long M0 = (long long)blockIdx.x * MT;
-    const int PL = MT + TQ; // samples per plane
+    const long long B0 = (long long)blockIdx.x * MT - TQ; // x_p index of plane element 0
+    const long long O0 = (long long)blockIdx.x * MT - 1;  // first output of this tile
+    const int PLs = plane_f / VEC;                         // samples per plane
 
-    // ---- stage taps and the phase-deinterleaved input tile --------------------------
+    // interior tile of a D == 1 filter: one TMA tensor copy stages the whole window
+    const long long row0 = B0 * VEC / 32;
+    const bool use_tma = (D == 1) && gm.tma_ok && B0 >= 0 &&
+                         row0 + (long long)gm.box_rows * gm.n_boxes <= gm.full_rows;
+    if (use_tma && tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)(gm.box_rows * gm.n_boxes) * 128u);
+        for (int bx = 0; bx < gm.n_boxes; bx++)
+            tma_load_2d(planes + (size_t)bx * gm.box_rows * 32, &tmap, 0, (int)(row0 + (long long)bx * gm.box_rows),
+                        bar);
+    }
     for (int i = tid; i < D * TQ; i += FIR_NT)
         hs[i] = __ldg(taps_pp + i);
-    {
-        const long long g_lo = (M0 - TQ + 1) * D - (D - 1);
-        const int total = PL * D;
-        if (D == 1) {
-            for (int i = tid; i < total; i += FIR_NT) {
-                float v[2];
-                fir_fetch<VEC>(x, hist, Tm1, g_lo + i, n_in, v);
-                float* dst = planes + padf(i * VEC);
-                if (VEC == 2)
-                    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-                else
-                    dst[0] = v[0];
+    if (!use_tma) {
+        // manual staging (first / last tiles, decimating filters, unaligned input): coalesced
+        // loads, 8 independent loads in flight per thread, phase de-interleave on the way in
+        const long long g_lo = B0 * D - (D - 1);
+        const int total = PLs * D;
+        for (int i0 = tid; i0 < total; i0 += FIR_NT * 8) {
+            float v[8][2];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * FIR_NT;
+                if (i < total)
+                    fir_fetch<VEC>(x, hist, gm.Tm1, g_lo + i, gm.n_in, v[u]);
             }
-        } else {
-            for (int i = tid; i < total; i += FIR_NT) {
-                int e = i / D;
-                int p = D - 1 - (i - e * D);
-                float v[2];
-                fir_fetch<VEC>(x, hist, Tm1, g_lo + i, n_in, v);
-                float* dst = planes + p * plane_f + padf(e * VEC);
-                if (VEC == 2)
-                    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-                else
-                    dst[0] = v[0];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * FIR_NT;
+                if (i < total) {
+                    int e = i, p = 0;
+                    if (D != 1) {
+                        e = i / D;
+                        p = D - 1 - (i - e * D);
+                    }
+                    float* dst = planes + p * plane_f + swz(e * VEC);
+                    if (VEC == 2)
+                        *reinterpret_cast<float2*>(dst) = make_float2(v[u][0], v[u][1]);
+                    else
+                        dst[0] = v[u][0];
+                }
             }
         }
     }
     __syncthreads();
+    if (use_tma)
+        mbar_wait(bar, 0);
 
     // ---- register-blocked multiply-accumulate -----------------------------------------
     float acc[FIR_ACC];
@@ -147,32 +223,34 @@ __global__ void __launch_bounds__(FIR_NT, 3)
     float W[FIR_RING];
     const int nsteps = TQ / CH; // even by construction
     for (int p = 0; p < D; p++) {
-        const float* xp = planes + p * plane_f + 36 * tid;
+        const float* plane = planes + p * plane_f;
         const float* hp = hs + p * TQ;
-        fir_load_half<0>(W, xp);
+        fir_load_half<0>(W, plane, tid);
         for (int b = 0; b < nsteps; b += 2) {
-            fir_load_half<1>(W, xp + 36 * (b + 1));
+            fir_load_half<1>(W, plane, tid + b + 1);
             fir_step<VEC, CH, 0>(acc, W, hp + b * CH);
-            fir_load_half<0>(W, xp + 36 * (b + 2));
+            fir_load_half<0>(W, plane, tid + b + 2);
             fir_step<VEC, CH, 32>(acc, W, hp + (b + 1) * CH);
         }
     }
     __syncthreads();
 
-    // ---- outputs: registers -> shared (padded) -> coalesced global -----------------------
+    // ---- outputs: registers -> shared (swizzled row per thread) -> coalesced global ----------
     {
-        float* o = planes + 36 * tid;
+        float* rb = planes + (tid << 5);
+        const int s = (tid & 7) << 2;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            *reinterpret_cast<float4*>(o + 4 * i) =
-                make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        for (int j = 0; j < 8; j++)
+            *reinterpret_cast<float4*>(rb + ((j << 2) ^ s)) =
+                make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
     __syncthreads();
+#pragma unroll 4
     for (int i = tid; i < MT; i += FIR_NT) {
-        long long m = M0 + i;
-        if (m >= n_out)
-            break;
-        const float* src = planes + padf(i * VEC);
+        const long long m = O0 + i;
+        if (m < 0 || m >= gm.n_out)
+            continue;
+        const float* src = planes + swz(i * VEC);
         if (VEC == 2) {
             float2 v = *reinterpret_cast<const float2*>(src);
             if (ep.fuse)
@@ -236,8 +314,9 @@ using namespace b200;
 struct b200_fir {
     int T = 0, D = 1, vec = 2;
     int TQ = 0;      // taps per phase, padded
-    int plane_f = 0; // floats per phase plane in smem
+    int plane_rows = 0, box_rows = 0, n_boxes = 0; // smem plane geometry (rows of 128 B)
     size_t smem = 0;
+    int use_tma = 1;
     int algorithm = 1;
     fir_epilogue ep{ 0, 1.f, 0.f };
     float* d_taps_pp = nullptr; // [D][TQ] reversed per phase
@@ -246,6 +325,41 @@ struct b200_fir {
     int cur = 0;
     int device = 0;
 };
+
+// 2-D view of the input stream for TMA: rows of 32 floats (128 B), SWIZZLE_128B, box = box_rows
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled()
+{
+    static encode_tiled_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+static int fir_make_tmap(CUtensorMap* tmap, const void* d_in, long long full_rows, int box_rows)
+{
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc)
+        return set_err(B200_ERR_CUDA, "fir: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gdim[2] = { 32, (cuuint64_t)full_rows };
+    cuuint64_t gstride[1] = { 128 };
+    cuuint32_t box[2] = { 32, (cuuint32_t)box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(d_in), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_err(B200_ERR_CUDA, "fir: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return B200_OK;
+}
 
 static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* d_out,
                       long long n_in, long long n_out, cudaStream_t s)
@@ -256,15 +370,34 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
     float* y = (float*)d_out;
     if (h->algorithm == 1) {
         const int MT = FIR_NT * (FIR_ACC / h->vec);
-        long long tiles = (n_out + MT - 1) / MT;
+        long long tiles = (n_out + 1 + MT - 1) / MT; // tile k covers outputs [k*MT - 1, (k+1)*MT - 1)
         if (tiles > 0x7fffffffLL)
             return set_err(B200_ERR_ARG, "fir: too many items for one call");
+        fir_geom gm{};
+        gm.Tm1 = h->T - 1;
+        gm.D = h->D;
+        gm.TQ = h->TQ;
+        gm.plane_rows = h->plane_rows;
+        gm.box_rows = h->box_rows;
+        gm.n_boxes = h->n_boxes;
+        gm.n_in = n_in;
+        gm.n_out = n_out;
+        gm.full_rows = n_in * h->vec / 32;
+        gm.tma_ok = 0;
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        if (h->use_tma && h->D == 1 && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0) {
+            int rc = fir_make_tmap(&tmap, d_in, gm.full_rows, h->box_rows);
+            if (rc != B200_OK)
+                return rc;
+            gm.tma_ok = 1;
+        }
         if (h->vec == 2)
             B200_LAUNCH((fir_direct_kernel<2>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
-                        h->d_taps_pp, h->T - 1, h->D, h->TQ, h->plane_f, n_in, n_out, h->ep);
+                        h->d_taps_pp, tmap, gm, h->ep);
         else
             B200_LAUNCH((fir_direct_kernel<1>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
-                        h->d_taps_pp, h->T - 1, h->D, h->TQ, h->plane_f, n_in, n_out, h->ep);
+                        h->d_taps_pp, tmap, gm, h->ep);
     } else {
         long long blocks = (n_out + 255) / 256;
         if (h->vec == 2)
@@ -311,10 +444,16 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     const int MT = FIR_NT * (FIR_ACC / h->vec);
     int tq = (h->T + h->D - 1) / h->D;
     h->TQ = (tq + 2 * CH - 1) / (2 * CH) * (2 * CH);
-    int PL = MT + h->TQ;
-    h->plane_f = padf(PL * h->vec) + 8; // +8: keep consecutive planes off the same banks
-    h->plane_f = (h->plane_f + 3) / 4 * 4;
-    h->smem = sizeof(float) * ((size_t)h->D * h->TQ + (size_t)h->D * h->plane_f);
+    (void)MT;
+    {
+        int need = FIR_NT + h->TQ / CH; // rows per plane: one per thread + one per tap step
+        h->n_boxes = (need + 255) / 256;
+        h->box_rows = (need + h->n_boxes - 1) / h->n_boxes;
+        h->plane_rows = h->box_rows * h->n_boxes;
+    }
+    h->smem = 16 + sizeof(float) * ((size_t)h->D * h->TQ + (size_t)h->D * h->plane_rows * 32) + 1024;
+    if (const char* e = getenv("B200_FIR_TMA"))
+        h->use_tma = atoi(e);
     h->algorithm = 1;
     if (h->smem > 200 * 1024 || p->algorithm == 4)
         h->algorithm = 4; // naive global-memory fallback

