@@ -53,8 +53,10 @@ struct fir_geom {
     int plane_rows;   // rows (of 32 floats) per phase plane
     int box_rows;     // rows per TMA box
     int n_boxes;      // TMA boxes per tile (D == 1 only)
-    int tma_ok;       // tensor map valid (input 16-byte aligned, enough full rows)
-    long long full_rows; // rows of the input that are completely inside [0, n_in)
+    int tma_ok;       // input tensor map valid (input 16-byte aligned, enough full rows)
+    int tma_out_ok;   // output tensor map valid
+    long long full_rows;     // rows of the input that are completely inside [0, n_in)
+    long long full_out_rows; // rows of the output completely inside [0, n_out)
     long long n_in, n_out;
 };
 
@@ -80,7 +82,9 @@ __device__ __forceinline__ void fir_fetch(const float* __restrict__ x, const flo
     }
 }
 
-// One step of CH taps against the register ring.  OFF = ring offset (floats) of output 0.
+// One step of CH taps against the register ring.  OFF = ring offset (floats) of the thread's row;
+// tap q' of the step meets ring element (q'+1): the window is read from one sample early so that
+// BOTH the input window and the output tile start on 128-byte rows (TMA load and TMA store).
 template <int VEC, int CH, int OFF>
 __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)[FIR_RING],
                                          const float* __restrict__ hs)
@@ -98,7 +102,7 @@ __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)
                 const float2 h2 = make_float2(hv[u], hv[u]);
 #pragma unroll
                 for (int l = 0; l < FIR_ACC; l += 2) {
-                    const int i = (OFF + (q4 + u) * VEC + l) % FIR_RING;
+                    const int i = (OFF + (q4 + u + 1) * VEC + l) % FIR_RING;
                     float2 a = __ffma2_rn(make_float2(W[i], W[i + 1]), h2, make_float2(acc[l], acc[l + 1]));
                     acc[l] = a.x;
                     acc[l + 1] = a.y;
@@ -106,7 +110,7 @@ __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)
             } else {
 #pragma unroll
                 for (int l = 0; l < FIR_ACC; l++)
-                    acc[l] = fmaf(hv[u], W[(OFF + (q4 + u) * VEC + l) % FIR_RING], acc[l]);
+                    acc[l] = fmaf(hv[u], W[(OFF + (q4 + u + 1) * VEC + l) % FIR_RING], acc[l]);
             }
         }
     }
@@ -137,15 +141,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
                  : "memory");
 }
 
-// Tile k produces outputs [k*MT - 1, (k+1)*MT - 1): the one-sample shift makes every thread's
-// window start on a 128-byte row of the input (rows are counted from the first input sample),
-// which is what lets interior tiles be staged by ONE TMA tensor copy (D == 1).
+// Tile k produces outputs [k*MT, (k+1)*MT).  Plane element 0 is x_p[k*MT - TQ] (one sample before
+// the oldest sample the taps reach), so every thread's window and every thread's 128 B of outputs
+// start on a 128-byte row: interior tiles are staged by ONE TMA tensor load (D == 1) and written
+// back by ONE TMA tensor store.
 // smem: [mbarrier 16 B][taps D*TQ floats][pad to 1024 B][D planes of plane_rows*32 floats]
 template <int VEC>
 __global__ void __launch_bounds__(FIR_NT, 5)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
-                      const __grid_constant__ CUtensorMap tmap, fir_geom gm, fir_epilogue ep)
+                      const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
+                      fir_geom gm, fir_epilogue ep)
 {
     constexpr int R = FIR_ACC / VEC;  // outputs per thread
     constexpr int CH = FIR_ACC / VEC; // taps per step
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(FIR_NT, 5)
     const int plane_f = gm.plane_rows << 5;
     const int tid = threadIdx.x;
     const long long B0 = (long long)blockIdx.x * MT - TQ; // x_p index of plane element 0
-    const long long O0 = (long long)blockIdx.x * MT - 1;  // first output of this tile
+    const long long O0 = (long long)blockIdx.x * MT;      // first output of this tile
     const int PLs = plane_f / VEC;                         // samples per plane
 
     // interior tile of a D == 1 filter: one TMA tensor copy stages the whole window
@@ -235,7 +241,21 @@ __global__ void __launch_bounds__(FIR_NT, 5)
     }
     __syncthreads();
 
-    // ---- outputs: registers -> shared (swizzled row per thread) -> coalesced global ----------
+    // ---- outputs: registers -> shared (swizzled row per thread) -> global ----------------------
+    if (ep.fuse) {
+        if (VEC == 2) {
+#pragma unroll
+            for (int l = 0; l < FIR_ACC; l += 2) {
+                float2 v = cmul_nofma(make_float2(acc[l], acc[l + 1]), ep.kre, ep.kim);
+                acc[l] = v.x;
+                acc[l + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int l = 0; l < FIR_ACC; l++)
+                acc[l] = __fmul_rn(acc[l], ep.kre);
+        }
+    }
     {
         float* rb = planes + (tid << 5);
         const int s = (tid & 7) << 2;
@@ -244,24 +264,32 @@ __global__ void __launch_bounds__(FIR_NT, 5)
             *reinterpret_cast<float4*>(rb + ((j << 2) ^ s)) =
                 make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
+    const long long orow0 = (long long)blockIdx.x * FIR_NT; // 128 output rows per tile
+    if (gm.tma_out_ok && orow0 + FIR_NT <= gm.full_out_rows) {
+        // whole tile inside the output: one TMA tensor store from the swizzled rows
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                             &tmap_out),
+                         "r"(0), "r"((int)orow0), "r"(smem_u32(planes))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
     __syncthreads();
 #pragma unroll 4
     for (int i = tid; i < MT; i += FIR_NT) {
         const long long m = O0 + i;
-        if (m < 0 || m >= gm.n_out)
-            continue;
+        if (m >= gm.n_out)
+            break;
         const float* src = planes + swz(i * VEC);
-        if (VEC == 2) {
-            float2 v = *reinterpret_cast<const float2*>(src);
-            if (ep.fuse)
-                v = cmul_nofma(v, ep.kre, ep.kim);
-            __stcs(reinterpret_cast<float2*>(y) + m, v);
-        } else {
-            float v = src[0];
-            if (ep.fuse)
-                v = __fmul_rn(v, ep.kre);
-            __stcs(y + m, v);
-        }
+        if (VEC == 2)
+            __stcs(reinterpret_cast<float2*>(y) + m, *reinterpret_cast<const float2*>(src));
+        else
+            __stcs(y + m, src[0]);
     }
 }
 
@@ -370,7 +398,7 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
     float* y = (float*)d_out;
     if (h->algorithm == 1) {
         const int MT = FIR_NT * (FIR_ACC / h->vec);
-        long long tiles = (n_out + 1 + MT - 1) / MT; // tile k covers outputs [k*MT - 1, (k+1)*MT - 1)
+        long long tiles = (n_out + MT - 1) / MT;
         if (tiles > 0x7fffffffLL)
             return set_err(B200_ERR_ARG, "fir: too many items for one call");
         fir_geom gm{};
@@ -392,12 +420,22 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
                 return rc;
             gm.tma_ok = 1;
         }
+        CUtensorMap tmap_out;
+        memset(&tmap_out, 0, sizeof(tmap_out));
+        gm.full_out_rows = n_out * h->vec / 32;
+        gm.tma_out_ok = 0;
+        if (h->use_tma && gm.full_out_rows >= FIR_NT && (uintptr_t)d_out % 16 == 0) {
+            int rc = fir_make_tmap(&tmap_out, d_out, gm.full_out_rows, FIR_NT);
+            if (rc != B200_OK)
+                return rc;
+            gm.tma_out_ok = 1;
+        }
         if (h->vec == 2)
             B200_LAUNCH((fir_direct_kernel<2>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
-                        h->d_taps_pp, tmap, gm, h->ep);
+                        h->d_taps_pp, tmap, tmap_out, gm, h->ep);
         else
             B200_LAUNCH((fir_direct_kernel<1>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
-                        h->d_taps_pp, tmap, gm, h->ep);
+                        h->d_taps_pp, tmap, tmap_out, gm, h->ep);
     } else {
         long long blocks = (n_out + 255) / 256;
         if (h->vec == 2)
