@@ -71,21 +71,32 @@ __device__ __forceinline__ float2 pfb_fetch(const float2* __restrict__ x, const 
 }
 
 constexpr int PFB64_TT = 64;  // frames per tile
-constexpr int PFB64_RS = 65;  // u row stride (complex)
+constexpr int PFB64_RS = 81;  // u row stride (complex): 81 = 1 mod 16 keeps every DFT access conflict-free
+constexpr int PFB64_CS = 20;  // stride between the four c0 groups after pass A (20 = 4 mod 16)
 
-// M = 64.  256 threads.  smem: X[(TT+P4-1)][64] | U[TT][65] | taps[P4][64] | tw64[64]
+// M = 64.  256 threads, persistent over 64-frame tiles.
+// smem: X[(TT+P4-1)][64] | U[TT][65] | taps[P4][64] | tw64[64] | mbarrier
+// The input tile is one contiguous span of the stream, so interior tiles are staged by a 1-D TMA
+// bulk copy issued as soon as the branch filters of the previous tile have consumed X -- it lands
+// while the 64-point DFTs and the output stores of that tile run.
+template <int P4T> // > 0: taps per branch known at compile time (fully unrolled filters)
 __global__ void __launch_bounds__(256, 2)
     pfb64_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
                  const float* __restrict__ taps_rm /* [P4][64] */, int P4, int Ptrue,
-                 long long n_frames, long long n_in, int ch_begin, int ch_count)
+                 long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok)
 {
-    extern __shared__ __align__(16) float2 sm[];
+    extern __shared__ __align__(128) float2 sm[];
     const int rows = PFB64_TT + P4 - 1;
     float2* X = sm;
     float2* U = X + rows * 64;
     float* hT = reinterpret_cast<float*>(U + PFB64_TT * PFB64_RS);
     float2* tw = reinterpret_cast<float2*>(hT + P4 * 64);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 64);
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
     for (int i = tid; i < P4 * 64; i += 256)
         hT[i] = __ldg(taps_rm + i);
     if (tid < 64) {
@@ -95,15 +106,41 @@ __global__ void __launch_bounds__(256, 2)
     }
     const long long nh = (long long)(Ptrue - 1) * 64;
     const long long n_tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
+    const uint32_t tile_bytes = (uint32_t)rows * 64u * 8u;
+    // can tile `t` be staged by TMA?  (whole span inside [0, n_in), 16-byte aligned source)
+    auto tma_tile = [&](long long t) {
+        const long long g0 = (t * PFB64_TT - (P4 - 1)) * 64;
+        return tma_ok && g0 >= 0 && g0 + (long long)rows * 64 <= n_in;
+    };
+    __syncthreads();
+    long long tile = blockIdx.x;
+    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
+        mbar_arrive_expect_tx(bar, tile_bytes);
+        bulk_copy_g2s(X, x + (tile * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
+    }
+    uint32_t phase = 0;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < n_tiles; tile += gridDim.x) {
         const long long f0 = tile * PFB64_TT; // first frame of the tile
-        __syncthreads();                      // previous tile's U/X consumers done
         // rows: row j holds frame (f0 - (P4-1) + j), col = position within the frame
-        const long long g0 = (f0 - (P4 - 1)) * 64;
-        for (int i = tid; i < rows * 64; i += 256)
-            X[i] = pfb_fetch(x, halo, nh, g0 + i, n_in);
-        __syncthreads();
+        if (tma_tile(tile)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            const long long g0 = (f0 - (P4 - 1)) * 64;
+            for (int i0 = tid; i0 < rows * 64; i0 += 256 * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * 64)
+                        v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * 64)
+                        X[i0 + u * 256] = v[u];
+            }
+            __syncthreads();
+        }
 
         // ---- branch filters: thread = (branch i, 16 consecutive frames) ------------------
         {
@@ -113,33 +150,54 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
             for (int j = 0; j < 16; j++)
                 acc[j] = make_float2(0.f, 0.f);
-            for (int rc = 0; rc < P4; rc += 4) {
-                // taps r = rc..rc+3 ; rows needed: j + (P4-1) - r for j in 0..15 -> base = P4-1-rc-3
-                float h0 = hT[(rc + 0) * 64 + i], h1 = hT[(rc + 1) * 64 + i];
-                float h2 = hT[(rc + 2) * 64 + i], h3 = hT[(rc + 3) * 64 + i];
-                const float2* base = col + (P4 - 1 - rc - 3) * 64;
-                float2 w[19];
+            if (P4T > 0) {
+                // taps in registers, every input row read exactly once: row rho feeds the
+                // (frame j, tap r) pairs with j + P4-1 - r == rho
+                float hreg[P4T > 0 ? P4T : 1];
 #pragma unroll
-                for (int q = 0; q < 19; q++)
-                    w[q] = base[q * 64];
+                for (int r = 0; r < P4T; r++)
+                    hreg[r] = hT[r * 64 + i];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    // r = rc+u uses row offset j + 3 - u
-                    acc[j].x = fmaf(h0, w[j + 3].x, acc[j].x);
-                    acc[j].y = fmaf(h0, w[j + 3].y, acc[j].y);
-                    acc[j].x = fmaf(h1, w[j + 2].x, acc[j].x);
-                    acc[j].y = fmaf(h1, w[j + 2].y, acc[j].y);
-                    acc[j].x = fmaf(h2, w[j + 1].x, acc[j].x);
-                    acc[j].y = fmaf(h2, w[j + 1].y, acc[j].y);
-                    acc[j].x = fmaf(h3, w[j].x, acc[j].x);
-                    acc[j].y = fmaf(h3, w[j].y, acc[j].y);
+                for (int rho = 0; rho < 16 + P4T - 1; rho++) {
+                    const float2 v = col[rho * 64];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int r = j + P4T - 1 - rho;
+                        if (r >= 0 && r < P4T)
+                            acc[j] = __ffma2_rn(v, make_float2(hreg[r], hreg[r]), acc[j]);
+                    }
+                }
+            } else {
+                for (int rc = 0; rc < P4; rc += 4) {
+                    // taps r = rc..rc+3 ; rows needed: j + (P4-1) - r for j in 0..15
+                    const float h0 = hT[(rc + 0) * 64 + i], h1 = hT[(rc + 1) * 64 + i];
+                    const float h2 = hT[(rc + 2) * 64 + i], h3 = hT[(rc + 3) * 64 + i];
+                    const float2* base = col + (P4 - 1 - rc - 3) * 64;
+                    float2 w[19];
+#pragma unroll
+                    for (int q = 0; q < 19; q++)
+                        w[q] = base[q * 64];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        acc[j] = __ffma2_rn(w[j + 3], make_float2(h0, h0), acc[j]);
+                        acc[j] = __ffma2_rn(w[j + 2], make_float2(h1, h1), acc[j]);
+                        acc[j] = __ffma2_rn(w[j + 1], make_float2(h2, h2), acc[j]);
+                        acc[j] = __ffma2_rn(w[j], make_float2(h3, h3), acc[j]);
+                    }
                 }
             }
 #pragma unroll
             for (int j = 0; j < 16; j++)
                 U[(tg * 16 + j) * PFB64_RS + i] = acc[j];
         }
-        __syncthreads();
+        __syncthreads(); // U complete; X fully consumed
+        {
+            const long long nxt = tile + gridDim.x;
+            if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
+                mbar_arrive_expect_tx(bar, tile_bytes);
+                bulk_copy_g2s(X, x + (nxt * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
+            }
+        }
 
         // ---- 64-point reverse DFT across branches: i = 16 i1 + i0, c = c0 + 4 c1 -----------
         {
@@ -167,12 +225,12 @@ __global__ void __launch_bounds__(256, 2)
             for (int j = 0; j < 4; j++)
 #pragma unroll
                 for (int c0 = 0; c0 < 4; c0++)
-                    row[c0 * 16 + 4 * g + j] = v[4 * j + c0];
+                    row[c0 * PFB64_CS + 4 * g + j] = v[4 * j + c0];
             __syncwarp();
             // pass B: thread (t, c0 = g): DFT16 over i0 -> c1
 #pragma unroll
             for (int i0 = 0; i0 < 16; i0++)
-                v[i0] = row[g * 16 + i0];
+                v[i0] = row[g * PFB64_CS + i0];
             idft16(v);
             const long long f = f0 + t;
             if (f < n_frames) {
@@ -185,6 +243,7 @@ __global__ void __launch_bounds__(256, 2)
                 }
             }
         }
+        __syncthreads(); // U free for the next tile's branch filters
     }
 }
 
@@ -274,9 +333,20 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
     if (h->M == 64) {
         long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
         long long g = tiles < h->grid ? tiles : h->grid;
-        B200_LAUNCH(pfb64_kernel, (unsigned)g, 256, h->smem, s, (const float2*)d_in,
-                    (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,
-                    h->ch_begin, h->ch_count);
+#define PFB64_GO(PT)                                                                              \
+    B200_LAUNCH(pfb64_kernel<PT>, (unsigned)g, 256, h->smem, s, (const float2*)d_in,                  \
+                (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
+                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
+        switch (h->P4) {
+        case 4: PFB64_GO(4); break;
+        case 8: PFB64_GO(8); break;
+        case 12: PFB64_GO(12); break;
+        case 16: PFB64_GO(16); break;
+        case 24: PFB64_GO(24); break;
+        case 32: PFB64_GO(32); break;
+        default: PFB64_GO(0); break;
+        }
+#undef PFB64_GO
     } else {
         long long tiles = (n_frames + h->TT - 1) / h->TT;
         if (tiles > 0x7fffffffLL)
@@ -341,13 +411,18 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
     if (M == 64) {
         int rows = PFB64_TT + h->P4 - 1;
         h->smem = sizeof(float2) * ((size_t)rows * 64 + (size_t)PFB64_TT * PFB64_RS + 64) +
-                  sizeof(float) * (size_t)h->P4 * 64;
+                  sizeof(float) * (size_t)h->P4 * 64 + 16;
         if (h->smem > 220 * 1024) {
             b200_pfb_destroy(h);
             return set_err(B200_ERR_UNSUPPORTED, "pfb_create: taps_per_channel too large for M=64 tile");
         }
-        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->grid = 2 * sm_count();
     } else {
         h->TT = 4096 / M;
