@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fir_ols.cuh"
 
 namespace b200 {
 
@@ -345,6 +346,7 @@ struct b200_fir {
     int plane_rows = 0, box_rows = 0, n_boxes = 0; // smem plane geometry (rows of 128 B)
     size_t smem = 0;
     int use_tma = 1;
+    ols_plan* ols = nullptr; // algorithm 3
     int algorithm = 1;
     fir_epilogue ep{ 0, 1.f, 0.f };
     float* d_taps_pp = nullptr; // [D][TQ] reversed per phase
@@ -396,6 +398,8 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         return B200_OK;
     const float* x = (const float*)d_in;
     float* y = (float*)d_out;
+    if (h->algorithm == 3)
+        return ols_launch(h->ols, d_hist, d_in, d_out, n_in, n_out, s);
     if (h->algorithm == 1) {
         const int MT = FIR_NT * (FIR_ACC / h->vec);
         long long tiles = (n_out + MT - 1) / MT;
@@ -458,6 +462,7 @@ int b200_fir_destroy(b200_fir* h)
     cudaFree(h->d_taps);
     cudaFree(h->d_hist[0]);
     cudaFree(h->d_hist[1]);
+    ols_destroy(h->ols);
     delete h;
     return B200_OK;
 }
@@ -495,8 +500,29 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     h->algorithm = 1;
     if (h->smem > 200 * 1024 || p->algorithm == 4)
         h->algorithm = 4; // naive global-memory fallback
-    if (p->algorithm == 3)
-        h->algorithm = 1; // overlap-save not built yet: direct form is always valid
+    // overlap-save fast convolution: complex streams, enough taps per output to pay for two
+    // FFTs per block (crossover measured on B200: ~100 taps per output sample)
+    {
+        const bool can = h->vec == 2 && ols_supported(h->T, h->D);
+        bool want = (p->algorithm == 3);
+        if (p->algorithm == 0 && can && h->T / h->D >= 96)
+            want = true;
+        if (const char* e = getenv("B200_FIR_ALGO"))
+            if (p->algorithm == 0)
+                want = atoi(e) == 3;
+        if (want && !can && p->algorithm == 3) {
+            b200_fir_destroy(h);
+            return set_err(B200_ERR_UNSUPPORTED, "fir_create: overlap-save needs a complex stream and 2..32768 taps");
+        }
+        if (want && can) {
+            int rc = ols_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->ols);
+            if (rc != B200_OK) {
+                b200_fir_destroy(h);
+                return rc;
+            }
+            h->algorithm = 3;
+        }
+    }
 
 #define FIR_CUDA(call)                                                                   \
     do {                                                                                 \

@@ -200,6 +200,60 @@ def test_fir_streaming_equals_oneshot(cuda, T, D):
         assert np.array_equal(got, ref), f"chunk={chunk}: chunked != one-shot"
 
 
+@pytest.mark.parametrize("T,D", [(2, 1), (64, 1), (65, 2), (256, 1), (1024, 4), (1000, 7), (3073, 1), (3000, 3),
+                                 (3074, 1), (4096, 1), (4096, 4), (6001, 2)])
+def test_fir_overlap_save_matches_oracle_and_direct(cuda, T, D):
+    """algorithm 3 (FFT overlap-save) against the fp64 oracle, the direct form, and itself when
+    the stream is chunked or time-segmented (FFT rounding differs per blocking -> tolerance)."""
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T + D)
+    n = 3 * 4096 * 7 + 1234
+    x = cplx(rng, n)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)
+    f = nb.FirFilter(taps, D, algorithm=3)
+    assert f.algorithm == 3
+    y, nc = f.work(dx)
+    ref = o.fir(x, taps, D)
+    assert y.numel() == n // D and nc == (n // D) * D
+    assert o.rel_rms(host(y), ref) < TOL_RMS
+    yd, _ = nb.FirFilter(taps, D, algorithm=1).work(dx)
+    assert o.rel_rms(host(y), host(yd)) < TOL_RMS
+    # streaming in ragged chunks
+    f2 = nb.FirFilter(taps, D, algorithm=3)
+    outs, pos = [], 0
+    for chunk in (5000, 1, 4096, 33333, 10 ** 9):
+        if n - pos < D:
+            break
+        yy, c = f2.work(dx[pos:min(pos + max(chunk, D), n)])
+        outs.append(host(yy))
+        pos += c
+    assert o.rel_rms(np.concatenate(outs), ref[: sum(a.size for a in outs)]) < TOL_RMS
+    assert sum(a.size for a in outs) == n // D
+    # time segments with a halo
+    if T > 1:
+        L = (n // 4) // D * D
+        parts = []
+        for g in range(4):
+            lo, hi = g * L, (n if g == 3 else (g + 1) * L)
+            halo = None if g == 0 else dx[lo - (T - 1):lo]
+            parts.append(host(f.work_segment(dx[lo:hi], halo)))
+        assert o.rel_rms(np.concatenate(parts), ref) < TOL_RMS
+    # fused multiply_const folded into the spectrum
+    k = 0.5 - 0.25j
+    yk, _ = nb.FirFilter(taps, D, multiply_const=k, algorithm=3).work(dx)
+    assert o.rel_rms(host(yk), o.multiply_const(ref.astype(np.complex64), k)) < TOL_RMS
+
+
+def test_fir_auto_algorithm_choice(cuda):
+    import newsched_b200 as nb
+    t = np.ones(64, np.float32)
+    assert nb.FirFilter(t, 1).algorithm == 1                      # short: direct FFMA2 form
+    assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
+    assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 1
+    assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 4   # huge D: fallback kernel
+
+
 def test_fir_empty_and_short(cuda):
     import newsched_b200 as nb
     f = nb.FirFilter(np.ones(8, np.float32), 4)
@@ -216,7 +270,7 @@ def test_fir_segment_halo_equals_stream(cuda):
     x = cplx(rng, n)
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     dx = dev(cuda, x)
-    f = nb.FirFilter(taps, D)
+    f = nb.FirFilter(taps, D, algorithm=1)   # direct form: bit-exact across any segmentation
     ref = host(f.work(dx)[0])
     segs = 8
     L = n // segs
