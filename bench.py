@@ -206,6 +206,7 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     if world != args.gpus and world > 1:
         args.gpus = world
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -251,7 +252,7 @@ def run_b200(args):
     achieved = 12.0 * SAMPLES / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": None,
-                "kernel": "fft4096_kernel<fwd, mag> (window + 3x radix-16 + |.|)",
+                "kernel": "fft4096_tma_kernel<fwd, mag> (TMA prefetch + window + 3x radix-16 + |.|)",
                 "algorithmic_bytes_per_sample": 12, "peak_source": peak_src,
                 "launch_ms": k_ms}
     traffic_file = os.path.join(ROOT, "profiles", "r01_fft4096_traffic.json")
@@ -319,6 +320,17 @@ def run_b200(args):
         extras["fir_ccf_1024taps_decim4_mulc_64Mi"] = {
             "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 1024 / 1e3,
             "frac_of_measured_fp32": gs * 1024 / 1e3 / fp32_tf}
+        extras["fir_ccf_1024taps_decim4_mulc_64Mi"]["algorithm"] = fir.algorithm  # 3 = overlap-save FFT
+        extras["fir_ccf_1024taps_decim4_mulc_64Mi"]["note"] = (
+            "tflops = direct-form algorithmic flops (1024/sample) / time; overlap-save executes fewer")
+        taps = (rng.uniform(-1, 1, 4096) / 4096).astype(np.float32)
+        fir5 = nb.FirFilter(taps, 1)
+        y5 = torch.empty(n3, dtype=torch.complex64, device=dev)
+        t = timed(torch, lambda: fir5.work_segment(x[:n3], None, y5), 3, 2, lambda: None) / 3
+        extras["fir_ccf_4096taps_64Mi"] = {"Msamples_s": n3 / (t * 1e-3) / 1e6, "ms": t,
+                                          "algorithm": fir5.algorithm,
+                                          "direct_form_equiv_tflops": n3 * 4 * 4096 / (t * 1e-3) / 1e12}
+        del y5
         extras["fp32_fma_tflops_measured"] = fp32_tf
         yc = torch.empty(SAMPLES, dtype=torch.complex64, device=dev)
         reps = max(3, min(steps, 20))
@@ -346,6 +358,38 @@ def run_b200(args):
         del yc, y1, y3
     except Exception as e:  # pragma: no cover
         extras["error"] = repr(e)
+
+    # ---- multi-GPU only: BASELINE config 5 (time-segmented FIR, 4096 taps, halo + NCCL gather)
+    if dist is not None:
+        try:
+            from newsched_b200 import multigpu as mg
+            rng5 = np.random.default_rng(5)
+            taps5 = (rng5.uniform(-1, 1, 4096) / 4096).astype(np.float32)
+            seg = x                                         # this rank's 2^27-sample time segment
+            fir5 = nb.FirFilter(taps5, 1)
+            sf = mg.SegmentedFir(fir5, rank, world)
+            y5 = torch.empty(SAMPLES, dtype=torch.complex64, device=dev)
+            t = timed(torch, lambda: sf.run(seg, y5), 3, 2, barrier) / 3
+            t = max_over_ranks(t)
+            extras["config5_segmented_fir_4096taps"] = {
+                "Msamples_s_outputs_sharded": world * SAMPLES / (t * 1e-3) / 1e6, "ms": t,
+                "halo_bytes_per_rank": 4095 * 8, "algorithm": fir5.algorithm}
+            full = mg.gather_concat(y5, rank, world, sizes=[SAMPLES] * world)   # warm-up (NCCL p2p setup)
+            del full
+            torch.cuda.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            full = mg.gather_concat(y5, rank, world, sizes=[SAMPLES] * world)
+            e1.record()
+            torch.cuda.synchronize()
+            tg = max_over_ranks(e0.elapsed_time(e1))
+            extras["config5_segmented_fir_4096taps"]["nccl_gather_ms"] = tg
+            extras["config5_segmented_fir_4096taps"]["Msamples_s_incl_gather"] = (
+                world * SAMPLES / ((t + tg) * 1e-3) / 1e6)
+            del full, y5
+        except Exception as e:  # pragma: no cover
+            extras["config5_error"] = repr(e)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
