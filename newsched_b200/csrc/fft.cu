@@ -54,15 +54,18 @@ __global__ void __launch_bounds__(256, 2)
     for (long long vec = blockIdx.x; vec < n_vec; vec += gridDim.x) {
         const float2* x = in + vec * 4096;
         float2 v[16];
+        // pull the NEXT vector into L2 while this one is transformed (one bulk prefetch, no smem)
+        if (tid == 0 && vec + gridDim.x < n_vec && ((uintptr_t)in % 16 == 0))
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + (vec + gridDim.x) * 4096),
+                         "r"(4096 * 8)
+                         : "memory");
         // ---- pass 1: over n2, thread = L = n1*16+n0
 #pragma unroll
         for (int i = 0; i < 16; i++)
             v[i] = __ldcs(x + i * 256 + tid);
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            v[i].x *= wreg[i];
-            v[i].y *= wreg[i];
-        }
+        for (int i = 0; i < 16; i++)
+            v[i] = __fmul2_rn(v[i], make_float2(wreg[i], wreg[i]));
         dft16<FWD>(v);
 #pragma unroll
         for (int k0 = 0; k0 < 16; k0++)
@@ -155,10 +158,8 @@ __global__ void __launch_bounds__(256, 2)
         for (int i = 0; i < 16; i++)
             v[i] = sIn[i * 256 + tid];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            v[i].x *= wreg[i];
-            v[i].y *= wreg[i];
-        }
+        for (int i = 0; i < 16; i++)
+            v[i] = __fmul2_rn(v[i], make_float2(wreg[i], wreg[i]));
         dft16<FWD>(v);
 #pragma unroll
         for (int k0 = 0; k0 < 16; k0++)
