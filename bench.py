@@ -154,7 +154,7 @@ def cpu_fft_mag_rate(steps, warmup, target_s=0.5):
         "value": x.size * steps / dt / 1e6, "unit": "Msamples/s", "cores": o.num_threads(),
         "kind": "port",
         "sample": f"{nv_step} vectors x {N_FFT} complex64 ({x.nbytes >> 20} MiB) per step, {steps} steps; "
-                  "oracle.c fp32 radix-2 Stockham + window + |.|, OpenMP static over vectors "
+                  "oracle.c fp32 radix-4 Stockham + window + |.|, OpenMP static over vectors "
                   "(CPU restatement, not VOLK/FFTW: the reference snapshot has no FFT block)",
         "ms_per_step": dt / steps * 1e3,
     }

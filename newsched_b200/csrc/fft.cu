@@ -208,6 +208,166 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---- N = 256, 512, 1024, 2048: same machinery, N = R0 * 256 ------------------------------------
+// A CTA always works on 4096 contiguous samples = V = 16/R0 vectors.  Pass 1 is V radix-R0
+// butterflies per thread (16 points in registers, as before) with twiddle W_N^{L k0}; that leaves
+// 16 rows of 256 points, and passes 2-3 are exactly the N = 4096 ones.  Output index is
+// k = k0 + R0 (k1 + 16 k2); pass 3 maps lanes to (k0 fastest, then k1) so stores are contiguous.
+// Rows are padded (column stride 17, row stride 272 + 16/R0) to keep every pattern conflict-free.
+template <int R0>
+struct fr0 {
+    static constexpr int V = 16 / R0;
+    static constexpr int SK = 17;
+    static constexpr int SR = 16 * 17 + (16 / R0);
+    static constexpr int N = R0 * 256;
+    static constexpr size_t SMEM = 4096 * 8 + 16 * SR * 8 + 256 * 8 + 16;
+};
+
+template <bool FWD>
+__device__ __forceinline__ void dft2(float2& a, float2& b)
+{
+    float2 s = a + b, d = a - b;
+    a = s;
+    b = d;
+}
+
+// natural-order 8-point DFT
+template <bool FWD>
+__device__ __forceinline__ void dft8(float2 (&z)[8])
+{
+    float2 e0 = z[0], e1 = z[2], e2 = z[4], e3 = z[6];
+    float2 o0 = z[1], o1 = z[3], o2 = z[5], o3 = z[7];
+    dft4<FWD>(e0, e1, e2, e3);
+    dft4<FWD>(o0, o1, o2, o3);
+    o1 = mul_w16<FWD, 2>(o1); // W8^1 = W16^2
+    o2 = mul_w16<FWD, 4>(o2);
+    o3 = mul_w16<FWD, 6>(o3);
+    z[0] = e0 + o0;
+    z[4] = e0 - o0;
+    z[1] = e1 + o1;
+    z[5] = e1 - o1;
+    z[2] = e2 + o2;
+    z[6] = e2 - o2;
+    z[3] = e3 + o3;
+    z[7] = e3 - o3;
+}
+
+template <int R0, bool FWD, int OUT>
+__global__ void __launch_bounds__(256, 2)
+    fft_r0_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec,
+                  const float* __restrict__ weff, const float2* __restrict__ tw1,
+                  const float2* __restrict__ tw2, int tma_ok)
+{
+    using G = fr0<R0>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sIn = reinterpret_cast<float2*>(smem_raw);
+    float2* sA = sIn + 4096;
+    float2* sT2 = sA + 16 * G::SR;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + 256);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    float wreg[R0];
+    float2 t1[R0];
+#pragma unroll
+    for (int i = 0; i < R0; i++) {
+        wreg[i] = __ldg(weff + i * 256 + tid);
+        t1[i] = __ldg(tw1 + i * 256 + tid);
+    }
+    sT2[tid] = __ldg(tw2 + tid);
+    __syncthreads();
+    const long long n_blocks = (n_vec + G::V - 1) / G::V;
+    auto tma_block = [&](long long b) { return tma_ok && (b + 1) * G::V <= n_vec; };
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < n_blocks && tma_block(blk)) {
+        mbar_arrive_expect_tx(bar, 4096 * 8);
+        bulk_copy_g2s(sIn, in + blk * 4096, 4096 * 8, bar);
+    }
+    uint32_t phase = 0;
+    for (; blk < n_blocks; blk += gridDim.x) {
+        const long long vec0 = blk * G::V;
+        float2 v[16];
+        if (tma_block(blk)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = sIn[i * 256 + tid];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const long long vv = vec0 + i / R0; // element i*256+tid belongs to vector i / R0
+                v[i] = vv < n_vec ? __ldcs(in + blk * 4096 + i * 256 + tid) : make_float2(0.f, 0.f);
+            }
+        }
+        // ---- pass 1: V radix-R0 butterflies; v[vv*R0 + n2]
+#pragma unroll
+        for (int vv = 0; vv < G::V; vv++) {
+            float2 z[R0];
+#pragma unroll
+            for (int n2 = 0; n2 < R0; n2++)
+                z[n2] = __fmul2_rn(v[vv * R0 + n2], make_float2(wreg[n2], wreg[n2]));
+            if (R0 == 2)
+                dft2<FWD>(z[0], z[R0 > 1 ? 1 : 0]);
+            if (R0 == 4)
+                dft4<FWD>(z[0], z[R0 > 1 ? 1 : 0], z[R0 > 2 ? 2 : 0], z[R0 > 3 ? 3 : 0]);
+            if (R0 == 8)
+                dft8<FWD>(reinterpret_cast<float2(&)[8]>(z));
+            const int n1 = tid >> 4, n0 = tid & 15;
+#pragma unroll
+            for (int k0 = 0; k0 < R0; k0++)
+                sA[(vv * R0 + k0) * G::SR + n1 * G::SK + n0] = cmul(z[k0], t1[k0]);
+        }
+        __syncthreads();
+        if (tid == 0 && blk + gridDim.x < n_blocks && tma_block(blk + gridDim.x)) {
+            mbar_arrive_expect_tx(bar, 4096 * 8);
+            bulk_copy_g2s(sIn, in + (blk + gridDim.x) * 4096, 4096 * 8, bar);
+        }
+        // ---- pass 2: per row, DFT16 over n1, in place
+        {
+            const int r = tid >> 4, n0 = tid & 15;
+            float2* row = sA + r * G::SR + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i * G::SK];
+            dft16<FWD>(v);
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++)
+                row[k1 * G::SK] = cmul(v[pos16(k1)], sT2[k1 * 16 + n0]);
+        }
+        __syncthreads();
+        // ---- pass 3: lanes = (k0 fastest, k1, vector)
+        {
+            const int k0 = tid % R0, k1 = (tid / R0) & 15, vv = tid / (R0 * 16);
+            const float2* row = sA + (vv * R0 + k0) * G::SR + k1 * G::SK;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i];
+            dft16<FWD>(v);
+            if (vec0 + vv < n_vec) {
+                const long long base = blk * 4096 + vv * G::N + (tid % (R0 * 16));
+                if (OUT == B200_FFT_OUT_COMPLEX) {
+                    float2* y = reinterpret_cast<float2*>(out) + base;
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; k2++)
+                        __stcs(y + k2 * 16 * R0, v[pos16(k2)]);
+                } else {
+                    float* y = reinterpret_cast<float*>(out) + base;
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; k2++) {
+                        float2 z = v[pos16(k2)];
+                        float p = fmaf(z.x, z.x, z.y * z.y);
+                        __stcs(y + k2 * 16 * R0, OUT == B200_FFT_OUT_MAG ? sqrt_approx(p) : p);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- generic power-of-two radix-2 Stockham (N = 8 .. 8192) ----------------------------------
 template <bool FWD, int OUT>
 __global__ void __launch_bounds__(512)
@@ -300,6 +460,21 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
         else
             B200_LAUNCH((fft4096_kernel<FWD, OUT>), (unsigned)g, 256, 0, s, (const float2*)d_in, d_out,
                         n_vec, h->d_weff, h->d_tw1, h->d_tw2);
+    } else if (h->N == 256 || h->N == 512 || h->N == 1024 || h->N == 2048) {
+        const int R0 = h->N / 256, V = 16 / R0;
+        long long nb = (n_vec + V - 1) / V;
+        long long g = nb < h->grid_4k ? nb : h->grid_4k;
+        const int tma_ok = (uintptr_t)d_in % 16 == 0;
+#define FFT_R0_GO(R)                                                                                  \
+    B200_LAUNCH((fft_r0_kernel<R, FWD, OUT>), (unsigned)g, 256, fr0<R>::SMEM, s, (const float2*)d_in, \
+                d_out, n_vec, h->d_weff, h->d_tw1, h->d_tw2, tma_ok)
+        switch (R0) {
+        case 1: FFT_R0_GO(1); break;
+        case 2: FFT_R0_GO(2); break;
+        case 4: FFT_R0_GO(4); break;
+        default: FFT_R0_GO(8); break;
+        }
+#undef FFT_R0_GO
     } else {
         long long blocks = (n_vec + h->vpb - 1) / h->vpb;
         if (blocks > 0x7fffffffLL)
@@ -332,6 +507,24 @@ static cudaError_t fft_tma_attr()
 {
     return cudaFuncSetAttribute(fft4096_tma_kernel<FWD, OUT>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F4K_TMA_SMEM);
+}
+
+template <int R0, bool FWD, int OUT>
+static cudaError_t fft_r0_attr()
+{
+    return cudaFuncSetAttribute(fft_r0_kernel<R0, FWD, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fr0<R0>::SMEM);
+}
+template <int R0>
+static cudaError_t fft_r0_attr_all()
+{
+    cudaError_t e = cudaSuccess;
+    if ((e = fft_r0_attr<R0, true, 0>()) != cudaSuccess) return e;
+    if ((e = fft_r0_attr<R0, true, 1>()) != cudaSuccess) return e;
+    if ((e = fft_r0_attr<R0, true, 2>()) != cudaSuccess) return e;
+    if ((e = fft_r0_attr<R0, false, 0>()) != cudaSuccess) return e;
+    if ((e = fft_r0_attr<R0, false, 1>()) != cudaSuccess) return e;
+    return fft_r0_attr<R0, false, 2>();
 }
 
 template <bool FWD, int OUT>
@@ -444,6 +637,35 @@ int b200_fft_create(const b200_fft_params* p, b200_fft** out)
         FFT_CUDA((fft_tma_attr<false, 0>()));
         FFT_CUDA((fft_tma_attr<false, 1>()));
         FFT_CUDA((fft_tma_attr<false, 2>()));
+    } else if (N == 256 || N == 512 || N == 1024 || N == 2048) {
+        const int R0 = N / 256;
+        std::vector<float2> t1((size_t)R0 * 256), t2(256);
+        for (int k0 = 0; k0 < R0; k0++)
+            for (int L = 0; L < 256; L++) {
+                double ang = sgn * 2.0 * M_PI * (double)((L * k0) % N) / (double)N;
+                double wr = std::cos(ang), wi = std::sin(ang);
+                double pr = kph_re, pi = kph_im;
+                if (h->flip && R0 > 1 && (k0 & 1)) { // (-1)^k, k = k0 + R0 (k1 + 16 k2), R0 even
+                    pr = -pr;
+                    pi = -pi;
+                }
+                t1[(size_t)k0 * 256 + L] = make_float2((float)(wr * pr - wi * pi), (float)(wr * pi + wi * pr));
+            }
+        for (int k1 = 0; k1 < 16; k1++)
+            for (int n0 = 0; n0 < 16; n0++) {
+                double ang = sgn * 2.0 * M_PI * (double)(n0 * k1) / 256.0;
+                double f = (h->flip && R0 == 1 && (k1 & 1)) ? -1.0 : 1.0; // N = 256: parity of k is k1's
+                t2[k1 * 16 + n0] = make_float2((float)(f * std::cos(ang)), (float)(f * std::sin(ang)));
+            }
+        FFT_CUDA(cudaMalloc(&h->d_tw1, sizeof(float2) * t1.size()));
+        FFT_CUDA(cudaMemcpy(h->d_tw1, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
+        FFT_CUDA(cudaMalloc(&h->d_tw2, sizeof(float2) * t2.size()));
+        FFT_CUDA(cudaMemcpy(h->d_tw2, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
+        h->grid_4k = 2 * sm_count();
+        FFT_CUDA(fft_r0_attr_all<1>());
+        FFT_CUDA(fft_r0_attr_all<2>());
+        FFT_CUDA(fft_r0_attr_all<4>());
+        FFT_CUDA(fft_r0_attr_all<8>());
     } else {
         std::vector<float2> tw(N / 2);
         for (int j = 0; j < N / 2; j++) {

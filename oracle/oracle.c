@@ -348,7 +348,7 @@ ORC_API int orc_fft_f64(float* out, const float* in, int64_t n_vec, int N, int f
     return err;
 }
 
-/* fp32 FFT "as a CPU block would compute it": iterative radix-2 Stockham autosort with
+/* fp32 FFT "as a CPU block would compute it": iterative radix-4 Stockham autosort with
  * a precomputed fp32 twiddle table, vectorisable inner loops; used as the timed CPU
  * baseline (bench.py cpu_baseline / --impl reference) and as a second checker. */
 typedef struct {
@@ -367,10 +367,9 @@ ORC_API orc_fft_plan* orc_fft_plan_create(int N)
     p->log2n = 0;
     while ((1 << p->log2n) < N)
         p->log2n++;
-    int h = N / 2 > 0 ? N / 2 : 1;
-    p->twr = (float*)malloc(sizeof(float) * (size_t)h);
-    p->twi = (float*)malloc(sizeof(float) * (size_t)h);
-    for (int j = 0; j < N / 2; j++) {
+    p->twr = (float*)malloc(sizeof(float) * (size_t)N);
+    p->twi = (float*)malloc(sizeof(float) * (size_t)N);
+    for (int j = 0; j < N; j++) { /* full circle: the radix-4 passes need W^{3p} */
         double ang = -2.0 * M_PI * (double)j / (double)N;
         p->twr[j] = (float)cos(ang);
         p->twi[j] = (float)sin(ang);
@@ -387,43 +386,72 @@ ORC_API void orc_fft_plan_destroy(orc_fft_plan* p)
     free(p);
 }
 
-/* One Stockham radix-2 pass: n = current sub-transform count stride bookkeeping.
- * x -> y, split re/im planes.  s = stride (number of interleaved sequences), m = half
- * length of the current transforms. */
-static void stockham_f32(const orc_fft_plan* p, float* xr, float* xi, float* yr, float* yi,
-                         float sign)
+/* Stockham autosort FFT, split re/im planes, radix-4 passes (one radix-2 pass first when log2 N
+ * is odd).  Each pass reads x and writes y, then the roles swap; the return value says where the
+ * result ended up (0 = the buffers passed as x, 1 = the buffers passed as y).
+ * n = current transform length, s = stride (number of interleaved sub-sequences). */
+static int stockham_f32(const orc_fft_plan* p, float* xr, float* xi, float* yr, float* yi,
+                        float sign)
 {
     const int N = p->N;
-    int s = 1;
-    for (int n = N; n > 1; n >>= 1, s <<= 1) {
+    int s = 1, n = N, where = 0;
+    float* t;
+    if (p->log2n & 1) { /* radix-2 pass */
         int m = n >> 1;
         int tstep = N / n;
         for (int q = 0; q < m; q++) {
-            float wr = p->twr[q * tstep];
-            float wi = sign * p->twi[q * tstep];
-            const float* ar = xr + s * q;
-            const float* ai = xi + s * q;
-            const float* br = xr + s * (q + m);
-            const float* bi = xi + s * (q + m);
-            float* cr = yr + s * 2 * q;
-            float* ci = yi + s * 2 * q;
-            float* dr = cr + s;
-            float* di = ci + s;
-            for (int j = 0; j < s; j++) {
-                float a_r = ar[j], a_i = ai[j], b_r = br[j], b_i = bi[j];
-                float sr = a_r - b_r, si = a_i - b_i;
-                cr[j] = a_r + b_r;
-                ci[j] = a_i + b_i;
-                dr[j] = sr * wr - si * wi;
-                di[j] = sr * wi + si * wr;
-            }
+            float wr = p->twr[q * tstep], wi = sign * p->twi[q * tstep];
+            float a_r = xr[q], a_i = xi[q], b_r = xr[q + m], b_i = xi[q + m];
+            float sr = a_r - b_r, si = a_i - b_i;
+            yr[2 * q] = a_r + b_r;
+            yi[2 * q] = a_i + b_i;
+            yr[2 * q + 1] = sr * wr - si * wi;
+            yi[2 * q + 1] = sr * wi + si * wr;
         }
-        float* t;
         t = xr; xr = yr; yr = t;
         t = xi; xi = yi; yi = t;
+        where ^= 1;
+        n >>= 1;
+        s <<= 1;
     }
-    /* result is in (xr, xi) after the final swap; callers pass buffers so that an
-     * even/odd number of passes is handled by the caller via log2n parity. */
+    for (; n > 1; n >>= 2, s <<= 2) {
+        const int m = n >> 2;
+        const int tstep = N / n;
+        for (int q = 0; q < m; q++) {
+            const float w1r = p->twr[q * tstep], w1i = sign * p->twi[q * tstep];
+            const float w2r = p->twr[2 * q * tstep], w2i = sign * p->twi[2 * q * tstep];
+            const float w3r = p->twr[3 * q * tstep], w3i = sign * p->twi[3 * q * tstep];
+            const float *ar = xr + s * q, *ai = xi + s * q;
+            const float *br = ar + s * m, *bi = ai + s * m;
+            const float *cr = br + s * m, *ci = bi + s * m;
+            const float *dr = cr + s * m, *di = ci + s * m;
+            float *o0r = yr + s * 4 * q, *o0i = yi + s * 4 * q;
+            float *o1r = o0r + s, *o1i = o0i + s, *o2r = o1r + s, *o2i = o1i + s, *o3r = o2r + s, *o3i = o2i + s;
+            for (int j = 0; j < s; j++) {
+                float apcr = ar[j] + cr[j], apci = ai[j] + ci[j];
+                float amcr = ar[j] - cr[j], amci = ai[j] - ci[j];
+                float bpdr = br[j] + dr[j], bpdi = bi[j] + di[j];
+                float bmdr = br[j] - dr[j], bmdi = bi[j] - di[j];
+                /* forward (sign=+1): -j (b-d) = (bmdi, -bmdr); reverse: +j (b-d) */
+                float jr = sign * bmdi, ji = -sign * bmdr;
+                float t1r = amcr + jr, t1i = amci + ji;
+                float t2r = apcr - bpdr, t2i = apci - bpdi;
+                float t3r = amcr - jr, t3i = amci - ji;
+                o0r[j] = apcr + bpdr;
+                o0i[j] = apci + bpdi;
+                o1r[j] = t1r * w1r - t1i * w1i;
+                o1i[j] = t1r * w1i + t1i * w1r;
+                o2r[j] = t2r * w2r - t2i * w2i;
+                o2i[j] = t2r * w2i + t2i * w2r;
+                o3r[j] = t3r * w3r - t3i * w3i;
+                o3i[j] = t3r * w3i + t3i * w3r;
+            }
+        }
+        t = xr; xr = yr; yr = t;
+        t = xi; xi = yi; yi = t;
+        where ^= 1;
+    }
+    return where;
 }
 
 ORC_API int orc_fft_f32(const orc_fft_plan* p, float* out, const float* in, int64_t n_vec,
@@ -450,9 +478,9 @@ ORC_API int orc_fft_f32(const orc_fft_plan* p, float* out, const float* in, int6
                     xr[n] = x[2 * src] * w;
                     xi[n] = x[2 * src + 1] * w;
                 }
-                stockham_f32(p, xr, xi, yr, yi, forward ? 1.0f : -1.0f);
-                const float* rr = (p->log2n & 1) ? yr : xr;
-                const float* ri = (p->log2n & 1) ? yi : xi;
+                int where = stockham_f32(p, xr, xi, yr, yi, forward ? 1.0f : -1.0f);
+                const float* rr = where ? yr : xr;
+                const float* ri = where ? yi : xi;
                 if (mag) {
                     float* y = out + v * (int64_t)N;
                     for (int j = 0; j < N; j++) {
@@ -570,9 +598,9 @@ ORC_API int64_t orc_pfb_channelizer_f32(float* out, const float* in, int64_t n_i
                 xr[i] = ar;
                 xi[i] = ai;
             }
-            stockham_f32(plan, xr, xi, yr, yi, -1.0f); /* reverse DFT: e^{+j} */
-            const float* rr = (plan->log2n & 1) ? yr : xr;
-            const float* ri = (plan->log2n & 1) ? yi : xi;
+            int where = stockham_f32(plan, xr, xi, yr, yi, -1.0f); /* reverse DFT: e^{+j} */
+            const float* rr = where ? yr : xr;
+            const float* ri = where ? yi : xi;
             for (int c = 0; c < M; c++) {
                 out[2 * (t * M + c)] = rr[c];
                 out[2 * (t * M + c) + 1] = ri[c];

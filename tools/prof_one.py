@@ -18,6 +18,11 @@ if what == "fftmag":
     op = nb.FFT(N, True, w, output=nb.OUT_MAG); out = torch.empty(n, dtype=torch.float32, device="cuda"); fn = lambda: op.work(x, out)
 elif what == "fft":
     op = nb.FFT(N, True, w); out = torch.empty_like(x); fn = lambda: op.work(x, out)
+elif what.startswith("fftn"):
+    Nn = int(what[4:]); t2 = np.arange(Nn) / (Nn - 1)
+    w2 = (0.35875 - 0.48829 * np.cos(2 * np.pi * t2) + 0.14128 * np.cos(4 * np.pi * t2) - 0.01168 * np.cos(6 * np.pi * t2)).astype(np.float32)
+    n = N * 32768; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    op = nb.FFT(Nn, True, w2); out = torch.empty_like(x); fn = lambda: op.work(x, out)
 elif what == "fir64":
     op = nb.FirFilter((rng.uniform(-1, 1, 64) / 64).astype(np.float32)); out = torch.empty_like(x); fn = lambda: op.work_segment(x, None, out)
 elif what == "fir1024d4":
