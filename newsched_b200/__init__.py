@@ -19,7 +19,7 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200dsp.so")
+LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "lib", "libb200dsp.so"))
 _lib = None
 
 OUT_COMPLEX, OUT_MAG, OUT_MAG_SQUARED = 0, 1, 2

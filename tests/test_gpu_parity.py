@@ -54,6 +54,26 @@ def test_copy_full_size_checksum(cuda):
     assert cuda.equal(x, y)
 
 
+def test_copy_and_fir_beyond_32bit_byte_counts(cuda):
+    """Sizes past 2^31 bytes per call: the reference computes byte counts in `int`
+    (copy.hpp:37 `int size = n_items * _itemsize`) and is limited to < 2 GiB per call; the
+    C-ABI takes size_t / int64 and indexes in 64 bits."""
+    import newsched_b200 as nb
+    n = (1 << 28) + 12345                      # complex64 samples: 2 GiB + a ragged tail
+    x = cuda.empty(n, dtype=cuda.complex64, device="cuda")
+    xr = cuda.view_as_real(x)
+    xr[:, 0] = cuda.arange(n, device="cuda", dtype=cuda.float32) % 4093.0
+    xr[:, 1] = -(cuda.arange(n, device="cuda", dtype=cuda.float32) % 611.0)
+    y = nb.copy(x)
+    assert cuda.equal(cuda.view_as_real(y)[-100000:], xr[-100000:]) and cuda.equal(y[:1000], x[:1000])
+    assert float(cuda.view_as_real(y)[:, 0].double().sum()) == float(xr[:, 0].double().sum())
+    del y
+    taps = np.zeros(64, np.float32)
+    taps[5] = 1.0                              # pure delay by 5 samples: exact
+    z, nc = nb.FirFilter(taps, 1).work(x)
+    assert nc == n and cuda.equal(z[5:], x[:-5]) and not bool(z[:5].abs().any())
+
+
 # --------------------------------------------------------------------- multiply_const
 def test_multiply_const_k1_exact(cuda, golden):
     import newsched_b200 as nb
