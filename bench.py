@@ -134,6 +134,10 @@ def cpu_fft_mag_rate(steps, warmup, target_s=0.5):
     """Times the oracle's fp32 FFT+|.| (OpenMP, all host threads) on a bounded sample."""
     import numpy as np
     import oracle as o
+    try:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it may run on
+        o.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        o.set_num_threads(os.cpu_count() or 1)
     w = blackman_harris(N_FFT)
     rng = np.random.default_rng(0x5EED)
     nv = 256
