@@ -107,6 +107,12 @@ B200_API int b200_multiply_const_ff(float* d_out, const float* d_in, float k, si
 B200_API int b200_multiply_const_cc(void* d_out, const void* d_in, float k_re, float k_im, size_t n, b200_stream_t s);
 B200_API int b200_multiply_const_ss(int16_t* d_out, const int16_t* d_in, int16_t k, size_t n, b200_stream_t s);
 B200_API int b200_multiply_const_ii(int32_t* d_out, const int32_t* d_in, int32_t k, size_t n, b200_stream_t s);
+/* two-input stream blocks (natural neighbours on the same kernels):
+ * out = a * b / out = a + b over n scalars; cc = full complex product, non-fused rounding. */
+B200_API int b200_multiply_ff(float* d_out, const float* d_a, const float* d_b, size_t n, b200_stream_t s);
+B200_API int b200_multiply_cc(void* d_out, const void* d_a, const void* d_b, size_t n, b200_stream_t s);
+B200_API int b200_add_ff(float* d_out, const float* d_a, const float* d_b, size_t n, b200_stream_t s);
+B200_API int b200_add_cc(void* d_out, const void* d_a, const void* d_b, size_t n, b200_stream_t s);
 /* complex_to_mag: out[i] = sqrtf(re*re + im*im) over n complex64. */
 B200_API int b200_complex_to_mag(float* d_out, const void* d_in, size_t n, b200_stream_t s);
 B200_API int b200_complex_to_mag_squared(float* d_out, const void* d_in, size_t n, b200_stream_t s);

@@ -14,7 +14,7 @@ import os
 import subprocess
 
 __all__ = [
-    "lib", "build", "B200Error", "copy", "multiply_const", "complex_to_mag", "FirFilter", "FFT",
+    "lib", "build", "B200Error", "copy", "multiply_const", "multiply", "add", "complex_to_mag", "FirFilter", "FFT",
     "PfbChannelizer", "Chain", "DeviceRing", "launch_count", "LIB_PATH",
 ]
 
@@ -106,6 +106,10 @@ SIGNATURES = {
     "b200_multiply_const_cc": (_I, [_V, _V, _F, _F, _SZ, _V]),
     "b200_multiply_const_ss": (_I, [_V, _V, C.c_int16, _SZ, _V]),
     "b200_multiply_const_ii": (_I, [_V, _V, C.c_int32, _SZ, _V]),
+    "b200_multiply_ff": (_I, [_V, _V, _V, _SZ, _V]),
+    "b200_multiply_cc": (_I, [_V, _V, _V, _SZ, _V]),
+    "b200_add_ff": (_I, [_V, _V, _V, _SZ, _V]),
+    "b200_add_cc": (_I, [_V, _V, _V, _SZ, _V]),
     "b200_complex_to_mag": (_I, [_V, _V, _SZ, _V]),
     "b200_complex_to_mag_squared": (_I, [_V, _V, _SZ, _V]),
     "b200_fir_create": (_I, [C.POINTER(_FirParams), C.POINTER(_V)]),
@@ -227,6 +231,31 @@ def multiply_const(x, k, out=None, stream=None):
     else:
         raise B200Error(f"multiply_const: unsupported dtype {x.dtype}")
     return out
+
+
+def _binary(name, a, b, out, stream):
+    torch = _torch()
+    _need_cuda(a)
+    _need_cuda(b)
+    if a.dtype != b.dtype or a.shape != b.shape:
+        raise B200Error("two-input blocks need equal dtypes and shapes")
+    if a.dtype not in (torch.float32, torch.complex64):
+        raise B200Error(f"{name}: unsupported dtype {a.dtype}")
+    if out is None:
+        out = torch.empty_like(a)
+    fn = getattr(lib(), f"b200_{name}_{'cc' if a.dtype == torch.complex64 else 'ff'}")
+    _check(fn(out.data_ptr(), a.data_ptr(), b.data_ptr(), a.numel(), _stream(stream)))
+    return out
+
+
+def multiply(a, b, out=None, stream=None):
+    """Two-input multiply block (float32 or complex64), out = a * b."""
+    return _binary("multiply", a, b, out, stream)
+
+
+def add(a, b, out=None, stream=None):
+    """Two-input add block (float32 or complex64), out = a + b."""
+    return _binary("add", a, b, out, stream)
 
 
 def complex_to_mag(x, squared: bool = False, out=None, stream=None):

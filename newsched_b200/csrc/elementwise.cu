@@ -223,6 +223,79 @@ static int copy_narrow(const uint8_t* in, uint8_t* out, size_t n_bytes, cudaStre
     return B200_OK;
 }
 
+// ---- two-input ops: out[i] = f(a[i], b[i]) over float lanes (complex = 2 lanes) ------------------
+// MODE 0: a+b (ff and cc are the same thing lane-wise), 1: a*b real, 2: a*b complex
+template <int MODE>
+__device__ __forceinline__ float4 bin4(float4 a, float4 b)
+{
+    if (MODE == 0)
+        return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+    if (MODE == 1)
+        return make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
+    float2 p = cmul_nofma(make_float2(a.x, a.y), b.x, b.y);
+    float2 q = cmul_nofma(make_float2(a.z, a.w), b.z, b.w);
+    return make_float4(p.x, p.y, q.x, q.y);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(EW_THREADS)
+    ew_binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                     size_t n_floats, int vec_ok)
+{
+    const size_t nvec = vec_ok ? n_floats / 4 : 0;
+    size_t base = (size_t)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
+    float4 va[EW_UNROLL], vb[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; u++) {
+        size_t i = base + (size_t)u * EW_THREADS;
+        if (i < nvec) {
+            va[u] = __ldcs(reinterpret_cast<const float4*>(a) + i);
+            vb[u] = __ldcs(reinterpret_cast<const float4*>(b) + i);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; u++) {
+        size_t i = base + (size_t)u * EW_THREADS;
+        if (i < nvec)
+            __stcs(reinterpret_cast<float4*>(out) + i, bin4<MODE>(va[u], vb[u]));
+    }
+    // scalar remainder (or everything when the buffers are not 16-byte aligned): complex pairs
+    // stay together because the lane count is even for MODE 2
+    const size_t step = (MODE == 2) ? 2 : 1;
+    for (size_t j = nvec * 4 + ((size_t)blockIdx.x * EW_THREADS + threadIdx.x) * step; j < n_floats;
+         j += (size_t)gridDim.x * EW_THREADS * step) {
+        if (MODE == 0)
+            out[j] = __fadd_rn(a[j], b[j]);
+        else if (MODE == 1)
+            out[j] = __fmul_rn(a[j], b[j]);
+        else {
+            float2 p = cmul_nofma(make_float2(a[j], a[j + 1]), b[j], b[j + 1]);
+            out[j] = p.x;
+            out[j + 1] = p.y;
+        }
+    }
+}
+
+template <int MODE>
+static int ew_binary(const void* a, const void* b, void* out, size_t n_floats, cudaStream_t s)
+{
+    if (n_floats == 0)
+        return B200_OK;
+    if (!a || !b || !out)
+        return set_err(B200_ERR_ARG, "elementwise: null pointer");
+    const uintptr_t al = (MODE == 2) ? 8 : 4;
+    if ((uintptr_t)a % al || (uintptr_t)b % al || (uintptr_t)out % al)
+        return set_err(B200_ERR_ARG, "elementwise: pointer not aligned to the item type");
+    const int vec_ok = ((uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 && (uintptr_t)out % 16 == 0) ? 1 : 0;
+    const size_t per_block = (size_t)EW_THREADS * EW_UNROLL * 4;
+    size_t blocks = vec_ok ? (n_floats + per_block - 1) / per_block : (n_floats + EW_THREADS - 1) / EW_THREADS;
+    if (blocks > 0x7fffffffull)
+        return set_err(B200_ERR_ARG, "elementwise: too many items for one call");
+    B200_LAUNCH((ew_binary_kernel<MODE>), (unsigned)blocks, EW_THREADS, 0, s, (const float*)a, (const float*)b,
+                (float*)out, n_floats, vec_ok);
+    return B200_OK;
+}
+
 } // namespace b200
 
 using namespace b200;
@@ -265,6 +338,22 @@ int b200_multiply_const_ss(int16_t* d_out, const int16_t* d_in, int16_t k, size_
 int b200_multiply_const_ii(int32_t* d_out, const int32_t* d_in, int32_t k, size_t n, b200_stream_t s)
 {
     return ew_launch<op_mul_ii>(d_in, d_out, n, op_mul_ii{ (uint32_t)k }, cs(s));
+}
+int b200_multiply_ff(float* d_out, const float* d_a, const float* d_b, size_t n, b200_stream_t s)
+{
+    return ew_binary<1>(d_a, d_b, d_out, n, cs(s));
+}
+int b200_multiply_cc(void* d_out, const void* d_a, const void* d_b, size_t n, b200_stream_t s)
+{
+    return ew_binary<2>(d_a, d_b, d_out, 2 * n, cs(s));
+}
+int b200_add_ff(float* d_out, const float* d_a, const float* d_b, size_t n, b200_stream_t s)
+{
+    return ew_binary<0>(d_a, d_b, d_out, n, cs(s));
+}
+int b200_add_cc(void* d_out, const void* d_a, const void* d_b, size_t n, b200_stream_t s)
+{
+    return ew_binary<0>(d_a, d_b, d_out, 2 * n, cs(s));
 }
 int b200_complex_to_mag(float* d_out, const void* d_in, size_t n, b200_stream_t s)
 {

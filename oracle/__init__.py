@@ -61,6 +61,9 @@ def _declare(L):
     L.orc_multiply_const_cc_mt.argtypes = L.orc_multiply_const_cc.argtypes
     L.orc_multiply_const_ss.argtypes = [C.c_void_p, C.c_void_p, C.c_int16, C.c_int64]
     L.orc_multiply_const_ii.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]
+    L.orc_multiply_ff.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.orc_multiply_cc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.orc_add_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.orc_complex_to_mag.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.orc_complex_to_mag_squared.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     for name in ("orc_fir_ccf_f64", "orc_fir_fff_f64", "orc_fir_ccf_f32", "orc_fir_fff_f32",
@@ -125,6 +128,22 @@ def multiply_const(x: np.ndarray, k) -> np.ndarray:
         lib().orc_multiply_const_ii(_p(out), _p(x), int(np.int32(k)), x.size)
     else:
         raise TypeError(x.dtype)
+    return out
+
+
+def multiply(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """two-input multiply (float32 / complex64)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b, dtype=a.dtype)
+    out = np.empty_like(a)
+    (lib().orc_multiply_cc if a.dtype == np.complex64 else lib().orc_multiply_ff)(_p(out), _p(a), _p(b), a.size)
+    return out
+
+
+def add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """two-input add (float32 / complex64)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b, dtype=a.dtype)
+    out = np.empty_like(a)
+    lib().orc_add_f(_p(out), _p(a), _p(b), a.size * (2 if a.dtype == np.complex64 else 1))
     return out
 
 

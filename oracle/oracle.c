@@ -98,6 +98,28 @@ ORC_API void orc_multiply_const_ii(int32_t* out, const int32_t* in, int32_t k, i
         out[i] = (int32_t)((uint32_t)in[i] * (uint32_t)k);
 }
 
+/* two-input blocks (GNU Radio multiply_XX / add_XX semantics; absent from the snapshot):
+ * element-wise product / sum, complex product with each partial product rounded to fp32 */
+ORC_API void orc_multiply_ff(float* out, const float* a, const float* b, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++)
+        out[i] = a[i] * b[i];
+}
+ORC_API void orc_multiply_cc(float* out, const float* a, const float* b, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) {
+        float ar = a[2 * i], ai = a[2 * i + 1], br = b[2 * i], bi = b[2 * i + 1];
+        float p0 = ar * br, p1 = ai * bi, p2 = ar * bi, p3 = ai * br;
+        out[2 * i] = p0 - p1;
+        out[2 * i + 1] = p2 + p3;
+    }
+}
+ORC_API void orc_add_f(float* out, const float* a, const float* b, int64_t n_floats)
+{
+    for (int64_t i = 0; i < n_floats; i++)
+        out[i] = a[i] + b[i];
+}
+
 /* -------------------------------------------------------- complex_to_mag
  * y = sqrtf(re*re + im*im), fp32, not hypot (volk_32fc_magnitude_32f
  * semantics). */

@@ -9,6 +9,7 @@
 #include <gnuradio/blocklib/cuda/copy.hpp>
 #include <gnuradio/blocklib/cuda/fft.hpp>
 #include <gnuradio/blocklib/cuda/fir_filter.hpp>
+#include <gnuradio/blocklib/cuda/multiply.hpp>
 #include <gnuradio/blocklib/cuda/multiply_const.hpp>
 #include <gnuradio/blocklib/cuda/null_source.hpp>
 #include <gnuradio/blocklib/cuda/pfb_channelizer.hpp>
@@ -30,6 +31,8 @@ int orc_fft_f64(float*, const float*, int64_t, int, int, const float*, int);
 void orc_window_blackmanharris(float*, int);
 void orc_multiply_const_cc(float*, const float*, float, float, int64_t);
 void orc_complex_to_mag(float*, const float*, int64_t);
+void orc_multiply_cc(float*, const float*, const float*, int64_t);
+void orc_add_f(float*, const float*, const float*, int64_t);
 int64_t orc_pfb_channelizer_f64(float*, const float*, int64_t, const float*, int, int, const float*);
 }
 
@@ -360,6 +363,32 @@ QA_TEST(Config4, PfbChannelizer64)
     fg->run();
     EXPECT_EQ(snk->data().size(), exp.size());
     EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+}
+
+// two-input sync blocks: both inputs are clamped to the common minimum by sync_block::do_work
+QA_TEST(TwoInput, MultiplyAndAdd)
+{
+    auto a = noise(777777, 21), b = noise(777777, 22);
+    auto sa = blocks::vector_source_c::make(a);
+    auto sb = blocks::vector_source_c::make(b);
+    auto mul = cuda::multiply_cc::make();
+    auto add = cuda::add_cc::make();
+    auto snk_m = blocks::vector_sink_c::make(), snk_a = blocks::vector_sink_c::make();
+    auto fg = flowgraph::make();
+    fg->connect(sa, 0, mul, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 2u << 20));
+    fg->connect(sb, 0, mul, 1)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 4u << 20));
+    fg->connect(sa, 0, add, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 2u << 20));
+    fg->connect(sb, 0, add, 1)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 2u << 20));
+    fg->connect(mul, 0, snk_m, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 2u << 20));
+    fg->connect(add, 0, snk_a, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 2u << 20));
+    fg->set_scheduler(schedulers::scheduler_mt::make());
+    fg->validate();
+    fg->run();
+    std::vector<gr_complex> em(a.size()), ea(a.size());
+    orc_multiply_cc((float*)em.data(), (const float*)a.data(), (const float*)b.data(), (int64_t)a.size());
+    orc_add_f((float*)ea.data(), (const float*)a.data(), (const float*)b.data(), (int64_t)a.size() * 2);
+    EXPECT_EQ(snk_m->data(), em);
+    EXPECT_EQ(snk_a->data(), ea);
 }
 
 // stream tags survive device-resident edges (the reference's cuda_buffer breaks them: SURVEY.md 2.3)

@@ -115,6 +115,21 @@ def test_multiply_const_golden(cuda, golden):
     assert o.rel_rms(y, golden["mulc_y64"]) < TOL_EW
 
 
+@pytest.mark.parametrize("n", [1, 3, 4097, (1 << 20) + 5])
+def test_two_input_multiply_add(cuda, n):
+    import newsched_b200 as nb
+    rng = np.random.default_rng(n + 9)
+    a, b = cplx(rng, n + 1), cplx(rng, n + 1)
+    for off in (0, 1):
+        da, db = dev(cuda, a)[off:off + n], dev(cuda, b)[off:off + n]
+        assert np.array_equal(host(nb.multiply(da, db)), o.multiply(a[off:off + n], b[off:off + n]))
+        assert np.array_equal(host(nb.add(da, db)), o.add(a[off:off + n], b[off:off + n]))
+        ar, br = np.ascontiguousarray(a.real), np.ascontiguousarray(b.imag)
+        dar, dbr = dev(cuda, ar)[off:off + n], dev(cuda, br)[off:off + n]
+        assert np.array_equal(host(nb.multiply(dar, dbr)), o.multiply(ar[off:off + n], br[off:off + n]))
+        assert np.array_equal(host(nb.add(dar, dbr)), o.add(ar[off:off + n], br[off:off + n]))
+
+
 # --------------------------------------------------------------------- complex_to_mag
 @pytest.mark.parametrize("n", [1, 5, 4096, (1 << 20) + 3])
 def test_complex_to_mag(cuda, n):

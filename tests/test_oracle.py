@@ -32,6 +32,17 @@ def test_multiply_const_values(golden):
                           (xl.astype(np.int64) * 1000003).astype(np.int32))
 
 
+def test_two_input_blocks(golden):
+    x = golden["mulc_x"]
+    y = x[::-1].copy()
+    assert o.rel_rms(o.multiply(x, y), x.astype(np.complex128) * y.astype(np.complex128)) < 1e-6
+    assert np.array_equal(o.add(x, y), x + y)
+    assert np.array_equal(o.multiply(x.real.copy(), y.imag.copy()), x.real * y.imag)
+    # multiply by a constant vector == multiply_const
+    k = np.full(x.size, 0.5 - 0.25j, np.complex64)
+    assert np.array_equal(o.multiply(x, k), o.multiply_const(x, 0.5 - 0.25j))
+
+
 def test_complex_to_mag(golden):
     x = golden["mulc_x"]
     assert o.rel_rms(o.complex_to_mag(x), golden["mag_y64"]) < 1e-6
