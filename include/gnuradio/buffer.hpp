@@ -84,15 +84,20 @@ public:
         _tags.emplace_back(offset, key, value, srcid);
     }
     // copy the tags of the window the block just consumed from its input edge onto this (output)
-    // edge; called before post_write, so the window starts at total_written() of this edge
-    void propagate_tags(std::shared_ptr<buffer> in_buf, int n_consumed)
+    // edge; called before post_write, so the window starts at total_written() of this edge.
+    // For rate-changing blocks the relative position is scaled by n_produced / n_consumed
+    // ("decimation-scaled offsets"; the reference has no rate-change support).
+    void propagate_tags(std::shared_ptr<buffer> in_buf, int n_consumed, int n_produced = -1)
     {
         std::vector<tag_t> src = in_buf->get_tags((unsigned)std::max(n_consumed, 0));
         uint64_t in_base = in_buf->total_read();
         std::scoped_lock g(_buf_mutex);
         for (auto& t : src) {
             tag_t c = t;
-            c.offset = _total_written + (t.offset - in_base);
+            uint64_t rel = t.offset - in_base;
+            if (n_produced >= 0 && n_consumed > 0 && n_produced != n_consumed)
+                rel = rel * (uint64_t)n_produced / (uint64_t)n_consumed;
+            c.offset = _total_written + rel;
             _tags.push_back(c);
         }
     }

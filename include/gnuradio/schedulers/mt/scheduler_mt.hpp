@@ -168,7 +168,7 @@ class thread_wrapper : public neighbor_interface
                     if (pol == tag_propagation_policy_t::TPP_ALL_TO_ALL ||
                         (pol == tag_propagation_policy_t::TPP_ONE_TO_ONE && o == i))
                         for (auto& ob : _bufman->get_output_buffers(out_ports[o]))
-                            ob->propagate_tags(w.buffer, nc);
+                            ob->propagate_tags(w.buffer, nc, std::max(0, work_output[o].n_produced));
                 w.buffer->prune_tags(nc);
             }
             if (nc > 0) {

@@ -223,6 +223,33 @@ QA_TEST(SchedulerMTTags, PropagationPolicies)
     }
 }
 
+// tags through a rate-changing block land on the decimated offsets
+QA_TEST(SchedulerMTTags, DecimationScalesOffsets)
+{
+    const int D = 4;
+    std::vector<float> in(40000);
+    for (size_t i = 0; i < in.size(); i++)
+        in[i] = (float)i;
+    std::vector<tag_t> tags;
+    for (uint64_t off : { 0ull, 8ull, 4000ull, 39996ull })
+        tags.emplace_back(off, pmtf::make_string("k"), pmtf::make_int((int64_t)off));
+    auto src = blocks::vector_source_f::make(in, false, 1, tags);
+    auto dec = cpu_keep_one_in_n::make(D);
+    auto snk = blocks::vector_sink_f::make();
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, dec, 0);
+    fg->connect(dec, 0, snk, 0);
+    fg->set_scheduler(schedulers::scheduler_mt::make("s", 4096));
+    fg->validate();
+    fg->run();
+    auto got = snk->tags();
+    EXPECT_EQ(got.size(), tags.size());
+    bool ok = got.size() == tags.size();
+    for (size_t i = 0; ok && i < tags.size(); i++)
+        ok &= got[i].offset == tags[i].offset / D && pmtf::equal(got[i].value, tags[i].value);
+    EXPECT_TRUE(ok);
+}
+
 QA_TEST(Buffers, VmcircWindowIsLinear)
 {
     auto buf = vmcirc_buffer::make(1024, sizeof(int), nullptr);
