@@ -326,206 +326,6 @@ __global__ void __launch_bounds__(FIR_NT, 5)
     }
 }
 
-// ---- persistent, warp-specialised D == 1 kernel ------------------------------------------------
-// One producer warp keeps PS_STAGES input tiles in flight with TMA tensor loads (full/empty
-// mbarrier pair per stage); four consumer warps run the FFMA2 loop and never wait on global
-// memory.  Outputs leave through per-warp TMA tensor stores (32 rows each, double buffered), so
-// the consumer warps are not synchronised with each other at all in the steady state.  The few
-// edge tiles (stream start / ragged end) are staged and stored by the consumers by hand.
-constexpr int PS_STAGES = 2;
-constexpr int PS_THREADS = FIR_NT + 32;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void consumer_sync()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(FIR_NT) : "memory");
-}
-
-struct fir_ps_geom {
-    int Tm1, TQ;
-    int plane_rows, box_rows, n_boxes;
-    int stage_floats; // floats per input stage (multiple of 256)
-    long long full_rows, full_out_rows, n_in, n_out, n_tiles;
-};
-
-template <int VEC>
-__global__ void __launch_bounds__(PS_THREADS, 3)
-    fir_persist_kernel(const float* __restrict__ x, const float* __restrict__ hist, float* __restrict__ y,
-                       const float* __restrict__ taps_pp, const __grid_constant__ CUtensorMap tmap,
-                       const __grid_constant__ CUtensorMap tmap_out, fir_ps_geom gm, fir_epilogue ep)
-{
-    constexpr int R = FIR_ACC / VEC;
-    constexpr int CH = FIR_ACC / VEC;
-    constexpr int MT = FIR_NT * R;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + PS_STAGES;
-    float* hs = reinterpret_cast<float*>(smem_raw + 64);
-    const int TQ = gm.TQ;
-    float* stages;
-    {
-        uint32_t a = smem_u32(hs + TQ);
-        uint32_t aligned = (a + 1023u) & ~1023u;
-        stages = hs + TQ + (aligned - a) / 4;
-    }
-    float* outs = stages + PS_STAGES * gm.stage_floats; // 2 x (128 rows x 32 floats)
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    if (tid == 0) {
-        for (int i = 0; i < PS_STAGES; i++) {
-            mbar_init(full + i, 1);
-            mbar_init(empty + i, FIR_NT / 32);
-        }
-        fence_mbar_init();
-    }
-    for (int i = tid; i < TQ; i += PS_THREADS)
-        hs[i] = __ldg(taps_pp + i);
-    __syncthreads();
-
-    const long long my_tiles = (gm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const long long tma_rows = (long long)gm.box_rows * gm.n_boxes;
-    auto tile_of = [&](long long it) { return (long long)blockIdx.x + it * gridDim.x; };
-    auto tile_tma = [&](long long tile) {
-        const long long B0 = tile * MT - TQ;
-        return B0 >= 0 && B0 * VEC / 32 + tma_rows <= gm.full_rows;
-    };
-
-    if (warp == FIR_NT / 32) {
-        // ================= producer warp (one elected lane) =================
-        if (lane == 0) {
-            for (long long it = 0; it < my_tiles; it++) {
-                const int st = (int)(it % PS_STAGES);
-                const uint32_t k = (uint32_t)(it / PS_STAGES);
-                mbar_wait(empty + st, (k & 1) ^ 1);
-                const long long tile = tile_of(it);
-                if (tile_tma(tile)) {
-                    const long long row0 = (tile * MT - TQ) * VEC / 32;
-                    mbar_arrive_expect_tx(full + st, (uint32_t)tma_rows * 128u);
-                    for (int bx = 0; bx < gm.n_boxes; bx++)
-                        tma_load_2d(stages + (size_t)st * gm.stage_floats + (size_t)bx * gm.box_rows * 32, &tmap, 0,
-                                    (int)(row0 + (long long)bx * gm.box_rows), full + st);
-                } else {
-                    mbar_arrive(full + st); // edge tile: the consumers stage it themselves
-                }
-            }
-        }
-        return;
-    }
-
-    // ================= consumer warps =================
-    const int nsteps = TQ / CH;
-    for (long long it = 0; it < my_tiles; it++) {
-        const int st = (int)(it % PS_STAGES);
-        const uint32_t k = (uint32_t)(it / PS_STAGES);
-        const long long tile = tile_of(it);
-        float* plane = stages + (size_t)st * gm.stage_floats;
-        mbar_wait(full + st, k & 1);
-        if (!tile_tma(tile)) {
-            // edge tile: coalesced register-staged loads into the swizzled layout
-            const long long g_lo = tile * MT - TQ;
-            const int total = (gm.plane_rows << 5) / VEC;
-            for (int i0 = tid; i0 < total; i0 += FIR_NT * 8) {
-                float v[8][2];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + u * FIR_NT < total)
-                        fir_fetch<VEC>(x, hist, gm.Tm1, g_lo + i0 + u * FIR_NT, gm.n_in, v[u]);
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + u * FIR_NT;
-                    if (i < total) {
-                        float* dst = plane + swz(i * VEC);
-                        if (VEC == 2)
-                            *reinterpret_cast<float2*>(dst) = make_float2(v[u][0], v[u][1]);
-                        else
-                            dst[0] = v[u][0];
-                    }
-                }
-            }
-            consumer_sync();
-        }
-        float acc[FIR_ACC];
-#pragma unroll
-        for (int l = 0; l < FIR_ACC; l++)
-            acc[l] = 0.f;
-        float W[FIR_RING];
-        fir_load_half<0>(W, plane, tid);
-        for (int b = 0; b < nsteps; b += 2) {
-            fir_load_half<1>(W, plane, tid + b + 1);
-            fir_step<VEC, CH, 0>(acc, W, hs + b * CH);
-            fir_load_half<0>(W, plane, tid + b + 2);
-            fir_step<VEC, CH, 32>(acc, W, hs + (b + 1) * CH);
-        }
-        // this warp is done with the stage: hand it back to the producer
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(empty + st);
-
-        if (ep.fuse) {
-            if (VEC == 2) {
-#pragma unroll
-                for (int l = 0; l < FIR_ACC; l += 2) {
-                    float2 v = cmul_nofma(make_float2(acc[l], acc[l + 1]), ep.kre, ep.kim);
-                    acc[l] = v.x;
-                    acc[l + 1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int l = 0; l < FIR_ACC; l++)
-                    acc[l] = __fmul_rn(acc[l], ep.kre);
-            }
-        }
-        // ---- outputs: this warp's 32 rows -> swizzled smem -> one TMA tensor store
-        float* ob = outs + (size_t)(it & 1) * (FIR_NT * 32);
-        if (lane == 0) // the store issued two tiles ago (same buffer) must have finished reading
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        {
-            float* rb = ob + (tid << 5);
-            const int s = (tid & 7) << 2;
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                *reinterpret_cast<float4*>(rb + ((j << 2) ^ s)) =
-                    make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-        const long long orow0 = tile * FIR_NT + warp * 32;
-        if (orow0 + 32 <= gm.full_out_rows) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                                 &tmap_out),
-                             "r"(0), "r"((int)orow0), "r"(smem_u32(ob + (warp << 10)))
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        } else {
-            // ragged end: warp-local coalesced stores with bounds checks
-            __syncwarp();
-            const long long m0 = tile * MT + (long long)warp * 32 * R;
-            for (int i = lane; i < 32 * R; i += 32) {
-                const long long m = m0 + i;
-                if (m >= gm.n_out)
-                    break;
-                const float* src = ob + swz((warp * 32 * R + i) * VEC);
-                if (VEC == 2)
-                    __stcs(reinterpret_cast<float2*>(y) + m, *reinterpret_cast<const float2*>(src));
-                else
-                    __stcs(y + m, src[0]);
-            }
-            if (lane == 0)
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory"); // keep the group count in step
-            __syncwarp();
-        }
-    }
-    if (lane == 0)
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 // Fallback for parameter combinations the tiled kernel cannot stage (very large D):
 // one thread per output straight from global memory.
 template <int VEC>
@@ -578,11 +378,6 @@ struct b200_fir {
     int plane_rows = 0, box_rows = 0, n_boxes = 0; // smem plane geometry (rows of 128 B)
     size_t smem = 0;
     int use_tma = 1;
-    int persist = 0;       // persistent warp-specialised kernel for D == 1 (B200_FIR_PERSIST=1):
-                           // measured 9 % SLOWER than the one-tile-per-CTA kernel at 64 taps (3 CTAs/SM
-                           // x 4 consumer warps hide LDS latency worse than 6 x 4), kept as an experiment
-    size_t ps_smem = 0;
-    int ps_stage_floats = 0, ps_grid = 0;
     ols_plan* ols = nullptr; // algorithm 3
     int algorithm = 1;
     fir_epilogue ep{ 0, 1.f, 0.f };
@@ -672,32 +467,6 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
             gm.tma_out_ok = 1;
         }
         const bool decim = h->D > 1;
-        if (!decim && h->persist && gm.tma_ok && (uintptr_t)d_out % 16 == 0 && gm.full_out_rows >= 32) {
-            CUtensorMap tmap_o32;
-            int rc = fir_make_tmap(&tmap_o32, d_out, gm.full_out_rows, 32);
-            if (rc != B200_OK)
-                return rc;
-            fir_ps_geom pg{};
-            pg.Tm1 = h->T - 1;
-            pg.TQ = h->TQ;
-            pg.plane_rows = h->plane_rows;
-            pg.box_rows = h->box_rows;
-            pg.n_boxes = h->n_boxes;
-            pg.stage_floats = h->ps_stage_floats;
-            pg.full_rows = gm.full_rows;
-            pg.full_out_rows = gm.full_out_rows;
-            pg.n_in = n_in;
-            pg.n_out = n_out;
-            pg.n_tiles = tiles;
-            long long g = tiles < h->ps_grid ? tiles : h->ps_grid;
-            if (h->vec == 2)
-                B200_LAUNCH((fir_persist_kernel<2>), (unsigned)g, PS_THREADS, h->ps_smem, s, x, d_hist, y,
-                            h->d_taps_pp, tmap, tmap_o32, pg, h->ep);
-            else
-                B200_LAUNCH((fir_persist_kernel<1>), (unsigned)g, PS_THREADS, h->ps_smem, s, x, d_hist, y,
-                            h->d_taps_pp, tmap, tmap_o32, pg, h->ep);
-            return B200_OK;
-        }
         if (h->vec == 2) {
             if (decim)
                 B200_LAUNCH((fir_direct_kernel<2, true>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
@@ -770,12 +539,6 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     h->smem = 16 + sizeof(float) * ((size_t)h->D * h->TQ + (size_t)h->D * (h->plane_rows * 32 + 8)) + 1024;
     if (const char* e = getenv("B200_FIR_TMA"))
         h->use_tma = atoi(e);
-    if (const char* e = getenv("B200_FIR_PERSIST"))
-        h->persist = atoi(e);
-    h->ps_stage_floats = (h->plane_rows * 32 + 255) / 256 * 256;
-    h->ps_smem = 64 + sizeof(float) * ((size_t)h->TQ + (size_t)PS_STAGES * h->ps_stage_floats + 2 * FIR_NT * 32) + 1024;
-    if (h->ps_smem > 220 * 1024 || h->D != 1)
-        h->persist = 0;
     h->algorithm = 1;
     if (h->smem > 200 * 1024 || p->algorithm == 4)
         h->algorithm = 4; // naive global-memory fallback
@@ -843,23 +606,6 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
             FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<1, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
-    }
-    if (h->algorithm == 1 && h->persist) {
-        int per_sm = 0;
-        if (h->vec == 2) {
-            FIR_CUDA(cudaFuncSetAttribute(fir_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)h->ps_smem));
-            FIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_persist_kernel<2>, PS_THREADS,
-                                                                   h->ps_smem));
-        } else {
-            FIR_CUDA(cudaFuncSetAttribute(fir_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)h->ps_smem));
-            FIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_persist_kernel<1>, PS_THREADS,
-                                                                   h->ps_smem));
-        }
-        if (const char* e = getenv("B200_FIR_PERSIST_CTAS"))
-            per_sm = std::min(per_sm, atoi(e));
-        h->ps_grid = std::max(1, per_sm) * sm_count();
     }
 #undef FIR_CUDA
     *out = h;
