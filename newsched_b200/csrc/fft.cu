@@ -368,6 +368,126 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---- N = 16, 32, 64, 128: two passes (radix R0 then radix 16), N = R0 * 16 ----------------------
+// Same block shape again: a CTA transforms 4096 contiguous samples = 4096/N vectors staged by one
+// TMA bulk copy.  Pass 1: each thread does 16/R0 radix-R0 butterflies (over n2, n = 16 n2 + n0) and
+// applies W_N^{n0 k0}; pass 2: thread p = (vector, k0) does the DFT16 over n0.  k = k0 + R0 k1.
+// Results go through a padded shared tile so the global stores are fully coalesced even for N = 16.
+template <int R0>
+struct fsm {
+    static constexpr int N = R0 * 16;
+    static constexpr int V = 4096 / N;        // vectors per block
+    static constexpr int OS = N + R0;         // padded output row (keeps the scatter conflict-free)
+    static constexpr size_t SMEM = 4096 * 8 + 256 * 17 * 8 + (size_t)V * OS * 8 + 128 * 8 + 128 * 4 + 16;
+};
+
+template <int R0, bool FWD, int OUT>
+__global__ void __launch_bounds__(256, 2)
+    fft_small_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec,
+                     const float* __restrict__ weff, const float2* __restrict__ tw /* [k0][n0] */, int flip,
+                     int tma_ok)
+{
+    using G = fsm<R0>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sIn = reinterpret_cast<float2*>(smem_raw);
+    float2* sA = sIn + 4096;
+    float2* sO = sA + 256 * 17;
+    float2* sTw = sO + G::V * G::OS;
+    float* sW = reinterpret_cast<float*>(sTw + 128);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sW + 128);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < G::N) {
+        sW[tid] = __ldg(weff + tid);
+        sTw[tid] = __ldg(tw + tid);
+    }
+    __syncthreads();
+    const long long n_blocks = (n_vec + G::V - 1) / G::V;
+    auto tma_block = [&](long long b) { return tma_ok && (b + 1) * G::V <= n_vec; };
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < n_blocks && tma_block(blk)) {
+        mbar_arrive_expect_tx(bar, 4096 * 8);
+        bulk_copy_g2s(sIn, in + blk * 4096, 4096 * 8, bar);
+    }
+    uint32_t phase = 0;
+    for (; blk < n_blocks; blk += gridDim.x) {
+        const long long vec0 = blk * G::V;
+        const bool staged = tma_block(blk);
+        if (staged) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        // ---- pass 1: butterflies beta = j*256 + tid -> (vector, n0)
+#pragma unroll
+        for (int j = 0; j < 16 / R0; j++) {
+            const int beta = j * 256 + tid;
+            const int vv = beta >> 4, n0 = beta & 15;
+            float2 z[R0];
+#pragma unroll
+            for (int n2 = 0; n2 < R0; n2++) {
+                const int e = vv * G::N + n2 * 16 + n0;
+                float2 xv;
+                if (staged)
+                    xv = sIn[e];
+                else
+                    xv = (vec0 + vv < n_vec) ? __ldcs(in + blk * 4096 + e) : make_float2(0.f, 0.f);
+                const float w = sW[n2 * 16 + n0];
+                z[n2] = __fmul2_rn(xv, make_float2(w, w));
+            }
+            if (R0 == 2)
+                dft2<FWD>(z[0], z[R0 > 1 ? 1 : 0]);
+            if (R0 == 4)
+                dft4<FWD>(z[0], z[R0 > 1 ? 1 : 0], z[R0 > 2 ? 2 : 0], z[R0 > 3 ? 3 : 0]);
+            if (R0 == 8)
+                dft8<FWD>(reinterpret_cast<float2(&)[8]>(z));
+#pragma unroll
+            for (int k0 = 0; k0 < R0; k0++)
+                sA[(vv * R0 + k0) * 17 + n0] = cmul(z[k0], sTw[k0 * 16 + n0]);
+        }
+        __syncthreads(); // sA complete, sIn consumed
+        if (tid == 0 && blk + gridDim.x < n_blocks && tma_block(blk + gridDim.x)) {
+            mbar_arrive_expect_tx(bar, 4096 * 8);
+            bulk_copy_g2s(sIn, in + (blk + gridDim.x) * 4096, 4096 * 8, bar);
+        }
+        // ---- pass 2: thread p = vector*R0 + k0, DFT16 over n0
+        {
+            float2 v[16];
+            const float2* row = sA + tid * 17;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i];
+            dft16<FWD>(v);
+            const int vv = tid / R0, k0 = tid % R0;
+            float2* orow = sO + vv * G::OS + k0;
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++)
+                orow[k1 * R0] = v[pos16(k1)];
+        }
+        __syncthreads();
+        // ---- coalesced copy-out of the 4096 results (natural order within each vector)
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int e = i * 256 + tid;
+            const int vv = e / G::N, k = e % G::N;
+            if (vec0 + vv < n_vec) {
+                float2 z = sO[vv * G::OS + k];
+                if (OUT == B200_FFT_OUT_COMPLEX) {
+                    if (flip && (k & 1))
+                        z = make_float2(-z.x, -z.y);
+                    __stcs(reinterpret_cast<float2*>(out) + blk * 4096 + e, z);
+                } else {
+                    float p = fmaf(z.x, z.x, z.y * z.y);
+                    __stcs(reinterpret_cast<float*>(out) + blk * 4096 + e, OUT == B200_FFT_OUT_MAG ? sqrt_approx(p) : p);
+                }
+            }
+        }
+        __syncthreads(); // sO / sA free for the next block
+    }
+}
+
 // ---- generic power-of-two radix-2 Stockham (N = 8 .. 8192) ----------------------------------
 template <bool FWD, int OUT>
 __global__ void __launch_bounds__(512)
@@ -460,6 +580,21 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
         else
             B200_LAUNCH((fft4096_kernel<FWD, OUT>), (unsigned)g, 256, 0, s, (const float2*)d_in, d_out,
                         n_vec, h->d_weff, h->d_tw1, h->d_tw2);
+    } else if (h->N == 16 || h->N == 32 || h->N == 64 || h->N == 128) {
+        const int R0 = h->N / 16, V = 4096 / h->N;
+        long long nb = (n_vec + V - 1) / V;
+        long long g = nb < h->grid_4k ? nb : h->grid_4k;
+        const int tma_ok = (uintptr_t)d_in % 16 == 0;
+#define FFT_SM_GO(R)                                                                                     \
+    B200_LAUNCH((fft_small_kernel<R, FWD, OUT>), (unsigned)g, 256, fsm<R>::SMEM, s, (const float2*)d_in, \
+                d_out, n_vec, h->d_weff, h->d_tw1, h->flip, tma_ok)
+        switch (R0) {
+        case 1: FFT_SM_GO(1); break;
+        case 2: FFT_SM_GO(2); break;
+        case 4: FFT_SM_GO(4); break;
+        default: FFT_SM_GO(8); break;
+        }
+#undef FFT_SM_GO
     } else if (h->N == 256 || h->N == 512 || h->N == 1024 || h->N == 2048) {
         const int R0 = h->N / 256, V = 16 / R0;
         long long nb = (n_vec + V - 1) / V;
@@ -525,6 +660,24 @@ static cudaError_t fft_r0_attr_all()
     if ((e = fft_r0_attr<R0, false, 0>()) != cudaSuccess) return e;
     if ((e = fft_r0_attr<R0, false, 1>()) != cudaSuccess) return e;
     return fft_r0_attr<R0, false, 2>();
+}
+
+template <int R0, bool FWD, int OUT>
+static cudaError_t fft_small_attr()
+{
+    return cudaFuncSetAttribute(fft_small_kernel<R0, FWD, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)fsm<R0>::SMEM);
+}
+template <int R0>
+static cudaError_t fft_small_attr_all()
+{
+    cudaError_t e = cudaSuccess;
+    if ((e = fft_small_attr<R0, true, 0>()) != cudaSuccess) return e;
+    if ((e = fft_small_attr<R0, true, 1>()) != cudaSuccess) return e;
+    if ((e = fft_small_attr<R0, true, 2>()) != cudaSuccess) return e;
+    if ((e = fft_small_attr<R0, false, 0>()) != cudaSuccess) return e;
+    if ((e = fft_small_attr<R0, false, 1>()) != cudaSuccess) return e;
+    return fft_small_attr<R0, false, 2>();
 }
 
 template <bool FWD, int OUT>
@@ -637,6 +790,24 @@ int b200_fft_create(const b200_fft_params* p, b200_fft** out)
         FFT_CUDA((fft_tma_attr<false, 0>()));
         FFT_CUDA((fft_tma_attr<false, 1>()));
         FFT_CUDA((fft_tma_attr<false, 2>()));
+    } else if (N == 16 || N == 32 || N == 64 || N == 128) {
+        const int R0 = N / 16;
+        std::vector<float2> t1((size_t)R0 * 16);
+        for (int k0 = 0; k0 < R0; k0++)
+            for (int n0 = 0; n0 < 16; n0++) {
+                double ang = sgn * 2.0 * M_PI * (double)(n0 * k0) / (double)N;
+                double wr = std::cos(ang), wi = std::sin(ang);
+                t1[(size_t)k0 * 16 + n0] =
+                    make_float2((float)(wr * kph_re - wi * kph_im), (float)(wr * kph_im + wi * kph_re));
+            }
+        FFT_CUDA(cudaMalloc(&h->d_tw1, sizeof(float2) * 128));
+        FFT_CUDA(cudaMemset(h->d_tw1, 0, sizeof(float2) * 128));
+        FFT_CUDA(cudaMemcpy(h->d_tw1, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
+        h->grid_4k = 2 * sm_count();
+        FFT_CUDA(fft_small_attr_all<1>());
+        FFT_CUDA(fft_small_attr_all<2>());
+        FFT_CUDA(fft_small_attr_all<4>());
+        FFT_CUDA(fft_small_attr_all<8>());
     } else if (N == 256 || N == 512 || N == 1024 || N == 2048) {
         const int R0 = N / 256;
         std::vector<float2> t1((size_t)R0 * 256), t2(256);

@@ -359,7 +359,7 @@ def test_fft4096_golden(cuda, golden, key, fwd, shift):
         assert o.rel_rms(y[v * 4096:(v + 1) * 4096], golden[key][v * 4096:(v + 1) * 4096]) < TOL_RMS
 
 
-@pytest.mark.parametrize("N", [8, 16, 64, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("N", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
 @pytest.mark.parametrize("fwd", [True, False])
 def test_fft_matches_oracle(cuda, N, fwd):
     import newsched_b200 as nb
@@ -391,7 +391,7 @@ def test_fft_impulse_tone_exact_structure(cuda):
     assert int(np.argmax(np.abs(ys))) == (k0 + N // 2) % N   # DC lands on N/2
 
 
-@pytest.mark.parametrize("N", [64, 256, 1024, 2048, 4096])
+@pytest.mark.parametrize("N", [16, 64, 128, 256, 1024, 2048, 4096])
 def test_fft_mag_fused_and_premultiply(cuda, golden, N):
     import newsched_b200 as nb
     rng = np.random.default_rng(N + 1)
