@@ -40,6 +40,9 @@ public:
         return sync_block::done();
     }
 
+    size_t vlen() const { return d_vlen; }
+    bool squared() const { return d_squared; }
+
 private:
     size_t d_vlen;
     bool d_squared;

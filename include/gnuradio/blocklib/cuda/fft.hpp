@@ -38,7 +38,9 @@ public:
     }
     fft(size_t fft_size, bool forward, const std::vector<float>& window, bool shift, fft_output_t output,
         bool stream_input, bool fuse_pre, gr_complex k)
-        : block("fft"), d_n(fft_size), d_in_per_vec(stream_input ? fft_size : 1)
+        : block("fft"), d_n(fft_size), d_in_per_vec(stream_input ? fft_size : 1), d_forward(forward),
+          d_window(window), d_shift(shift), d_output(output), d_stream_input(stream_input), d_fuse_pre(fuse_pre),
+          d_k(k)
     {
         if (!window.empty() && window.size() != fft_size)
             throw std::invalid_argument("fft: window must have fft_size entries");
@@ -76,8 +78,24 @@ public:
         return block::done();
     }
 
+    // parameters (used by the fusion pass to rebuild the block with a fused neighbour)
+    size_t fft_size() const { return d_n; }
+    bool forward() const { return d_forward; }
+    const std::vector<float>& window() const { return d_window; }
+    bool shift() const { return d_shift; }
+    fft_output_t output() const { return d_output; }
+    bool stream_input() const { return d_stream_input; }
+    bool fused_pre_multiply_const() const { return d_fuse_pre; }
+    gr_complex pre_multiply_const() const { return d_k; }
+
 private:
     size_t d_n, d_in_per_vec;
+    bool d_forward;
+    std::vector<float> d_window;
+    bool d_shift;
+    fft_output_t d_output;
+    bool d_stream_input, d_fuse_pre;
+    gr_complex d_k;
     b200_fft* d_fft = nullptr;
 };
 

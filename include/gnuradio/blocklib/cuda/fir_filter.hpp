@@ -44,6 +44,7 @@ public:
         build();
     }
     std::vector<float> taps() const { return d_taps; }
+    bool has_fused_multiply_const() const { return d_fuse; }
     size_t decimation() const { return d_decim; }
 
     work_return_code_t work(std::vector<block_work_input>& work_input,

@@ -42,6 +42,7 @@ public:
         return sync_block::done();
     }
     T k() const { return d_k; }
+    size_t vlen() const { return d_vlen; }
 
 private:
     int launch(void* out, const void* in, size_t noi);

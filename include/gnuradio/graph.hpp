@@ -51,6 +51,36 @@ public:
         return connect(node_endpoint(src_node, src_node->get_port(src_port_name)),
                        node_endpoint(dst_node, dst_node->get_port(dst_port_name)));
     }
+    // remove one edge (graph rewriting before validate(): see gnuradio/blocklib/cuda/fusion.hpp)
+    void disconnect(edge_sptr e)
+    {
+        _edges.erase(std::remove(_edges.begin(), _edges.end(), e), _edges.end());
+        e->src().port()->disconnect(e->dst().port());
+        e->dst().port()->disconnect(e->src().port());
+        for (auto n : { e->src().node(), e->dst().node() }) {
+            bool used = false;
+            for (auto& o : _edges)
+                used |= (o->src().node() == n || o->dst().node() == n);
+            if (!used)
+                _nodes.erase(std::remove(_nodes.begin(), _nodes.end(), n), _nodes.end());
+        }
+    }
+    edge_vector_t out_edges(node_sptr n)
+    {
+        edge_vector_t r;
+        for (auto& e : _edges)
+            if (e->src().node() == n)
+                r.push_back(e);
+        return r;
+    }
+    edge_vector_t in_edges(node_sptr n)
+    {
+        edge_vector_t r;
+        for (auto& e : _edges)
+            if (e->dst().node() == n)
+                r.push_back(e);
+        return r;
+    }
     node_vector_t calc_used_nodes() { return _nodes; }
     block_vector_t calc_used_blocks()
     {

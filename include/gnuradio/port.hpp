@@ -59,6 +59,12 @@ public:
             _connected_ports.push_back(other);
     }
 
+    void disconnect(sptr other)
+    {
+        _connected_ports.erase(std::remove(_connected_ports.begin(), _connected_ports.end(), other),
+                               _connected_ports.end());
+    }
+
 protected:
     std::string _name, _alias;
     port_direction_t _direction;

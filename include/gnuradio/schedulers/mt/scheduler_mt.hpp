@@ -24,6 +24,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <exception>
 #include <map>
 #include <thread>
 
@@ -74,6 +75,7 @@ class thread_wrapper : public neighbor_interface
     std::condition_variable _cv;
     bool _notified = false;
     std::atomic<bool> _stop{ false }, _started{ false };
+    std::exception_ptr _error = nullptr;
 
     void finish_block(size_t bi)
     {
@@ -208,6 +210,25 @@ class thread_wrapper : public neighbor_interface
 
     void thread_body()
     {
+        try {
+            thread_loop();
+        } catch (...) {
+            // a block threw (e.g. a CUDA error surfaced through the C-ABI): remember it for wait()
+            // and release everybody else instead of std::terminate (the reference has no handler,
+            // SURVEY.md section 5 "Failure detection")
+            _error = std::current_exception();
+            for (size_t bi = 0; bi < _blocks.size(); bi++)
+                if (!_finished[bi]) {
+                    try {
+                        finish_block(bi);
+                    } catch (...) {
+                    }
+                }
+        }
+    }
+
+    void thread_loop()
+    {
         while (!_stop.load()) {
             bool any_ready = false, all_finished = true;
             for (size_t bi = 0; bi < _blocks.size(); bi++) {
@@ -260,6 +281,7 @@ public:
         if (_thread.joinable())
             _thread.join();
     }
+    std::exception_ptr error() const { return _error; }
 };
 
 class scheduler_mt : public scheduler
@@ -323,6 +345,9 @@ public:
     {
         for (auto& t : _threads)
             t->wait();
+        for (auto& t : _threads)
+            if (t->error())
+                std::rethrow_exception(t->error()); // first failure, after every thread has stopped
     }
 };
 

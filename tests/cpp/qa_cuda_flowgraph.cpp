@@ -9,6 +9,7 @@
 #include <gnuradio/blocklib/cuda/copy.hpp>
 #include <gnuradio/blocklib/cuda/fft.hpp>
 #include <gnuradio/blocklib/cuda/fir_filter.hpp>
+#include <gnuradio/blocklib/cuda/fusion.hpp>
 #include <gnuradio/blocklib/cuda/multiply.hpp>
 #include <gnuradio/blocklib/cuda/multiply_const.hpp>
 #include <gnuradio/blocklib/cuda/null_source.hpp>
@@ -337,6 +338,63 @@ QA_TEST(Config3, FirMulFftChain)
         EXPECT_EQ(snk->data().size(), exp.size());
         EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
     }
+}
+
+// the graph-rewriting fusion pass: fir -> multiply_const -> fft -> complex_to_mag collapses to
+// two blocks (FIR with fused k, FFT with fused |.|) and still matches the oracle of the 4-block chain
+QA_TEST(Fusion, AdjacentBlocksCollapse)
+{
+    const int N = 4096, T = 200, D = 4;
+    auto in = noise((size_t)N * D * 24, 31);
+    auto taps = rtaps(T, 32);
+    gr_complex k(0.5f, -0.25f);
+    std::vector<float> w(N);
+    orc_window_blackmanharris(w.data(), N);
+    std::vector<gr_complex> a(in.size() / D), b(a.size()), X(a.size());
+    orc_fir_ccf_f64((float*)a.data(), (const float*)in.data(), (int64_t)in.size(), taps.data(), T, D, nullptr);
+    orc_multiply_const_cc((float*)b.data(), (const float*)a.data(), k.real(), k.imag(), (int64_t)a.size());
+    orc_fft_f64((float*)X.data(), (const float*)b.data(), (int64_t)(b.size() / N), N, 1, w.data(), 0);
+    std::vector<float> exp(X.size());
+    for (size_t i = 0; i < X.size(); i++)
+        exp[i] = (float)std::abs(std::complex<double>(X[i]));
+
+    auto src = blocks::vector_source_c::make(in);
+    auto fir = cuda::fir_filter_ccf::make(D, taps);
+    auto mul = cuda::multiply_const_cc::make(k);
+    auto f = cuda::fft::make(N, true, w, false, cuda::fft_output_t::COMPLEX, /*stream_input=*/true);
+    auto mag = cuda::complex_to_mag::make(N);
+    auto snk = blocks::vector_sink_f::make(N);
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, fir, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_H2D);
+    fg->connect(fir, 0, mul, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2D);
+    fg->connect(mul, 0, f, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2D);
+    fg->connect(f, 0, mag, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2D);
+    fg->connect(mag, 0, snk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2H);
+    EXPECT_EQ(fg->calc_used_blocks().size(), (size_t)6);
+    int n = cuda::fuse_adjacent(*fg);
+    EXPECT_EQ(n, 2);                                       // fir+mul, fft+mag
+    EXPECT_EQ(fg->calc_used_blocks().size(), (size_t)4);   // src, fir, fft, sink
+    EXPECT_EQ(fg->edges().size(), (size_t)3);
+    for (auto& e : fg->edges())
+        EXPECT_TRUE(e->has_custom_buffer());               // device edges survive the rewrite
+    fg->set_scheduler(schedulers::scheduler_mt::make());
+    fg->validate();
+    fg->run();
+    EXPECT_EQ(snk->data().size(), exp.size());
+    EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+
+    // a fanned-out intermediate stream must NOT be fused away
+    auto src2 = blocks::vector_source_c::make(in, false, N);
+    auto f2 = cuda::fft::make(N, true, w);
+    auto mag2 = cuda::complex_to_mag::make(N);
+    auto tap2 = blocks::vector_sink_c::make(N);
+    auto snk2 = blocks::vector_sink_f::make(N);
+    auto fg2 = flowgraph::make();
+    fg2->connect(src2, 0, f2, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_H2D);
+    fg2->connect(f2, 0, mag2, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2D);
+    fg2->connect(f2, 0, tap2, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2H);
+    fg2->connect(mag2, 0, snk2, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_D2H);
+    EXPECT_EQ(cuda::fuse_adjacent(*fg2), 0);
 }
 
 // BASELINE config 4 (single GPU slice): 64-channel polyphase channelizer in a flowgraph

@@ -250,6 +250,50 @@ QA_TEST(SchedulerMTTags, DecimationScalesOffsets)
     EXPECT_TRUE(ok);
 }
 
+// a throwing block must end the flowgraph and surface in wait(), not abort the process
+class cpu_thrower : public sync_block
+{
+    int calls = 0;
+
+public:
+    static std::shared_ptr<cpu_thrower> make()
+    {
+        auto p = std::make_shared<cpu_thrower>();
+        p->add_port(port<float>::make("input", port_direction_t::INPUT));
+        p->add_port(port<float>::make("output", port_direction_t::OUTPUT));
+        return p;
+    }
+    cpu_thrower() : sync_block("thrower") {}
+    work_return_code_t work(std::vector<block_work_input>& in, std::vector<block_work_output>& out) override
+    {
+        if (++calls > 3)
+            throw std::runtime_error("device fell off the bus");
+        memcpy(out[0].buffer->write_ptr(), in[0].buffer->read_ptr(), sizeof(float) * out[0].n_items);
+        out[0].n_produced = out[0].n_items;
+        return work_return_code_t::WORK_OK;
+    }
+};
+
+QA_TEST(SchedulerMTTest, BlockExceptionSurfacesInWait)
+{
+    auto src = blocks::null_source::make(sizeof(float)); // endless
+    auto thr = cpu_thrower::make();
+    auto snk = blocks::null_sink::make(sizeof(float));
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, thr, 0);
+    fg->connect(thr, 0, snk, 0);
+    fg->set_scheduler(schedulers::scheduler_mt::make());
+    fg->validate();
+    fg->start();
+    bool caught = false;
+    try {
+        fg->wait();
+    } catch (const std::runtime_error& e) {
+        caught = std::string(e.what()).find("fell off") != std::string::npos;
+    }
+    EXPECT_TRUE(caught);
+}
+
 QA_TEST(Buffers, VmcircWindowIsLinear)
 {
     auto buf = vmcirc_buffer::make(1024, sizeof(int), nullptr);
