@@ -545,7 +545,7 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     // overlap-save fast convolution: complex streams, enough taps per output to pay for two
     // FFTs per block (crossover measured on B200: ~100 taps per output sample)
     {
-        const bool can = h->vec == 2 && ols_supported(h->T, h->D);
+        const bool can = ols_supported(h->T, h->D, h->vec == 1);
         bool want = (p->algorithm == 3);
         if (p->algorithm == 0 && can && h->T / h->D >= 96)
             want = true;
@@ -554,10 +554,10 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
                 want = atoi(e) == 3;
         if (want && !can && p->algorithm == 3) {
             b200_fir_destroy(h);
-            return set_err(B200_ERR_UNSUPPORTED, "fir_create: overlap-save needs a complex stream and 2..32768 taps");
+            return set_err(B200_ERR_UNSUPPORTED, "fir_create: overlap-save needs 2..32768 taps");
         }
         if (want && can) {
-            int rc = ols_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->ols);
+            int rc = ols_create(p->taps, h->T, h->D, h->vec == 1, h->ep.fuse, h->ep.kre, h->ep.kim, &h->ols);
             if (rc != B200_OK) {
                 b200_fir_destroy(h);
                 return rc;

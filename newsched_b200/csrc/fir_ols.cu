@@ -51,6 +51,16 @@ __device__ __forceinline__ float2 ols_fetch(const float2* __restrict__ x, const 
     return make_float2(0.f, 0.f);
 }
 
+__device__ __forceinline__ float ols_fetch_real(const float* __restrict__ x, const float* __restrict__ hist,
+                                                int Tm1, long long g, long long n_in)
+{
+    if (g >= 0)
+        return g < n_in ? __ldg(x + g) : 0.f;
+    if (hist && g >= -(long long)Tm1)
+        return __ldg(hist + (Tm1 + g));
+    return 0.f;
+}
+
 // three radix-16 passes over registers v[] (natural order in, X[tid + 256 j] in v[pos16(j)] out)
 template <bool FWD>
 __device__ __forceinline__ void fft4096_passes(float2 (&v)[16], float2* sA, const float2* sT2,
@@ -84,6 +94,10 @@ __device__ __forceinline__ void fft4096_passes(float2 (&v)[16], float2* sA, cons
     }
 }
 
+// REAL = true: float stream (fff).  Real taps commute with re/im, so TWO consecutive real blocks ride
+// through one complex transform as (block A) + j (block B): twice the sample rate of the complex
+// path for the same arithmetic.
+template <bool REAL>
 __global__ void __launch_bounds__(256, 2)
     fir_ols4096_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, float2* __restrict__ y,
                        const float2* __restrict__ Htab, const float2* __restrict__ tw1,
@@ -106,16 +120,28 @@ __global__ void __launch_bounds__(256, 2)
     sT2[tid] = __ldg(tw2 + tid);
     __syncthreads();
 
-    auto seg_start = [&](long long b) { return b * g.V - g.Ov - g.shift; };
+    // a "block" is one complex transform: one segment of the complex stream, or two consecutive
+    // segments (A, B = A + V) of the real stream
+    constexpr int SEGS = REAL ? 2 : 1;
+    auto seg_start = [&](long long b) { return b * SEGS * g.V - g.Ov - g.shift; };
     auto tma_block = [&](long long b) {
         const long long s = seg_start(b);
-        return g.tma_ok && s >= 0 && s + OLS_N <= g.n_in;
+        return g.tma_ok && s >= 0 && s + (SEGS - 1) * g.V + OLS_N <= g.n_in;
+    };
+    auto issue = [&](long long b) { // one elected thread
+        mbar_arrive_expect_tx(bar, OLS_N * 8);
+        if (REAL) {
+            const float* xr = reinterpret_cast<const float*>(x);
+            float* sf = reinterpret_cast<float*>(sIn);
+            bulk_copy_g2s(sf, xr + seg_start(b), OLS_N * 4, bar);
+            bulk_copy_g2s(sf + OLS_N, xr + seg_start(b) + g.V, OLS_N * 4, bar);
+        } else {
+            bulk_copy_g2s(sIn, x + seg_start(b), OLS_N * 8, bar);
+        }
     };
     long long blk = blockIdx.x;
-    if (tid == 0 && blk < g.n_blocks && tma_block(blk)) {
-        mbar_arrive_expect_tx(bar, OLS_N * 8);
-        bulk_copy_g2s(sIn, x + seg_start(blk), OLS_N * 8, bar);
-    }
+    if (tid == 0 && blk < g.n_blocks && tma_block(blk))
+        issue(blk);
     uint32_t phase = 0;
     for (; blk < g.n_blocks; blk += gridDim.x) {
         const long long s = seg_start(blk);
@@ -124,9 +150,23 @@ __global__ void __launch_bounds__(256, 2)
         if (via_tma) {
             mbar_wait(bar, phase);
             phase ^= 1;
+            if (REAL) {
+                const float* sf = reinterpret_cast<const float*>(sIn);
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    v[i] = make_float2(sf[i * 256 + tid], sf[OLS_N + i * 256 + tid]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    v[i] = sIn[i * 256 + tid];
+            }
+        } else if (REAL) {
+            const float* xr = reinterpret_cast<const float*>(x);
+            const float* hr = reinterpret_cast<const float*>(hist);
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                v[i] = sIn[i * 256 + tid];
+                v[i] = make_float2(ols_fetch_real(xr, hr, g.Tm1, s + i * 256 + tid, g.n_in),
+                                   ols_fetch_real(xr, hr, g.Tm1, s + g.V + i * 256 + tid, g.n_in));
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i++)
@@ -140,10 +180,8 @@ __global__ void __launch_bounds__(256, 2)
         __syncthreads();
         {
             const long long nxt = blk + gridDim.x;
-            if (tid == 0 && nxt < g.n_blocks && tma_block(nxt)) {
-                mbar_arrive_expect_tx(bar, OLS_N * 8);
-                bulk_copy_g2s(sIn, x + seg_start(nxt), OLS_N * 8, bar);
-            }
+            if (tid == 0 && nxt < g.n_blocks && tma_block(nxt))
+                issue(nxt);
         }
         {
             const int k0 = tid >> 4, n0 = tid & 15;
@@ -175,26 +213,37 @@ __global__ void __launch_bounds__(256, 2)
         // ---- inverse transform straight from registers (u[k2] plays x[n2*256 + tid])
         fft4096_passes<false>(u, sA, sT2, t1, tid);
         // ---- u[pos16(j)] = y_circ[tid + 256 j]; keep n >= Ov, every D-th input-rate sample
-        const long long out_base = blk * g.V - g.Ov; // input-rate index of circular sample 0
+        const long long out_base = blk * SEGS * g.V - g.Ov; // input-rate index of circular sample 0
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const int n = tid + 256 * j;
             if (n >= g.Ov && n < g.Ov + g.V) {
-                const long long gi = out_base + n;
-                long long m = gi;
-                bool ok = true;
-                if (g.D != 1) {
-                    ok = (gi % g.D == 0);
-                    m = gi / g.D;
-                }
-                if (ok && m < g.n_out) {
-                    float2 r = u[pos16(j)];
-                    if (g.accumulate) {
-                        const float2 prev = y[m];
-                        r.x += prev.x;
-                        r.y += prev.y;
+#pragma unroll
+                for (int sg = 0; sg < SEGS; sg++) {
+                    const long long gi = out_base + n + (long long)sg * g.V;
+                    long long m = gi;
+                    bool ok = true;
+                    if (g.D != 1) {
+                        ok = (gi % g.D == 0);
+                        m = gi / g.D;
                     }
-                    __stcs(y + m, r);
+                    if (ok && m < g.n_out) {
+                        if (REAL) {
+                            float* yr = reinterpret_cast<float*>(y);
+                            float r = sg == 0 ? u[pos16(j)].x : u[pos16(j)].y;
+                            if (g.accumulate)
+                                r += yr[m];
+                            __stcs(yr + m, r);
+                        } else {
+                            float2 r = u[pos16(j)];
+                            if (g.accumulate) {
+                                const float2 prev = y[m];
+                                r.x += prev.x;
+                                r.y += prev.y;
+                            }
+                            __stcs(y + m, r);
+                        }
+                    }
                 }
             }
         }
@@ -206,6 +255,7 @@ constexpr int OLS_PART = 2048; // taps per partition when the filter does not fi
 
 struct ols_plan {
     int T = 0, D = 1;
+    int real = 0;
     ols_geom g{};
     int n_parts = 1;
     float2* d_H = nullptr; // [n_parts][4096]
@@ -224,34 +274,39 @@ void ols_destroy(ols_plan* p)
     delete p;
 }
 
-static void ols_geometry(int T, int D, int* n_parts, int* Ov, int* V)
+// segment starts must be 16-byte aligned for the bulk copies: multiples of 2 complex / 4 real samples
+static void ols_geometry(int T, int D, int real, int* n_parts, int* Ov, int* V)
 {
+    const int q = real ? 4 : 2;
     int Tp = T;
     *n_parts = 1;
-    if (((T - 1) + 1) / 2 * 2 > OLS_N - 1024) { // does not leave >= 1024 valid samples: partition
+    if (((T - 1) + q - 1) / q * q > OLS_N - 1024) { // does not leave >= 1024 valid samples: partition
         *n_parts = (T + OLS_PART - 1) / OLS_PART;
         Tp = OLS_PART;
     }
-    *Ov = ((Tp - 1) + 1) / 2 * 2;
-    *V = (OLS_N - *Ov) / (2 * D) * (2 * D);
+    *Ov = ((Tp - 1) + q - 1) / q * q;
+    *V = (OLS_N - *Ov) / (q * D) * (q * D);
 }
 
-bool ols_supported(int T, int D)
+bool ols_supported(int T, int D, int real)
 {
     int np, Ov, V;
-    ols_geometry(T, D, &np, &Ov, &V);
-    return T >= 2 && V >= 2 * D && np <= 16;
+    ols_geometry(T, D, real, &np, &Ov, &V);
+    return T >= 2 && V >= 4 * D && np <= 16;
 }
 
-int ols_create(const float* taps, int T, int D, int fuse, float kre, float kim, ols_plan** out)
+int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, float kim, ols_plan** out)
 {
     *out = nullptr;
-    if (!ols_supported(T, D))
+    if (real)
+        kim = 0.f; // fff: the fused constant is real
+    if (!ols_supported(T, D, real))
         return set_err(B200_ERR_UNSUPPORTED, "fir overlap-save: %d taps / decimation %d do not fit the 4096-point block", T, D);
     ols_plan* p = new ols_plan();
     p->T = T;
     p->D = D;
-    ols_geometry(T, D, &p->n_parts, &p->g.Ov, &p->g.V);
+    p->real = real;
+    ols_geometry(T, D, real, &p->n_parts, &p->g.Ov, &p->g.V);
     p->g.D = D;
     p->g.Tm1 = T - 1;
     // H[k] = sum_n h[n] e^{-j 2 pi k n / N} / N, times the fused multiply_const
@@ -302,7 +357,10 @@ int ols_create(const float* taps, int T, int D, int fuse, float kre, float kim, 
     OLS_CUDA(cudaMemcpy(p->d_tw1, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
     OLS_CUDA(cudaMalloc(&p->d_tw2, sizeof(float2) * t2.size()));
     OLS_CUDA(cudaMemcpy(p->d_tw2, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
-    OLS_CUDA(cudaFuncSetAttribute(fir_ols4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OLS_SMEM));
+    OLS_CUDA(cudaFuncSetAttribute(fir_ols4096_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)OLS_SMEM));
+    OLS_CUDA(cudaFuncSetAttribute(fir_ols4096_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)OLS_SMEM));
 #undef OLS_CUDA
     p->grid = 2 * sm_count();
     *out = p;
@@ -318,16 +376,22 @@ int ols_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, 
     g.n_in = n_in;
     g.n_out = n_out;
     const long long covered = n_out * p->D; // input-rate samples that carry an output
-    g.n_blocks = (covered + g.V - 1) / g.V;
-    g.tma_ok = ((uintptr_t)d_in % 16 == 0) ? 1 : 0; // segment starts are even sample indices
+    const long long per_block = (long long)g.V * (p->real ? 2 : 1);
+    g.n_blocks = (covered + per_block - 1) / per_block;
+    g.tma_ok = ((uintptr_t)d_in % 16 == 0) ? 1 : 0; // segment starts are multiples of 16 bytes
     long long grid = g.n_blocks < p->grid ? g.n_blocks : p->grid;
     // uniformly partitioned convolution: y = sum_p (h_p * x delayed by p*2048), one pass each
     for (int part = 0; part < p->n_parts; part++) {
         g.shift = part * OLS_PART;
         g.accumulate = part > 0;
-        B200_LAUNCH(fir_ols4096_kernel, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
-                    (const float2*)d_hist, (float2*)d_out, p->d_H + (size_t)part * OLS_N, p->d_tw1, p->d_tw2,
-                    g);
+        if (p->real)
+            B200_LAUNCH(fir_ols4096_kernel<true>, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
+                        (const float2*)d_hist, (float2*)d_out, p->d_H + (size_t)part * OLS_N, p->d_tw1,
+                        p->d_tw2, g);
+        else
+            B200_LAUNCH(fir_ols4096_kernel<false>, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
+                        (const float2*)d_hist, (float2*)d_out, p->d_H + (size_t)part * OLS_N, p->d_tw1,
+                        p->d_tw2, g);
     }
     return B200_OK;
 }

@@ -4,8 +4,9 @@
 
 namespace b200 {
 struct ols_plan;
-bool ols_supported(int n_taps, int decimation);
-int ols_create(const float* taps, int n_taps, int decimation, int fuse, float kre, float kim, ols_plan** out);
+bool ols_supported(int n_taps, int decimation, int real);
+int ols_create(const float* taps, int n_taps, int decimation, int real, int fuse, float kre, float kim,
+               ols_plan** out);
 void ols_destroy(ols_plan* p);
 int ols_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, long long n_in,
                long long n_out, cudaStream_t s);

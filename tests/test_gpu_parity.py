@@ -280,12 +280,42 @@ def test_fir_overlap_save_matches_oracle_and_direct(cuda, T, D):
     assert o.rel_rms(host(yk), o.multiply_const(ref.astype(np.complex64), k)) < TOL_RMS
 
 
+@pytest.mark.parametrize("T,D", [(3, 1), (64, 1), (129, 2), (1024, 4), (2500, 3), (4096, 1)])
+def test_fir_overlap_save_real_stream(cuda, T, D):
+    """fff through algorithm 3: two real blocks per complex transform."""
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T * 3 + D)
+    n = 4 * 4096 * 5 + 777
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)
+    f = nb.FirFilter(taps, D, is_complex=False, algorithm=3)
+    assert f.algorithm == 3
+    y, nc = f.work(dx)
+    ref = o.fir(x, taps, D)
+    assert y.numel() == n // D and nc == (n // D) * D
+    assert o.rel_rms(host(y), ref) < TOL_RMS
+    # chunked streaming (history carried by the handle) and an unaligned start
+    f2 = nb.FirFilter(taps, D, is_complex=False, algorithm=3)
+    outs, pos = [], 0
+    for chunk in (4099, 1, 33333, 10 ** 9):
+        if n - pos < D:
+            break
+        yy, c = f2.work(dx[pos:min(pos + max(chunk, D), n)])
+        outs.append(host(yy))
+        pos += c
+    got = np.concatenate(outs)
+    assert got.size == n // D and o.rel_rms(got, ref) < TOL_RMS
+    yk, _ = nb.FirFilter(taps, D, is_complex=False, multiply_const=3.25, algorithm=3).work(dx)
+    assert o.rel_rms(host(yk), ref * np.float32(3.25)) < TOL_RMS
+
+
 def test_fir_auto_algorithm_choice(cuda):
     import newsched_b200 as nb
     t = np.ones(64, np.float32)
     assert nb.FirFilter(t, 1).algorithm == 1                      # short: direct FFMA2 form
     assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
-    assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 1
+    assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 3
     assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 4   # huge D: fallback kernel
 
 
