@@ -312,6 +312,7 @@ def run_b200(args):
             t = timed(torch, lambda: fir.work_segment(x1, None, y1), reps, 3, lambda: None) / reps
             gs = n1 / (t * 1e-3) / 1e9
             extras[f"fir_ccf_{T}taps_16Mi"] = {
+                "algorithm": fir.algorithm,   # 1 = direct FFMA2 form, 3 = overlap-save FFT (auto for >= 96 taps)
                 "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 4 * T / 1e3,
                 "frac_of_measured_fp32": gs * 4 * T / 1e3 / fp32_tf,
                 "hbm_gbs": gs * 16, "frac_of_hbm": gs * 16 / peak_gbs}
