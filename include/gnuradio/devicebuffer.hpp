@@ -31,6 +31,19 @@ namespace gr {
 
 enum class device_buffer_type { D2D, H2D, D2H };
 
+// What a GPU block needs from an edge buffer to order its asynchronous launches against its
+// neighbours (implemented by device_buffer below and by pinned_buffer in cudabuffer_pinned.hpp).
+class stream_ordered_buffer
+{
+public:
+    virtual ~stream_ordered_buffer() {}
+    virtual void wait_readable(b200_stream_t s) = 0; // the data about to be read has been written
+    virtual void wait_writable(b200_stream_t s) = 0; // the space about to be written has been read
+    virtual void record_read(b200_stream_t s) = 0;
+    virtual void record_write(b200_stream_t s) = 0;
+    static stream_ordered_buffer* from(const buffer_sptr& b) { return dynamic_cast<stream_ordered_buffer*>(b.get()); }
+};
+
 class device_buffer_properties : public buffer_properties
 {
     device_buffer_type _buffer_type;
@@ -47,7 +60,7 @@ public:
     }
 };
 
-class device_buffer : public buffer
+class device_buffer : public buffer, public stream_ordered_buffer
 {
     device_buffer_type _buffer_type;
     size_t _item_size, _num_items = 0, _buf_size = 0; // bytes of one mapping
@@ -236,10 +249,10 @@ public:
     }
 
     // ---- stream ordering used by GPU blocks (see device_stream_guard)
-    void wait_readable(b200_stream_t s) { ck(b200_stream_wait_event(s, _ev_written), "wait_event"); }
-    void wait_writable(b200_stream_t s) { ck(b200_stream_wait_event(s, _ev_read), "wait_event"); }
-    void record_read(b200_stream_t s) { ck(b200_event_record(_ev_read, s), "event_record"); }
-    void record_write(b200_stream_t s) { ck(b200_event_record(_ev_written, s), "event_record"); }
+    void wait_readable(b200_stream_t s) override { ck(b200_stream_wait_event(s, _ev_written), "wait_event"); }
+    void wait_writable(b200_stream_t s) override { ck(b200_stream_wait_event(s, _ev_read), "wait_event"); }
+    void record_read(b200_stream_t s) override { ck(b200_event_record(_ev_read, s), "event_record"); }
+    void record_write(b200_stream_t s) override { ck(b200_event_record(_ev_written, s), "event_record"); }
 
 private:
     static device_buffer* from_checked(const buffer_sptr& b)
@@ -267,19 +280,19 @@ public:
     device_stream_guard(In& in, Out& out, b200_stream_t s) : _in(in), _out(out), _s(s)
     {
         for (auto& w : _in)
-            if (auto* d = device_buffer::from(w.buffer))
+            if (auto* d = stream_ordered_buffer::from(w.buffer))
                 d->wait_readable(_s);
         for (auto& w : _out)
-            if (auto* d = device_buffer::from(w.buffer))
+            if (auto* d = stream_ordered_buffer::from(w.buffer))
                 d->wait_writable(_s);
     }
     ~device_stream_guard()
     {
         for (auto& w : _in)
-            if (auto* d = device_buffer::from(w.buffer))
+            if (auto* d = stream_ordered_buffer::from(w.buffer))
                 d->record_read(_s);
         for (auto& w : _out)
-            if (auto* d = device_buffer::from(w.buffer))
+            if (auto* d = stream_ordered_buffer::from(w.buffer))
                 d->record_write(_s);
     }
 };

@@ -15,6 +15,7 @@
 #include <gnuradio/blocklib/cuda/null_source.hpp>
 #include <gnuradio/blocklib/cuda/pfb_channelizer.hpp>
 #include <gnuradio/cudabuffer.hpp>
+#include <gnuradio/cudabuffer_pinned.hpp>
 #include <gnuradio/flowgraph.hpp>
 #include <gnuradio/schedulers/mt/scheduler_mt.hpp>
 
@@ -115,6 +116,28 @@ QA_TEST(SchedulerMTTest, CudaCopyMultiThreaded)
     fg->start();
     fg->wait();
     EXPECT_EQ(snk1->data(), input_data);
+}
+
+// pinned ("zero-copy") edges, as bm_mt_cuda_copy -m 1 uses them (bench/cuda/bm_copy.cpp:82-99)
+QA_TEST(SchedulerMTTest, CudaCopyPinnedBuffers)
+{
+    auto in = noise(1500007, 41);
+    auto src = blocks::vector_source_c::make(in);
+    auto snk = blocks::vector_sink_c::make();
+    auto c1 = cuda::copy::make(1), c2 = cuda::copy::make(1);
+    auto k = cuda::multiply_const_cc::make(gr_complex(0.f, 1.f));
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, c1, 0)->set_custom_buffer(PINNED_BUFFER_ARGS_SIZED(1u << 20));
+    fg->connect(c1, 0, k, 0)->set_custom_buffer(PINNED_BUFFER_ARGS_SIZED(3u << 20));
+    fg->connect(k, 0, c2, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2D, 2u << 20));
+    fg->connect(c2, 0, snk, 0)->set_custom_buffer(CUDA_BUFFER_PINNED_ARGS);
+    fg->set_scheduler(schedulers::scheduler_mt::make("sched", 1 << 20));
+    fg->validate();
+    fg->run();
+    std::vector<gr_complex> exp(in.size());
+    orc_multiply_const_cc((float*)exp.data(), (const float*)in.data(), 0.f, 1.f, (int64_t)in.size());
+    EXPECT_EQ(snk->data().size(), exp.size());
+    EXPECT_EQ(snk->data(), exp);
 }
 
 // small rings force many wrap-arounds of the doubly mapped device window

@@ -39,6 +39,7 @@ def test_host_boundary_cpu():
 def test_flowgraphs_on_gpu():
     out = _run(_build("qa_cuda_flowgraph"), 600)
     for name in ("SchedulerMTTest.CudaCopyBasic", "SchedulerMTTest.CudaCopyMultiThreaded",
+                 "SchedulerMTTest.CudaCopyPinnedBuffers",
                  "Config1.FirCcf64", "Config2.FftMag", "Config3.FirMulFftChain", "Config4.PfbChannelizer64",
                  "Fusion.AdjacentBlocksCollapse", "TwoInput.MultiplyAndAdd",
                  "SchedulerMTTags.TagsAcrossDeviceBuffers"):
