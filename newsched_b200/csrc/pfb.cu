@@ -13,6 +13,7 @@
 // in shared memory/registers (radix 4 x 16 for M = 64) -- one HBM read and one HBM write
 // per sample.  A dense filterbank*DFT GEMM would execute 8T = 8192 flop/sample and cannot
 // reach the HBM bound of this form, so it is not used here.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -251,7 +252,9 @@ __global__ void __launch_bounds__(256, 2)
 __global__ void __launch_bounds__(256)
     pfb_generic_kernel(const float2* __restrict__ x, const float2* __restrict__ halo,
                        float2* __restrict__ out, const float* __restrict__ taps /* [P][M] */, int M,
-                       int P, int TT, long long n_frames, long long n_in, int ch_begin, int ch_count)
+                       int P, int TT, long long n_frames, long long n_in, int ch_begin, int ch_count,
+                       float2* __restrict__ u_out /* != NULL: write the branch outputs [t][i], skip the DFT */,
+                       long long frame_offset)
 {
     extern __shared__ __align__(16) float2 sm[];
     const int rows = TT + P - 1;
@@ -265,22 +268,40 @@ __global__ void __launch_bounds__(256)
         tw[i] = make_float2(c, s);
     }
     const long long nh = (long long)(P - 1) * M;
-    const long long f0 = (long long)blockIdx.x * TT;
+    const long long f0 = frame_offset + (long long)blockIdx.x * TT;
     const long long g0 = (f0 - (P - 1)) * M;
-    for (int i = tid; i < rows * M; i += blockDim.x)
-        X[i] = pfb_fetch(x, halo, nh, g0 + i, n_in);
+    for (int i0 = tid; i0 < rows * M; i0 += blockDim.x * 8) { // 8 independent loads in flight
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (i0 + u * (int)blockDim.x < rows * M)
+                v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * (int)blockDim.x, n_in);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (i0 + u * (int)blockDim.x < rows * M)
+                X[i0 + u * (int)blockDim.x] = v[u];
+    }
+    float* hS = reinterpret_cast<float*>(tw + M); // taps [P][M] staged once per CTA
+    for (int i = tid; i < P * M; i += blockDim.x)
+        hS[i] = __ldg(taps + i);
     __syncthreads();
     for (int e = tid; e < TT * M; e += blockDim.x) {
         int t = e / M, i = e - t * M;
         float2 a = make_float2(0.f, 0.f);
         for (int r = 0; r < P; r++) {
-            float h = __ldg(taps + r * M + i);
+            float h = hS[r * M + i];
             float2 v = X[(t + P - 1 - r) * M + (M - 1 - i)];
-            a.x = fmaf(h, v.x, a.x);
-            a.y = fmaf(h, v.y, a.y);
+            a = __ffma2_rn(v, make_float2(h, h), a);
         }
-        U[e] = a;
+        if (u_out) {
+            if (f0 + t < n_frames)
+                u_out[((long long)blockIdx.x * TT + t) * M + i] = a; // coalesced across i
+        } else {
+            U[e] = a;
+        }
     }
+    if (u_out)
+        return;
     __syncthreads();
     for (int e = tid; e < TT * ch_count; e += blockDim.x) {
         int t = e / ch_count, cc = e - t * ch_count;
@@ -297,6 +318,18 @@ __global__ void __launch_bounds__(256)
         }
         out[f * ch_count + cc] = a;
     }
+}
+
+// out[t][c - ch_begin] = full[t][c] for a channel slice of the FFT-based generic path
+__global__ void pfb_slice_kernel(const float2* __restrict__ full, float2* __restrict__ out, long long n_frames,
+                                 int M, int ch_begin, int ch_count)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_frames * ch_count)
+        return;
+    long long t = e / ch_count;
+    int c = (int)(e - t * ch_count);
+    out[e] = full[t * M + ch_begin + c];
 }
 
 // new_tail[j] = sample (n_consumed - nh + j) of (old tail ++ x), complex64
@@ -323,6 +356,11 @@ struct b200_pfb {
     size_t smem = 0;
     int TT = 0;
     int grid = 296;
+    // generic M >= 16: branch filters -> scratch -> the library's own reverse FFT of length M
+    b200_fft* ifft = nullptr;
+    float2* d_u = nullptr;    // [chunk_frames][M] branch outputs
+    float2* d_full = nullptr; // [chunk_frames][M] FFT output when a channel slice is requested
+    long long chunk_frames = 0;
 };
 
 static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d_out,
@@ -347,13 +385,33 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         default: PFB64_GO(0); break;
         }
 #undef PFB64_GO
+    } else if (h->ifft) {
+        // branch filters into a scratch tile, then the M-point reverse FFT of fft.cu; chunked so the
+        // scratch allocated at create time is enough for any call
+        const bool slice = h->ch_count != h->M;
+        for (long long f0 = 0; f0 < n_frames; f0 += h->chunk_frames) {
+            const long long nf = std::min(h->chunk_frames, n_frames - f0);
+            const long long tiles = (nf + h->TT - 1) / h->TT;
+            B200_LAUNCH(pfb_generic_kernel, (unsigned)tiles, 256, h->smem, s, (const float2*)d_in,
+                        (const float2*)d_halo, (float2*)nullptr, h->d_taps_rm, h->M, h->P, h->TT, n_frames,
+                        n_in, h->ch_begin, h->ch_count, h->d_u, f0);
+            float2* dst = slice ? h->d_full : (float2*)d_out + f0 * h->M;
+            int rc = b200_fft_run(h->ifft, h->d_u, dst, nf, reinterpret_cast<b200_stream_t>(s));
+            if (rc != B200_OK)
+                return rc;
+            if (slice) {
+                const long long tot = nf * h->ch_count;
+                B200_LAUNCH(pfb_slice_kernel, (unsigned)((tot + 255) / 256), 256, 0, s, h->d_full,
+                            (float2*)d_out + f0 * h->ch_count, nf, h->M, h->ch_begin, h->ch_count);
+            }
+        }
     } else {
         long long tiles = (n_frames + h->TT - 1) / h->TT;
         if (tiles > 0x7fffffffLL)
             return set_err(B200_ERR_ARG, "pfb: too many items for one call");
         B200_LAUNCH(pfb_generic_kernel, (unsigned)tiles, 256, h->smem, s, (const float2*)d_in,
                     (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->M, h->P, h->TT, n_frames,
-                    n_in, h->ch_begin, h->ch_count);
+                    n_in, h->ch_begin, h->ch_count, (float2*)nullptr, 0LL);
     }
     return B200_OK;
 }
@@ -367,6 +425,9 @@ int b200_pfb_destroy(b200_pfb* h)
     cudaFree(h->d_taps_rm);
     cudaFree(h->d_tail[0]);
     cudaFree(h->d_tail[1]);
+    cudaFree(h->d_u);
+    cudaFree(h->d_full);
+    b200_fft_destroy(h->ifft);
     delete h;
     return B200_OK;
 }
@@ -428,13 +489,28 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
         h->TT = 4096 / M;
         if (h->TT < 1)
             h->TT = 1;
-        h->smem = sizeof(float2) * ((size_t)(h->TT + P - 1) * M + (size_t)h->TT * M + M);
+        h->smem = sizeof(float2) * ((size_t)(h->TT + P - 1) * M + (size_t)h->TT * M + M) +
+                  sizeof(float) * (size_t)P * M;
         if (h->smem > 220 * 1024) {
             b200_pfb_destroy(h);
             return set_err(B200_ERR_UNSUPPORTED, "pfb_create: taps_per_channel too large");
         }
         PFB_CUDA(cudaFuncSetAttribute(pfb_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)h->smem));
+        if (M >= 16) {
+            b200_fft_params fp{};
+            fp.n = M;
+            fp.forward = 0; // e^{+j}: the channelizer applies an un-normalised reverse DFT across branches
+            fp.output = B200_FFT_OUT_COMPLEX;
+            if (b200_fft_create(&fp, &h->ifft) != B200_OK) {
+                b200_pfb_destroy(h);
+                return B200_ERR_CUDA;
+            }
+            h->chunk_frames = (32ll << 20) / (8ll * M) / h->TT * h->TT; // 32 MiB of branch outputs
+            PFB_CUDA(cudaMalloc(&h->d_u, sizeof(float2) * (size_t)h->chunk_frames * M));
+            if (h->ch_count != M)
+                PFB_CUDA(cudaMalloc(&h->d_full, sizeof(float2) * (size_t)h->chunk_frames * M));
+        }
     }
 #undef PFB_CUDA
     *out = h;
