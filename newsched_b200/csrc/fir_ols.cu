@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda.h>
+
 #include "fft_core.cuh"
 #include "fir_ols.cuh"
 
@@ -251,6 +253,165 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Decimating complex filters, even D <= 8: polyphase overlap-save.
+//   y[m] = sum_p (h_p * x_p)[m],  h_p[q] = h[qD + p],  x_p[j] = x[jD - p]
+// so one block = D forward transforms (one per phase stream, each at the OUTPUT rate), the sum
+// sum_p X_p G_p accumulated in registers, and ONE inverse transform: (D + 1) transforms per
+// (4096 - ceil(T/D)) * D input samples instead of 2 per 4096 - (T - 1) with 1/D of the results
+// kept.  T = 1024, D = 4: 1.33 transformed samples per input sample instead of 2.67.
+//
+// Staging: the input is viewed as a 2-D tensor of rows of D samples (8-byte elements, row stride
+// D*8 bytes).  One TMA box {2, 256} pulls the two phases that share a 16-byte granule for 256
+// consecutive rows; 16 boxes fill a 64 KiB pair plane sP[n][2].  Every 32-byte sector is
+// requested exactly twice per block (once per pair), all requests 16-byte aligned.  A phase whose
+// sample falls into the next row is read one output period late and its spectrum table G_p is
+// advanced by one sample to compensate (tables for both cases are built at create time).
+constexpr int OLSD_MAXD = 8;
+constexpr size_t OLSD_SMEM = OLS_N * 16 + 16 * F4K_STRIDE * 8 + 256 * 8 + 16;
+
+struct olsd_geom {
+    int D, Ov, V, Tm1;
+    int tma_ok;
+    int rmin;  // row of circular sample 0 relative to (b V - Ov)
+    int gbase; // sample index of (row r, slot s) = r D + s + gbase
+    unsigned gidx; // 4 bits per slot: spectrum table (phase * 2 + late)
+    long long n_in, n_out, n_blocks;
+};
+
+__device__ __forceinline__ void tma_load_box2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1,
+                                               uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+    fir_olsd_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, float2* __restrict__ y,
+                    const float2* __restrict__ Gtab, const float2* __restrict__ tw1,
+                    const float2* __restrict__ tw2, const __grid_constant__ CUtensorMap tmap, olsd_geom g)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sP = reinterpret_cast<float2*>(smem_raw); // [4096][2]
+    float2* sA = sP + 2 * OLS_N;
+    float2* sT2 = sA + 16 * F4K_STRIDE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + 256);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    float2 t1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        t1[i] = __ldg(tw1 + i * 256 + tid);
+    sT2[tid] = __ldg(tw2 + tid);
+    __syncthreads();
+
+    const int n_pairs = g.D >> 1;
+    auto row0 = [&](long long b) { return b * g.V - g.Ov + g.rmin; };
+    auto tma_block = [&](long long b) {
+        const long long r = row0(b);
+        return g.tma_ok && r * g.D + g.gbase >= 0 && (r + OLS_N - 1) * g.D + g.D - 1 + g.gbase < g.n_in;
+    };
+    auto issue = [&](long long b, int pair) { // one elected thread: 16 boxes of {2 samples, 256 rows}
+        mbar_arrive_expect_tx(bar, OLS_N * 16);
+        const long long r = row0(b);
+#pragma unroll 1
+        for (int c = 0; c < 16; c++)
+            tma_load_box2d(sP + c * 512, &tmap, 2 * pair, (int)(r + 256 * c), bar);
+    };
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < g.n_blocks && tma_block(blk))
+        issue(blk, 0);
+    uint32_t phase = 0;
+    for (; blk < g.n_blocks; blk += gridDim.x) {
+        const bool via_tma = tma_block(blk);
+        const long long r0 = row0(blk);
+        float2 acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            acc[i] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int slot = 0; slot < g.D; slot++) {
+            const int e = slot & 1;
+            float2 v[16];
+            if (via_tma) {
+                if (e == 0) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    v[i] = sP[(i * 256 + tid) * 2 + e];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    v[i] = ols_fetch(x, hist, g.Tm1, (r0 + i * 256 + tid) * g.D + slot + g.gbase, g.n_in);
+            }
+            dft16<true>(v);
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0++)
+                sA[k0 * F4K_STRIDE + tid] = cmul(v[pos16(k0)], t1[k0]);
+            __syncthreads(); // also retires this slot's reads of sP
+            if (e == 1 && tid == 0) {
+                // refill the pair plane: next pair of this block, or pair 0 of this CTA's next block
+                if ((slot >> 1) + 1 < n_pairs) {
+                    if (via_tma)
+                        issue(blk, (slot >> 1) + 1);
+                } else {
+                    const long long nxt = blk + gridDim.x;
+                    if (nxt < g.n_blocks && tma_block(nxt))
+                        issue(nxt, 0);
+                }
+            }
+            {
+                const int k0 = tid >> 4, n0 = tid & 15;
+                float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    v[i] = row[i * 16];
+                dft16<true>(v);
+                row[0] = v[pos16(0)];
+#pragma unroll
+                for (int k1 = 1; k1 < 16; k1++)
+                    row[k1 * 16] = cmul(v[pos16(k1)], sT2[k1 * 16 + n0]);
+            }
+            __syncthreads();
+            {
+                const int k0 = tid & 15, k1 = tid >> 4;
+                const float2* row = sA + k0 * F4K_STRIDE + k1 * 16;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    v[i] = row[i];
+                dft16<true>(v);
+                const float2* G = Gtab + (size_t)((g.gidx >> (4 * slot)) & 15u) * OLS_N + tid;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    const float2 w = __ldg(G + k2 * 256), a = v[pos16(k2)];
+                    acc[k2].x = fmaf(a.x, w.x, fmaf(-a.y, w.y, acc[k2].x));
+                    acc[k2].y = fmaf(a.x, w.y, fmaf(a.y, w.x, acc[k2].y));
+                }
+            }
+            __syncthreads(); // pass-3 reads of sA done before the next transform's pass-1 writes
+        }
+        // ---- one inverse transform at the output rate, straight from the accumulators
+        fft4096_passes<false>(acc, sA, sT2, t1, tid);
+        const long long out_base = blk * g.V - g.Ov;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int n = tid + 256 * j;
+            const long long m = out_base + n;
+            if (n >= g.Ov && n < g.Ov + g.V && m < g.n_out)
+                __stcs(y + m, acc[pos16(j)]);
+        }
+        __syncthreads();
+    }
+}
+
 constexpr int OLS_PART = 2048; // taps per partition when the filter does not fit one block
 
 struct ols_plan {
@@ -262,6 +423,9 @@ struct ols_plan {
     float2* d_tw1 = nullptr;
     float2* d_tw2 = nullptr;
     int grid = 296;
+    int poly = 0;          // polyphase form (fir_olsd_kernel): complex stream, even D <= 8
+    float2* d_G = nullptr; // [D][2][4096]: phase spectra, on time / advanced by one output sample
+    int pV = 0, pOv = 0;
 };
 
 void ols_destroy(ols_plan* p)
@@ -271,6 +435,7 @@ void ols_destroy(ols_plan* p)
     cudaFree(p->d_H);
     cudaFree(p->d_tw1);
     cudaFree(p->d_tw2);
+    cudaFree(p->d_G);
     delete p;
 }
 
@@ -288,8 +453,37 @@ static void ols_geometry(int T, int D, int real, int* n_parts, int* Ov, int* V)
     *V = (OLS_N - *Ov) / (q * D) * (q * D);
 }
 
+static bool olsd_supported(int T, int D, int real)
+{
+    if (real || D < 2 || D > OLSD_MAXD || (D & 1))
+        return false;
+    if (const char* e = getenv("B200_OLS_POLY"))
+        if (atoi(e) == 0)
+            return false;
+    const int Tq = (T + D - 1) / D;
+    return Tq >= 1 && OLS_N - Tq >= 1024;
+}
+
+typedef CUresult (*ols_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ols_encode_fn ols_encode_tiled()
+{
+    static ols_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (ols_encode_fn)p;
+    }();
+    return fn;
+}
+
 bool ols_supported(int T, int D, int real)
 {
+    if (olsd_supported(T, D, real))
+        return true;
     int np, Ov, V;
     ols_geometry(T, D, real, &np, &Ov, &V);
     return T >= 2 && V >= 4 * D && np <= 16;
@@ -306,7 +500,16 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
     p->T = T;
     p->D = D;
     p->real = real;
-    ols_geometry(T, D, real, &p->n_parts, &p->g.Ov, &p->g.V);
+    p->poly = olsd_supported(T, D, real) ? 1 : 0;
+    if (p->poly) {
+        const int Tq = (T + D - 1) / D;
+        p->pOv = Tq - 1;
+        p->pV = OLS_N - Tq;
+        p->n_parts = 1;
+        p->g.Ov = p->pOv;
+        p->g.V = p->pV;
+    } else
+        ols_geometry(T, D, real, &p->n_parts, &p->g.Ov, &p->g.V);
     p->g.D = D;
     p->g.Tm1 = T - 1;
     // H[k] = sum_n h[n] e^{-j 2 pi k n / N} / N, times the fused multiply_const
@@ -318,7 +521,26 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
     const double fr = fuse ? kre : 1.0, fi = fuse ? kim : 0.0;
     std::vector<float2> H((size_t)OLS_N * p->n_parts), t1(16 * 256), t2(256);
     const int Lp = p->n_parts == 1 ? T : OLS_PART;
-    for (int part = 0; part < p->n_parts; part++) {
+    std::vector<float2> G;
+    if (p->poly) {
+        // G[ph][late][k] = sum_q h[q D + ph] e^{-j 2 pi k (q - late) / N} / N, times the fused constant
+        G.resize((size_t)D * 2 * OLS_N);
+        for (int ph = 0; ph < D; ph++)
+            for (int late = 0; late < 2; late++)
+                for (int k = 0; k < OLS_N; k++) {
+                    double re = 0, im = 0;
+                    for (int q = 0; q * D + ph < T; q++) {
+                        int idx = (int)(((long long)k * (q - late)) & (OLS_N - 1));
+                        re += taps[q * D + ph] * cs[2 * idx];
+                        im += taps[q * D + ph] * cs[2 * idx + 1];
+                    }
+                    re /= OLS_N;
+                    im /= OLS_N;
+                    G[((size_t)ph * 2 + late) * OLS_N + k] =
+                        make_float2((float)(re * fr - im * fi), (float)(re * fi + im * fr));
+                }
+    }
+    for (int part = 0; part < (p->poly ? 0 : p->n_parts); part++) {
         const int t0 = part * Lp, tn = std::min(T - t0, Lp);
         for (int k = 0; k < OLS_N; k++) {
             double re = 0, im = 0;
@@ -353,6 +575,12 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
     } while (0)
     OLS_CUDA(cudaMalloc(&p->d_H, sizeof(float2) * H.size()));
     OLS_CUDA(cudaMemcpy(p->d_H, H.data(), sizeof(float2) * H.size(), cudaMemcpyHostToDevice));
+    if (p->poly) {
+        OLS_CUDA(cudaMalloc(&p->d_G, sizeof(float2) * G.size()));
+        OLS_CUDA(cudaMemcpy(p->d_G, G.data(), sizeof(float2) * G.size(), cudaMemcpyHostToDevice));
+        OLS_CUDA(cudaFuncSetAttribute(fir_olsd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)OLSD_SMEM));
+    }
     OLS_CUDA(cudaMalloc(&p->d_tw1, sizeof(float2) * t1.size()));
     OLS_CUDA(cudaMemcpy(p->d_tw1, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
     OLS_CUDA(cudaMalloc(&p->d_tw2, sizeof(float2) * t2.size()));
@@ -367,11 +595,66 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
     return B200_OK;
 }
 
+// polyphase form: geometry of the (row, slot) view for this call's pointer alignment, tensor map, launch
+static int olsd_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, long long n_in,
+                       long long n_out, cudaStream_t s)
+{
+    const int D = p->D;
+    olsd_geom g{};
+    g.D = D;
+    g.Ov = p->pOv;
+    g.V = p->pV;
+    g.Tm1 = p->T - 1;
+    g.n_in = n_in;
+    g.n_out = n_out;
+    g.n_blocks = (n_out + g.V - 1) / g.V;
+    // rows of D samples start at the 16-byte granule at or below d_in; `off` samples precede x[0] in it
+    const uintptr_t a = (uintptr_t)d_in;
+    const int off = (a % 16 == 8) ? 1 : 0;
+    g.gbase = -off;
+    int rs[OLSD_MAXD], slot[OLSD_MAXD];
+    g.rmin = 0;
+    for (int ph = 0; ph < D; ph++) {
+        const int z = off - ph; // x_ph[j] sits at row j + floor(z / D), slot z mod D
+        rs[ph] = z >= 0 ? 0 : -1;
+        slot[ph] = z >= 0 ? z : z + D;
+        g.rmin = std::min(g.rmin, rs[ph]);
+    }
+    g.gidx = 0;
+    for (int ph = 0; ph < D; ph++)
+        g.gidx |= (unsigned)(ph * 2 + (rs[ph] - g.rmin)) << (4 * slot[ph]);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const long long nrows = (n_in + off) / D;
+    g.tma_ok = 0;
+    if (a % 8 == 0 && nrows >= OLS_N && nrows < (1LL << 31)) {
+        if (ols_encode_fn enc = ols_encode_tiled()) {
+            cuuint64_t gdim[2] = { (cuuint64_t)D, (cuuint64_t)nrows };
+            cuuint64_t gstride[1] = { (cuuint64_t)D * 8 };
+            cuuint32_t box[2] = { 2, 256 };
+            cuuint32_t estr[2] = { 1, 1 };
+            CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)(a - 8 * off), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            g.tma_ok = (r == CUDA_SUCCESS) ? 1 : 0;
+        }
+    }
+    if (const char* e = getenv("B200_OLS_TMA"))
+        if (atoi(e) == 0)
+            g.tma_ok = 0;
+    const long long grid = g.n_blocks < p->grid ? g.n_blocks : p->grid;
+    B200_LAUNCH(fir_olsd_kernel, (unsigned)grid, 256, OLSD_SMEM, s, (const float2*)d_in, (const float2*)d_hist,
+                (float2*)d_out, p->d_G, p->d_tw1, p->d_tw2, tmap, g);
+    return B200_OK;
+}
+
 int ols_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, long long n_in,
                long long n_out, cudaStream_t s)
 {
     if (n_out <= 0)
         return B200_OK;
+    if (p->poly)
+        return olsd_launch(p, d_hist, d_in, d_out, n_in, n_out, s);
     ols_geom g = p->g;
     g.n_in = n_in;
     g.n_out = n_out;

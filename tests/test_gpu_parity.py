@@ -236,7 +236,8 @@ def test_fir_streaming_equals_oneshot(cuda, T, D):
 
 
 @pytest.mark.parametrize("T,D", [(2, 1), (64, 1), (65, 2), (256, 1), (1024, 4), (1000, 7), (3073, 1), (3000, 3),
-                                 (3074, 1), (4096, 1), (4096, 4), (6001, 2)])
+                                 (3074, 1), (4096, 1), (4096, 4), (6001, 2), (1024, 8), (96, 2),
+                                 (12288, 4), (13000, 4)])
 def test_fir_overlap_save_matches_oracle_and_direct(cuda, T, D):
     """algorithm 3 (FFT overlap-save) against the fp64 oracle, the direct form, and itself when
     the stream is chunked or time-segmented (FFT rounding differs per blocking -> tolerance)."""
@@ -278,6 +279,36 @@ def test_fir_overlap_save_matches_oracle_and_direct(cuda, T, D):
     k = 0.5 - 0.25j
     yk, _ = nb.FirFilter(taps, D, multiply_const=k, algorithm=3).work(dx)
     assert o.rel_rms(host(yk), o.multiply_const(ref.astype(np.complex64), k)) < TOL_RMS
+
+
+@pytest.mark.parametrize("T,D", [(1024, 4), (257, 2), (700, 8)])
+@pytest.mark.parametrize("start", [1, 2, 3])
+def test_fir_polyphase_overlap_save_any_pointer_alignment(cuda, T, D, start):
+    """Even-D complex filters run the polyphase overlap-save kernel, whose TMA row view depends on
+    whether x[0] sits on a 16-byte boundary: every alignment must give the same stream (and the
+    non-TMA path, B200_OLS_TMA=0 semantics, is what the edge blocks use in every run)."""
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T + D + start)
+    n = 4096 * D * 6 + 555
+    x = cplx(rng, n + start)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)[start:]
+    ref = o.fir(x[start:], taps, D)
+    f = nb.FirFilter(taps, D, algorithm=3)
+    y, nc = f.work(dx)
+    assert y.numel() == n // D and nc == (n // D) * D
+    assert o.rel_rms(host(y), ref) < TOL_RMS
+    # worst single sample too: a mis-paired phase would show up as a few wrong outputs
+    assert np.max(np.abs(host(y) - ref)) < 1e-4 * np.max(np.abs(ref))
+    # streaming with history across calls whose chunk starts alternate between alignments
+    f2 = nb.FirFilter(taps, D, algorithm=3)
+    outs, pos = [], 0
+    for chunk in (4096 * D * 2 + D, 4096 * D * 3, 10 ** 9):
+        yy, c = f2.work(dx[pos:min(pos + chunk, n)])
+        outs.append(host(yy))
+        pos += c
+    got = np.concatenate(outs)
+    assert got.size == n // D and o.rel_rms(got, ref) < TOL_RMS
 
 
 @pytest.mark.parametrize("T,D", [(3, 1), (64, 1), (129, 2), (1024, 4), (2500, 3), (4096, 1)])
