@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256, 2)
     sT2[tid] = __ldg(tw2 + tid);
     __syncthreads();
 
-    const int n_pairs = g.D >> 1;
+    const int n_pairs = g.D >> 1; // odd D: no pair planes (row stride not a multiple of 16 bytes), loads go direct
     auto row0 = [&](long long b) { return b * g.V - g.Ov + g.rmin; };
     auto tma_block = [&](long long b) {
         const long long r = row0(b);
@@ -455,7 +455,7 @@ static void ols_geometry(int T, int D, int real, int* n_parts, int* Ov, int* V)
 
 static bool olsd_supported(int T, int D, int real)
 {
-    if (real || D < 2 || D > OLSD_MAXD || (D & 1))
+    if (real || D < 2 || D > OLSD_MAXD)
         return false;
     if (const char* e = getenv("B200_OLS_POLY"))
         if (atoi(e) == 0)
@@ -627,7 +627,7 @@ static int olsd_launch(ols_plan* p, const float* d_hist, const void* d_in, void*
     memset(&tmap, 0, sizeof(tmap));
     const long long nrows = (n_in + off) / D;
     g.tma_ok = 0;
-    if (a % 8 == 0 && nrows >= OLS_N && nrows < (1LL << 31)) {
+    if (a % 8 == 0 && (D & 1) == 0 && nrows >= OLS_N && nrows < (1LL << 31)) {
         if (ols_encode_fn enc = ols_encode_tiled()) {
             cuuint64_t gdim[2] = { (cuuint64_t)D, (cuuint64_t)nrows };
             cuuint64_t gstride[1] = { (cuuint64_t)D * 8 };

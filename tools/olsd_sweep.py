@@ -8,7 +8,7 @@ n = 1 << 26
 g = torch.Generator(device="cuda").manual_seed(1)
 xc = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
 rng = np.random.default_rng(1)
-for T, D in [(1024, 4), (1024, 2), (1024, 8), (256, 2), (512, 4), (4096, 4), (2048, 8)]:
+for T, D in [(1024, 4), (1024, 2), (1024, 8), (256, 2), (512, 4), (4096, 4), (2048, 8), (768, 3), (1024, 5), (1024, 7)]:
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     res = []
     for poly in ("0", "1"):
