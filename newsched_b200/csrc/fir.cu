@@ -547,7 +547,12 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     {
         const bool can = ols_supported(h->T, h->D, h->vec == 1);
         bool want = (p->algorithm == 3);
-        if (p->algorithm == 0 && can && h->T / h->D >= 96)
+        // measured crossovers on B200 (tools/fir_sweep.py, tools/olsd_sweep.py): the full-rate form
+        // beats the direct kernel from ~96 taps per output; the polyphase form of a decimating
+        // complex filter already from ~40 (even D, TMA-staged; at 32 the two are within 5 %) / ~64 (odd D)
+        const int poly = can ? ols_polyphase(h->T, h->D, h->vec == 1) : 0;
+        const int cross = poly == 1 ? 40 : poly == 2 ? 64 : 96;
+        if (p->algorithm == 0 && can && h->T / h->D >= cross)
             want = true;
         if (const char* e = getenv("B200_FIR_ALGO"))
             if (p->algorithm == 0)

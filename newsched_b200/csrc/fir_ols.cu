@@ -480,6 +480,8 @@ static ols_encode_fn ols_encode_tiled()
     return fn;
 }
 
+int ols_polyphase(int T, int D, int real) { return olsd_supported(T, D, real) ? ((D & 1) ? 2 : 1) : 0; }
+
 bool ols_supported(int T, int D, int real)
 {
     if (olsd_supported(T, D, real))

@@ -5,6 +5,8 @@
 namespace b200 {
 struct ols_plan;
 bool ols_supported(int n_taps, int decimation, int real);
+// 0 = full-rate form, 1 = polyphase form staged by TMA (even D), 2 = polyphase with direct loads (odd D)
+int ols_polyphase(int n_taps, int decimation, int real);
 int ols_create(const float* taps, int n_taps, int decimation, int real, int fuse, float kre, float kim,
                ols_plan** out);
 void ols_destroy(ols_plan* p);

@@ -219,10 +219,10 @@ def test_fir_streaming_equals_oneshot(cuda, T, D):
     x = cplx(rng, n)
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     dx = dev(cuda, x)
-    ref, _ = nb.FirFilter(taps, D).work(dx)
+    ref, _ = nb.FirFilter(taps, D, algorithm=1).work(dx)   # direct form: bit-exact for any chunking
     ref = host(ref)
     for chunk in (1, T - 1 if T > 1 else 1, T, 997, 8192):
-        f = nb.FirFilter(taps, D)
+        f = nb.FirFilter(taps, D, algorithm=1)
         step = max(chunk, D)          # the scheduler re-presents unconsumed items with new ones
         outs, pos = [], 0
         while n - pos >= D:
@@ -348,6 +348,8 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
     assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 3
     assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 4   # huge D: fallback kernel
+    assert nb.FirFilter(np.ones(256, np.float32), 4).algorithm == 3    # polyphase overlap-save from T/D = 40
+    assert nb.FirFilter(np.ones(128, np.float32), 4).algorithm == 1
 
 
 def test_fir_empty_and_short(cuda):
