@@ -412,6 +412,167 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Full-rate complex filters with many taps: two-phase (2 x 2 polyphase) overlap-save.
+//   y[2m + a] = sum_{p,q} h[2q + p] x[2(m - q) + a - p]
+// i.e. with the even / odd streams x_0, x_1 and tap phases h_0, h_1 (all at HALF rate)
+//   Y_0 = H_0 X_0 + z^-1 H_1 X_1,   Y_1 = H_1 X_0 + H_0 X_1.
+// One block = 2 forward + 2 inverse 4096-point transforms for 2 (4095 - ceil(T/2)) samples: the
+// overlap costs T/2 instead of T - 1 of every 4096 points (T = 4096: 4 transformed samples per
+// output instead of 8 with two 2048-tap partitions; T = 2048: 2.7 instead of 4).
+// The block's input is one CONTIGUOUS run of 8192 samples, which already is the pair plane
+// sP[n][2] = (x_0[n], x_1[n]): a single 64 KiB bulk copy, read back with one LDS.128 per point.
+// If x[0] sits 8 bytes past a 16-byte boundary the roles of the streams swap (x'_c = granule-
+// aligned phases) and one term needs a one-sample ADVANCE instead of the delay; the host picks the
+// four coefficient tables C[a][c] per call from {H_0, H_1, z^-1 H_1, z^+1 H_0}.
+struct ols2_geom {
+    int Ov, V, Tm1, tma_ok, off;
+    int c00, c01, c10, c11; // table index of C[a][c]
+    long long n_in, n_out, n_blocks;
+};
+
+__global__ void __launch_bounds__(256, 2)
+    fir_ols2_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, float2* __restrict__ y,
+                    const float2* __restrict__ Htab, const float2* __restrict__ tw1,
+                    const float2* __restrict__ tw2, ols2_geom g)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sP = reinterpret_cast<float2*>(smem_raw); // [4096][2]
+    float2* sA = sP + 2 * OLS_N;
+    float2* sT2 = sA + 16 * F4K_STRIDE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + 256);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    float2 t1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        t1[i] = __ldg(tw1 + i * 256 + tid);
+    sT2[tid] = __ldg(tw2 + tid);
+    __syncthreads();
+
+    // block b: half-rate times j0 + n, j0 = b V - Ov; aligned-stream element 2 (j0 + n) + c is
+    // sample x[2 (j0 + n) + c - off]
+    auto first = [&](long long b) { return 2 * (b * g.V - g.Ov) - g.off; };
+    auto tma_block = [&](long long b) {
+        const long long s = first(b);
+        return g.tma_ok && s >= 0 && s + 2 * OLS_N <= g.n_in;
+    };
+    auto issue = [&](long long b) {
+        mbar_arrive_expect_tx(bar, OLS_N * 16);
+        bulk_copy_g2s(sP, x + first(b), OLS_N * 8, bar);
+        bulk_copy_g2s(sP + OLS_N, x + first(b) + OLS_N, OLS_N * 8, bar);
+    };
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < g.n_blocks && tma_block(blk))
+        issue(blk);
+    uint32_t phase = 0;
+    const bool out16 = ((uintptr_t)y & 15) == 0;
+    for (; blk < g.n_blocks; blk += gridDim.x) {
+        const long long s0 = first(blk);
+        float2 v0[16], v1[16];
+        if (tma_block(blk)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float4 q = reinterpret_cast<const float4*>(sP)[i * 256 + tid];
+                v0[i] = make_float2(q.x, q.y);
+                v1[i] = make_float2(q.z, q.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                v0[i] = ols_fetch(x, hist, g.Tm1, s0 + 2 * (i * 256 + tid), g.n_in);
+                v1[i] = ols_fetch(x, hist, g.Tm1, s0 + 2 * (i * 256 + tid) + 1, g.n_in);
+            }
+        }
+        // ---- X_0: the first barrier inside retires every read of sP, so the next block's copy
+        //      can start right behind it and overlaps all four transforms
+        dft16<true>(v0);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++)
+            sA[k0 * F4K_STRIDE + tid] = cmul(v0[pos16(k0)], t1[k0]);
+        __syncthreads();
+        {
+            const long long nxt = blk + gridDim.x;
+            if (tid == 0 && nxt < g.n_blocks && tma_block(nxt))
+                issue(nxt);
+        }
+        {
+            const int k0 = tid >> 4, n0 = tid & 15;
+            float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v0[i] = row[i * 16];
+            dft16<true>(v0);
+            row[0] = v0[pos16(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++)
+                row[k1 * 16] = cmul(v0[pos16(k1)], sT2[k1 * 16 + n0]);
+        }
+        __syncthreads();
+        {
+            const int k0 = tid & 15, k1 = tid >> 4;
+            const float2* row = sA + k0 * F4K_STRIDE + k1 * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v0[i] = row[i];
+            dft16<true>(v0); // X_0[tid + 256 k2] in v0[pos16(k2)]
+        }
+        __syncthreads();
+        // ---- X_1
+        fft4096_passes<true>(v1, sA, sT2, t1, tid);
+        // ---- Y_0, Y_1 in place (natural register order for the inverse pass 1)
+        {
+            float2 a0[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                const float2 xa = v0[pos16(k2)], xb = v1[pos16(k2)];
+                const int k = k2 * 256 + tid;
+                const float2 y0 = cmul(xa, __ldg(Htab + g.c00 * OLS_N + k)) + cmul(xb, __ldg(Htab + g.c01 * OLS_N + k));
+                const float2 y1 = cmul(xa, __ldg(Htab + g.c10 * OLS_N + k)) + cmul(xb, __ldg(Htab + g.c11 * OLS_N + k));
+                a0[k2] = y0;
+                v1[pos16(k2)] = y1; // slot pos16(k2) of v1 is dead from here on
+            }
+            // permute Y_1 from pos16 order into natural order, Y_0 already natural in a0
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++)
+                v0[k2] = a0[k2];
+        }
+        __syncthreads(); // X_1's pass-3 reads of sA are done
+        fft4096_passes<false>(v0, sA, sT2, t1, tid);
+        __syncthreads();
+        {
+            float2 b1[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++)
+                b1[k2] = v1[pos16(k2)];
+            fft4096_passes<false>(b1, sA, sT2, t1, tid);
+            // ---- v0[pos16(j)] = y[2 (j0 + n)], b1[pos16(j)] = y[2 (j0 + n) + 1], n = tid + 256 j
+            const long long j0 = blk * g.V - g.Ov;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int n = tid + 256 * j;
+                const long long m = 2 * (j0 + n);
+                if (n >= g.Ov && n < g.Ov + g.V && m < g.n_out) {
+                    const float2 e = v0[pos16(j)], o = b1[pos16(j)];
+                    if (out16 && m + 1 < g.n_out)
+                        __stcs(reinterpret_cast<float4*>(y + m), make_float4(e.x, e.y, o.x, o.y));
+                    else {
+                        __stcs(y + m, e);
+                        if (m + 1 < g.n_out)
+                            __stcs(y + m + 1, o);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 constexpr int OLS_PART = 2048; // taps per partition when the filter does not fit one block
 
 struct ols_plan {
@@ -426,6 +587,8 @@ struct ols_plan {
     int poly = 0;          // polyphase form (fir_olsd_kernel): complex stream, even D <= 8
     float2* d_G = nullptr; // [D][2][4096]: phase spectra, on time / advanced by one output sample
     int pV = 0, pOv = 0;
+    int two = 0;           // two-phase form (fir_ols2_kernel): complex stream, D == 1, many taps
+    float2* d_H2 = nullptr; // [4][4096]: H_0, H_1, z^-1 H_1, z^+1 H_0
 };
 
 void ols_destroy(ols_plan* p)
@@ -436,6 +599,7 @@ void ols_destroy(ols_plan* p)
     cudaFree(p->d_tw1);
     cudaFree(p->d_tw2);
     cudaFree(p->d_G);
+    cudaFree(p->d_H2);
     delete p;
 }
 
@@ -464,6 +628,18 @@ static bool olsd_supported(int T, int D, int real)
     return Tq >= 1 && OLS_N - Tq >= 1024;
 }
 
+// two-phase form: worth it once the overlap of the one-phase form eats a quarter of the block
+static bool ols2_supported(int T, int D, int real)
+{
+    if (real || D != 1)
+        return false;
+    int min_taps = 1024;
+    if (const char* e = getenv("B200_OLS_TWO"))
+        min_taps = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    const int Tq = (T + 1) / 2;
+    return T >= min_taps && OLS_N - 1 - Tq >= 1024;
+}
+
 typedef CUresult (*ols_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -484,7 +660,7 @@ int ols_polyphase(int T, int D, int real) { return olsd_supported(T, D, real) ? 
 
 bool ols_supported(int T, int D, int real)
 {
-    if (olsd_supported(T, D, real))
+    if (olsd_supported(T, D, real) || ols2_supported(T, D, real))
         return true;
     int np, Ov, V;
     ols_geometry(T, D, real, &np, &Ov, &V);
@@ -507,6 +683,13 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
         const int Tq = (T + D - 1) / D;
         p->pOv = Tq - 1;
         p->pV = OLS_N - Tq;
+        p->n_parts = 1;
+        p->g.Ov = p->pOv;
+        p->g.V = p->pV;
+    } else if (ols2_supported(T, D, real)) {
+        p->two = 1;
+        p->pOv = (T + 1) / 2;
+        p->pV = OLS_N - 1 - p->pOv;
         p->n_parts = 1;
         p->g.Ov = p->pOv;
         p->g.V = p->pV;
@@ -542,7 +725,26 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
                         make_float2((float)(re * fr - im * fi), (float)(re * fi + im * fr));
                 }
     }
-    for (int part = 0; part < (p->poly ? 0 : p->n_parts); part++) {
+    std::vector<float2> H2;
+    if (p->two) {
+        H2.resize((size_t)4 * OLS_N);
+        for (int tab = 0; tab < 4; tab++) {
+            const int ph = (tab == 1 || tab == 2) ? 1 : 0;      // tap phase
+            const int dl = tab == 2 ? 1 : tab == 3 ? -1 : 0;    // delay in half-rate samples
+            for (int k = 0; k < OLS_N; k++) {
+                double re = 0, im = 0;
+                for (int q = 0; 2 * q + ph < T; q++) {
+                    int idx = (int)(((long long)k * (q + dl)) & (OLS_N - 1));
+                    re += taps[2 * q + ph] * cs[2 * idx];
+                    im += taps[2 * q + ph] * cs[2 * idx + 1];
+                }
+                re /= OLS_N;
+                im /= OLS_N;
+                H2[(size_t)tab * OLS_N + k] = make_float2((float)(re * fr - im * fi), (float)(re * fi + im * fr));
+            }
+        }
+    }
+    for (int part = 0; part < ((p->poly || p->two) ? 0 : p->n_parts); part++) {
         const int t0 = part * Lp, tn = std::min(T - t0, Lp);
         for (int k = 0; k < OLS_N; k++) {
             double re = 0, im = 0;
@@ -577,6 +779,12 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
     } while (0)
     OLS_CUDA(cudaMalloc(&p->d_H, sizeof(float2) * H.size()));
     OLS_CUDA(cudaMemcpy(p->d_H, H.data(), sizeof(float2) * H.size(), cudaMemcpyHostToDevice));
+    if (p->two) {
+        OLS_CUDA(cudaMalloc(&p->d_H2, sizeof(float2) * H2.size()));
+        OLS_CUDA(cudaMemcpy(p->d_H2, H2.data(), sizeof(float2) * H2.size(), cudaMemcpyHostToDevice));
+        OLS_CUDA(cudaFuncSetAttribute(fir_ols2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)OLSD_SMEM));
+    }
     if (p->poly) {
         OLS_CUDA(cudaMalloc(&p->d_G, sizeof(float2) * G.size()));
         OLS_CUDA(cudaMemcpy(p->d_G, G.data(), sizeof(float2) * G.size(), cudaMemcpyHostToDevice));
@@ -650,6 +858,30 @@ static int olsd_launch(ols_plan* p, const float* d_hist, const void* d_in, void*
     return B200_OK;
 }
 
+static int ols2_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, long long n_in,
+                       long long n_out, cudaStream_t s)
+{
+    ols2_geom g{};
+    g.Ov = p->pOv;
+    g.V = p->pV;
+    g.Tm1 = p->T - 1;
+    g.n_in = n_in;
+    g.n_out = n_out;
+    g.n_blocks = (n_out + 2LL * g.V - 1) / (2LL * g.V);
+    const uintptr_t a = (uintptr_t)d_in;
+    g.off = (a % 16 == 8) ? 1 : 0;
+    g.tma_ok = (a % 8 == 0) ? 1 : 0;
+    if (g.off == 0) { // Y_0 = H_0 X_0 + z^-1 H_1 X_1 ; Y_1 = H_1 X_0 + H_0 X_1
+        g.c00 = 0, g.c01 = 2, g.c10 = 1, g.c11 = 0;
+    } else {          // aligned streams x'_0 = x_1 delayed, x'_1 = x_0: Y_0 = H_1 X'_0 + H_0 X'_1 ; Y_1 = z H_0 X'_0 + H_1 X'_1
+        g.c00 = 1, g.c01 = 0, g.c10 = 3, g.c11 = 1;
+    }
+    const long long grid = g.n_blocks < p->grid ? g.n_blocks : p->grid;
+    B200_LAUNCH(fir_ols2_kernel, (unsigned)grid, 256, OLSD_SMEM, s, (const float2*)d_in, (const float2*)d_hist,
+                (float2*)d_out, p->d_H2, p->d_tw1, p->d_tw2, g);
+    return B200_OK;
+}
+
 int ols_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, long long n_in,
                long long n_out, cudaStream_t s)
 {
@@ -657,6 +889,8 @@ int ols_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, 
         return B200_OK;
     if (p->poly)
         return olsd_launch(p, d_hist, d_in, d_out, n_in, n_out, s);
+    if (p->two)
+        return ols2_launch(p, d_hist, d_in, d_out, n_in, n_out, s);
     ols_geom g = p->g;
     g.n_in = n_in;
     g.n_out = n_out;
