@@ -72,8 +72,7 @@ __device__ __forceinline__ float2 pfb_fetch(const float2* __restrict__ x, const 
 }
 
 constexpr int PFB64_TT = 64;  // frames per tile
-constexpr int PFB64_RS = 81;  // u row stride (complex): 81 = 1 mod 16 keeps every DFT access conflict-free
-constexpr int PFB64_CS = 20;  // stride between the four c0 groups after pass A (20 = 4 mod 16)
+constexpr int PFB64_RS = 68;  // u row stride (complex): 68 = 4 mod 16 keeps the 4-lane-contiguous DFT accesses conflict-free
 
 // M = 64.  256 threads, persistent over 64-frame tiles.
 // smem: X[(TT+P4-1)][64] | U[TT][65] | taps[P4][64] | tw64[64] | mbarrier
@@ -200,47 +199,52 @@ __global__ void __launch_bounds__(256, 2)
             }
         }
 
-        // ---- 64-point reverse DFT across branches: i = 16 i1 + i0, c = c0 + 4 c1 -----------
+        // ---- 64-point reverse DFT across branches: i = 4 i1 + i0, c = c1 + 16 c0 -----------
+        //   stage 1, thread (frame t, i0):  A_{i0}[c1] = W64^{i0 c1} sum_{i1} u[4 i1 + i0] W16^{i1 c1}
+        //   stage 2, thread (4 frames, c1): y[c1 + 16 c0] = sum_{i0} A_{i0}[c1] W4^{i0 c0}
+        // Stage 2 puts 16 consecutive channels on 16 consecutive lanes, so every output store
+        // instruction writes whole 128-byte lines (the radix 4 x 16 order wrote 32-byte pieces of
+        // eight lines per instruction, and the store wavefronts were a quarter of the LSU traffic).
+        // Rows are warp-local (warp w owns frames 8w..8w+7) in both stages: __syncwarp suffices.
         {
-            const int t = tid >> 2, g = tid & 3;
+            const int t = tid >> 2, i0 = tid & 3;
             float2* row = U + t * PFB64_RS;
             float2 v[16];
-            // pass A: DFT4 over i1 for i0 = 4g..4g+3 ; v[4*j + i1]
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int i1 = 0; i1 < 16; i1++)
+                v[i1] = row[4 * i1 + i0];
+            idft16(v); // A[c1] in v[4*(c1&3) + (c1>>2)]
+            __syncwarp();
+            row[i0] = v[0];
 #pragma unroll
-                for (int i1 = 0; i1 < 4; i1++)
-                    v[4 * j + i1] = row[i1 * 16 + 4 * g + j];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                idft4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                const int i0 = 4 * g + j;
-#pragma unroll
-                for (int c0 = 1; c0 < 4; c0++) {
-                    float2 w = tw[(i0 * c0) & 63];
-                    v[4 * j + c0] = cmulc(v[4 * j + c0], w.x, w.y);
-                }
+            for (int c1 = 1; c1 < 16; c1++) {
+                const float2 w = tw[(i0 * c1) & 63];
+                row[4 * c1 + i0] = cmulc(v[4 * (c1 & 3) + (c1 >> 2)], w.x, w.y);
             }
             __syncwarp();
+        }
+        {
+            const int lane = tid & 31, c1 = lane & 15;
+            const int fq = (tid >> 5) * 8 + (lane >> 4) * 4; // first of this thread's four frames
+            const int swap = (c1 >> 2) & 1;                  // bank-conflict-free order of the two 16-byte halves
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int q = 0; q < 4; q++) {
+                const float4* src = reinterpret_cast<const float4*>(U + (fq + q) * PFB64_RS + 4 * c1);
+                const float4 p0 = src[swap], p1 = src[swap ^ 1];
+                const float4 lo = swap ? p1 : p0, hi = swap ? p0 : p1;
+                float2 a = make_float2(lo.x, lo.y), b = make_float2(lo.z, lo.w);
+                float2 c = make_float2(hi.x, hi.y), d = make_float2(hi.z, hi.w);
+                idft4(a, b, c, d); // y[c1 + 16 c0], c0 = 0..3
+                const long long f = f0 + fq + q;
+                if (f < n_frames) {
+                    float2* y = out + f * ch_count - ch_begin;
+                    const float2 r[4] = { a, b, c, d };
 #pragma unroll
-                for (int c0 = 0; c0 < 4; c0++)
-                    row[c0 * PFB64_CS + 4 * g + j] = v[4 * j + c0];
-            __syncwarp();
-            // pass B: thread (t, c0 = g): DFT16 over i0 -> c1
-#pragma unroll
-            for (int i0 = 0; i0 < 16; i0++)
-                v[i0] = row[g * PFB64_CS + i0];
-            idft16(v);
-            const long long f = f0 + t;
-            if (f < n_frames) {
-                float2* y = out + f * ch_count;
-#pragma unroll
-                for (int c1 = 0; c1 < 16; c1++) {
-                    int c = g + 4 * c1 - ch_begin;
-                    if (c >= 0 && c < ch_count)
-                        __stcs(y + c, v[4 * (c1 & 3) + (c1 >> 2)]);
+                    for (int c0 = 0; c0 < 4; c0++) {
+                        const int ch = c1 + 16 * c0;
+                        if (ch >= ch_begin && ch < ch_begin + ch_count)
+                            __stcs(y + ch, r[c0]);
+                    }
                 }
             }
         }
