@@ -148,6 +148,33 @@ B200_API int b200_fir_get_history(b200_fir* h, void* d_hist, b200_stream_t s);
 B200_API int b200_fir_algorithm(const b200_fir* h);                     /* what auto selected */
 B200_API int b200_fir_geometry(const b200_fir* h, int* decimation, int* item_bytes);
 
+/* ---- interp_fir_filter / rational_resampler (ccf / fff) ------
+ * y[m] = sum_k h[k] xu[m*D - k] with xu = x zero-stuffed by L (polyphase: only the T/L products
+ * per output that meet a real sample are formed).  interpolation L, decimation D; D = 1 is
+ * interp_fir_filter.  A run consumes whole groups of D items and produces L per group
+ * (n_consumed = floor(n_in/D)*D, n_produced = floor(n_in/D)*L), so every call starts at phase 0;
+ * the ceil(T/L)-1 input samples of history live in the handle.  Absent from the reference
+ * snapshot; the block interface it stands behind is gr::block::work
+ * (runtime/include/gnuradio/block.hpp:81-85). */
+typedef struct b200_resampler b200_resampler;
+typedef struct {
+    const float* taps;     /* host pointer, n_taps floats */
+    int32_t n_taps;
+    int32_t interpolation; /* L >= 1 */
+    int32_t decimation;    /* D >= 1 */
+    int32_t is_complex;    /* 1 = ccf, 0 = fff */
+} b200_resampler_params;
+B200_API int b200_resampler_create(const b200_resampler_params* p, b200_resampler** h);
+B200_API int b200_resampler_destroy(b200_resampler* h);
+B200_API int b200_resampler_run(b200_resampler* h, const void* d_in, void* d_out, int64_t n_in_items,
+                                int64_t* n_consumed, int64_t* n_produced, b200_stream_t s);
+/* stateless: the ceil(T/L)-1 samples before d_in[0] come from d_halo (device; NULL = zeros) */
+B200_API int b200_resampler_run_segment(b200_resampler* h, const void* d_halo, const void* d_in, void* d_out,
+                                        int64_t n_in_items, int64_t* n_produced, b200_stream_t s);
+B200_API int b200_resampler_reset(b200_resampler* h, b200_stream_t s);
+B200_API int b200_resampler_geometry(const b200_resampler* h, int* interpolation, int* decimation,
+                                     int* item_bytes);
+
 /* ---- fft (vector length N, forward / reverse, optional window, optional shift) -----
  * fft_vcc semantics; no 1/N scaling.  Shared-memory Stockham, no cuFFT.
  * Prologue fusion: an adjacent upstream multiply_const_cc (pre_scale).

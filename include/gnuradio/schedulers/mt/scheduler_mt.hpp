@@ -198,8 +198,17 @@ class thread_wrapper : public neighbor_interface
             return executor_iteration_status::DONE;
         }
         if (!progress) {
-            // 0/0 work: blocked, unless nothing more can ever arrive
+            // 0/0 work: blocked, unless nothing more can ever arrive.  A block with an output
+            // multiple (an interpolator needs L free items) may also have produced nothing only
+            // because downstream has not drained yet: its space still grows, so that is BLKD_OUT,
+            // not the end of the stream.
             if (all_upstream_done) {
+                bool output_pending = false;
+                for (auto& p : out_ports)
+                    for (auto& buf : _bufman->get_output_buffers(p))
+                        output_pending |= !buf->reader_done() && buf->total_written() != buf->total_read();
+                if (output_pending)
+                    return executor_iteration_status::BLKD_OUT;
                 finish_block(bi);
                 return executor_iteration_status::DONE;
             }

@@ -45,6 +45,11 @@ class _FirParams(C.Structure):
                 ("k_im", C.c_float), ("algorithm", C.c_int32)]
 
 
+class _ResamplerParams(C.Structure):
+    _fields_ = [("taps", C.POINTER(C.c_float)), ("n_taps", C.c_int32), ("interpolation", C.c_int32),
+                ("decimation", C.c_int32), ("is_complex", C.c_int32)]
+
+
 class _FftParams(C.Structure):
     _fields_ = [("n", C.c_int32), ("forward", C.c_int32), ("window", C.POINTER(C.c_float)),
                 ("shift", C.c_int32), ("output", C.c_int32), ("fuse_pre_multiply_const", C.c_int32),
@@ -121,6 +126,12 @@ SIGNATURES = {
     "b200_fir_get_history": (_I, [_V, _V, _V]),
     "b200_fir_algorithm": (_I, [_V]),
     "b200_fir_geometry": (_I, [_V, C.POINTER(_I), C.POINTER(_I)]),
+    "b200_resampler_create": (_I, [C.POINTER(_ResamplerParams), C.POINTER(_V)]),
+    "b200_resampler_destroy": (_I, [_V]),
+    "b200_resampler_run": (_I, [_V, _V, _V, _I64, _PI64, _PI64, _V]),
+    "b200_resampler_run_segment": (_I, [_V, _V, _V, _V, _I64, _PI64, _V]),
+    "b200_resampler_reset": (_I, [_V, _V]),
+    "b200_resampler_geometry": (_I, [_V, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "b200_fft_create": (_I, [C.POINTER(_FftParams), C.POINTER(_V)]),
     "b200_fft_destroy": (_I, [_V]),
     "b200_fft_run": (_I, [_V, _V, _V, _I64, _V]),
@@ -382,6 +393,62 @@ class FFT:
         try:
             if self._h:
                 lib().b200_fft_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class RationalResampler:
+    """rational_resampler_ccf / _fff (interpolation L, decimation D; D = 1 is interp_fir_filter):
+    y[m] = sum_k h[k] xu[m*D - k] with xu the L-fold zero-stuffed input.  Streaming: each work()
+    consumes whole groups of D items and produces L per group; history lives on the device."""
+
+    def __init__(self, taps, interpolation: int = 1, decimation: int = 1, is_complex: bool = True):
+        arr, ptr = _floats(taps)
+        p = _ResamplerParams(ptr, arr.size, int(interpolation), int(decimation), int(bool(is_complex)))
+        h = C.c_void_p()
+        _check(lib().b200_resampler_create(C.byref(p), C.byref(h)))
+        self._h = h
+        self.n_taps, self.interpolation, self.decimation = arr.size, int(interpolation), int(decimation)
+        self.is_complex = bool(is_complex)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _n_out(self, n_in):
+        return (n_in // self.decimation) * self.interpolation
+
+    def work(self, x, out=None, stream=None):
+        """One work() call: returns (y, n_consumed)."""
+        torch = _torch()
+        _need_cuda(x)
+        assert x.dtype == (torch.complex64 if self.is_complex else torch.float32)
+        if out is None:
+            out = torch.empty(self._n_out(x.numel()), dtype=x.dtype, device=x.device)
+        nc, npd = C.c_int64(), C.c_int64()
+        _check(lib().b200_resampler_run(self._h, x.data_ptr(), out.data_ptr(), x.numel(), C.byref(nc),
+                                        C.byref(npd), _stream(stream)))
+        return out[: npd.value], nc.value
+
+    def work_segment(self, x, halo=None, out=None, stream=None):
+        torch = _torch()
+        _need_cuda(x)
+        if out is None:
+            out = torch.empty(self._n_out(x.numel()), dtype=x.dtype, device=x.device)
+        npd = C.c_int64()
+        _check(lib().b200_resampler_run_segment(self._h, halo.data_ptr() if halo is not None else None,
+                                                x.data_ptr(), out.data_ptr(), x.numel(), C.byref(npd),
+                                                _stream(stream)))
+        return out[: npd.value]
+
+    def reset(self, stream=None):
+        _check(lib().b200_resampler_reset(self._h, _stream(stream)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b200_resampler_destroy(self._h)
                 self._h = None
         except Exception:
             pass

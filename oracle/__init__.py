@@ -66,6 +66,10 @@ def _declare(L):
     L.orc_add_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.orc_complex_to_mag.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.orc_complex_to_mag_squared.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    for name in ("orc_resample_ccf_f64", "orc_resample_fff_f64"):
+        f = getattr(L, name)
+        f.restype = C.c_int64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     for name in ("orc_fir_ccf_f64", "orc_fir_fff_f64", "orc_fir_ccf_f32", "orc_fir_fff_f32",
                  "orc_fir_ccf_f64_mt", "orc_fir_ccf_f32_mt", "orc_fir_fff_f32_mt"):
         f = getattr(L, name)
@@ -173,6 +177,24 @@ def fir(x: np.ndarray, taps, decim: int = 1, hist=None, precise: bool = True, mt
     if mt:
         name += "_mt"
     r = getattr(lib(), name)(_p(out), _p(x), x.size, _p(taps), T, int(decim), _p(hist))
+    assert r == n_out
+    return out
+
+
+def resample(x: np.ndarray, taps, interp: int = 1, decim: int = 1, hist=None) -> np.ndarray:
+    """interp_fir_filter / rational_resampler (ccf / fff), fp64 accumulate: y[m] = sum_k h[k] xu[m D - k]
+    with xu the interp-fold zero-stuffed x; (len(x) // decim) * interp outputs.
+    hist: the ceil(T/interp)-1 samples preceding x[0] (oldest first) or None for zeros."""
+    taps = _c(taps, np.float32)
+    cplx = np.iscomplexobj(x)
+    x = _c(x, np.complex64 if cplx else np.float32)
+    if hist is not None:
+        hist = _c(hist, x.dtype)
+        assert hist.size == (taps.size + interp - 1) // interp - 1
+    n_out = (x.size // decim) * interp
+    out = np.empty(n_out, x.dtype)
+    fn = lib().orc_resample_ccf_f64 if cplx else lib().orc_resample_fff_f64
+    r = fn(_p(out), _p(x), x.size, _p(taps), taps.size, int(interp), int(decim), _p(hist))
     assert r == n_out
     return out
 

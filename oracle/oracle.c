@@ -281,6 +281,49 @@ ORC_API int64_t orc_fir_fff_f32_mt(float* out, const float* in, int64_t n_in, co
     return fir_f32(out, in, n_in, taps, T, D, hist, 1, 1);
 }
 
+/* ---------------------------------------------------------------- resampler
+ * interp_fir_filter / rational_resampler (absent from the reference
+ * snapshot -- "parity unpinned", cross-checked against scipy.signal.upfirdn in tests/test_oracle.py):
+ *   y[m] = sum_k h[k] xu[m D - k],  xu[i] = x[i / L] if L divides i else 0,
+ * i.e. y[m] = sum_q h[q L + phi] x[j - q] with m D = j L + phi.  floor(n_in / D) groups of D inputs
+ * give L outputs each.  hist = the ceil(T/L)-1 samples before in[0] (oldest first) or NULL. */
+static int64_t resample_f64(float* out, const float* in, int64_t n_in, const float* taps, int T, int L, int D,
+                            const float* hist, int vec)
+{
+    const int64_t n_out = (n_in / D) * L;
+    const int Tq = (T + L - 1) / L, nh = Tq - 1;
+    for (int64_t m = 0; m < n_out; m++) {
+        const int64_t i = m * D, j = i / L;
+        const int phi = (int)(i % L);
+        double acc[2] = { 0.0, 0.0 };
+        for (int q = 0; (int64_t)q * L + phi < T; q++) {
+            const int64_t s = j - q;
+            const double h = taps[(int64_t)q * L + phi];
+            for (int c = 0; c < vec; c++) {
+                double xv = 0.0;
+                if (s >= 0)
+                    xv = in[s * vec + c];
+                else if (hist && s >= -(int64_t)nh)
+                    xv = hist[(nh + s) * vec + c];
+                acc[c] += h * xv;
+            }
+        }
+        for (int c = 0; c < vec; c++)
+            out[m * vec + c] = (float)acc[c];
+    }
+    return n_out;
+}
+ORC_API int64_t orc_resample_ccf_f64(float* out, const float* in, int64_t n_in, const float* taps, int T, int L,
+                                     int D, const float* hist)
+{
+    return resample_f64(out, in, n_in, taps, T, L, D, hist, 2);
+}
+ORC_API int64_t orc_resample_fff_f64(float* out, const float* in, int64_t n_in, const float* taps, int T, int L,
+                                     int D, const float* hist)
+{
+    return resample_f64(out, in, n_in, taps, T, L, D, hist, 1);
+}
+
 /* ---------------------------------------------------------------- window
  * 4-term 92 dB Blackman-Harris, symmetric:
  * w[n] = a0 - a1 cos(2 pi n/(N-1)) + a2 cos(4 pi n/(N-1)) - a3 cos(6 pi n/(N-1)). */

@@ -14,6 +14,7 @@
 #include <gnuradio/blocklib/cuda/multiply_const.hpp>
 #include <gnuradio/blocklib/cuda/null_source.hpp>
 #include <gnuradio/blocklib/cuda/pfb_channelizer.hpp>
+#include <gnuradio/blocklib/cuda/rational_resampler.hpp>
 #include <gnuradio/cudabuffer.hpp>
 #include <gnuradio/cudabuffer_pinned.hpp>
 #include <gnuradio/flowgraph.hpp>
@@ -29,6 +30,8 @@ using namespace gr;
 extern "C" {
 int64_t orc_fir_ccf_f64(float*, const float*, int64_t, const float*, int, int, const float*);
 int64_t orc_fir_fff_f64(float*, const float*, int64_t, const float*, int, int, const float*);
+int64_t orc_resample_ccf_f64(float*, const float*, int64_t, const float*, int, int, int, const float*);
+int64_t orc_resample_fff_f64(float*, const float*, int64_t, const float*, int, int, int, const float*);
 int orc_fft_f64(float*, const float*, int64_t, int, int, const float*, int);
 void orc_window_blackmanharris(float*, int);
 void orc_multiply_const_cc(float*, const float*, float, float, int64_t);
@@ -266,6 +269,47 @@ QA_TEST(Config1, FirFffDecim)
     orc_fir_fff_f64(exp.data(), in.data(), (int64_t)in.size(), taps.data(), 129, 5, nullptr);
     EXPECT_EQ(snk->data().size(), exp.size());
     EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+}
+
+// interpolating FIR and rational resampler as rate-changing blocks on device edges
+QA_TEST(Resampler, InterpAndRational)
+{
+    auto in = noise(300000, 11);
+    {
+        auto taps = rtaps(96, 12);
+        auto src = blocks::vector_source_c::make(in);
+        auto rs = cuda::interp_fir_filter_ccf::make(4, taps);
+        auto snk = blocks::vector_sink_c::make();
+        auto fg = flowgraph::make();
+        fg->connect(src, 0, rs, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 1u << 20));
+        fg->connect(rs, 0, snk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 1u << 20));
+        fg->set_scheduler(schedulers::scheduler_mt::make());
+        fg->validate();
+        fg->run();
+        std::vector<gr_complex> exp(in.size() * 4);
+        orc_resample_ccf_f64((float*)exp.data(), (const float*)in.data(), (int64_t)in.size(), taps.data(), 96, 4, 1, nullptr);
+        EXPECT_EQ(snk->data().size(), exp.size());
+        EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+    }
+    {
+        std::vector<float> inf(in.size());
+        for (size_t i = 0; i < inf.size(); i++)
+            inf[i] = in[i].imag();
+        auto taps = rtaps(211, 13);
+        auto src = blocks::vector_source_f::make(inf);
+        auto rs = cuda::rational_resampler_fff::make(3, 7, taps);
+        auto snk = blocks::vector_sink_f::make();
+        auto fg = flowgraph::make();
+        fg->connect(src, 0, rs, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 1u << 20));
+        fg->connect(rs, 0, snk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 1u << 20));
+        fg->set_scheduler(schedulers::scheduler_mt::make());
+        fg->validate();
+        fg->run();
+        std::vector<float> exp(inf.size() / 7 * 3);
+        orc_resample_fff_f64(exp.data(), inf.data(), (int64_t)inf.size(), taps.data(), 211, 3, 7, nullptr);
+        EXPECT_EQ(snk->data().size(), exp.size());
+        EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+    }
 }
 
 // BASELINE config 2 with real data: source -> fft(4096, Blackman-Harris) -> complex_to_mag -> sink,
