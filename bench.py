@@ -425,6 +425,37 @@ def run_b200(args):
         except Exception as e:  # pragma: no cover
             extras["config5_error"] = repr(e)
 
+    # ---- multi-GPU only: BASELINE config 4 (64-channel channelizer over the GPUs), both partitions
+    # of SURVEY.md 8(e): channel slices of ONE stream (every GPU reads the whole input, writes
+    # 64/world channels: does not scale for an HBM-bound kernel) and time segments with a
+    # (P-1)*M-sample halo (every GPU filters its own 2^27-sample segment, all 64 channels)
+    if dist is not None and 64 % world == 0:
+        try:
+            from newsched_b200 import multigpu as mg
+            import scipy.signal as sig
+            pt = sig.firwin(1024, 1 / 64).astype(np.float32)
+            cb, cc = mg.channel_slice(64, rank, world)
+            pfb_c = nb.PfbChannelizer(pt, 64, cb, cc)
+            yc = torch.empty((SAMPLES // 64, cc), dtype=torch.complex64, device=dev)
+            t = max_over_ranks(timed(torch, lambda: pfb_c.work_segment(x, None, yc), 5, 2, barrier) / 5)
+            c4 = {"channel_sharded_one_stream_Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "channel_sharded_ms": t,
+                  "channels_per_gpu": cc}
+            del yc
+            pfb_t = nb.PfbChannelizer(pt, 64)
+            yt = torch.empty((SAMPLES // 64, 64), dtype=torch.complex64, device=dev)
+
+            def seg_run():
+                halo = mg.exchange_halo(x, 15 * 64, rank, world)
+                pfb_t.work_segment(x, halo, yt)
+            t = max_over_ranks(timed(torch, seg_run, 5, 2, barrier) / 5)
+            c4["time_segmented_Msamples_s"] = world * SAMPLES / (t * 1e-3) / 1e6
+            c4["time_segmented_ms"] = t
+            c4["halo_bytes_per_rank"] = 15 * 64 * 8
+            extras["config4_channelizer_64ch"] = c4
+            del yt
+        except Exception as e:  # pragma: no cover
+            extras["config4_error"] = repr(e)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
