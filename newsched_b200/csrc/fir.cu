@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fir_ffa.cuh"
 #include "fir_ols.cuh"
 
 namespace b200 {
@@ -379,6 +380,7 @@ struct b200_fir {
     size_t smem = 0;
     int use_tma = 1;
     ols_plan* ols = nullptr; // algorithm 3
+    ffa_plan* ffa = nullptr; // algorithm 5
     int algorithm = 1;
     fir_epilogue ep{ 0, 1.f, 0.f };
     float* d_taps_pp = nullptr; // [D][TQ] reversed per phase
@@ -432,6 +434,8 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
     float* y = (float*)d_out;
     if (h->algorithm == 3)
         return ols_launch(h->ols, d_hist, d_in, d_out, n_in, n_out, s);
+    if (h->algorithm == 5)
+        return ffa_launch(h->ffa, d_hist, d_in, d_out, n_in, n_out, s);
     if (h->algorithm == 1) {
         const int MT = FIR_NT * (FIR_ACC / h->vec);
         long long tiles = (n_out + MT - 1) / MT;
@@ -505,6 +509,7 @@ int b200_fir_destroy(b200_fir* h)
     cudaFree(h->d_hist[0]);
     cudaFree(h->d_hist[1]);
     ols_destroy(h->ols);
+    ffa_destroy(h->ffa);
     delete h;
     return B200_OK;
 }
@@ -569,6 +574,34 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
             }
             h->algorithm = 3;
         }
+    }
+
+    // 2-parallel fast FIR (algorithm 5): full-rate filters in the FP32-bound range below the
+    // overlap-save crossover execute 0.77x the FMAs of the direct form
+    if (h->algorithm == 1 && h->D == 1) {
+        const bool can5 = ffa_supported(h->T, h->D, h->vec == 1);
+        bool want5 = p->algorithm == 5;
+        // measured (tools/ffa_sweep.py): 0.70x the per-tap cost of the direct form but 3x its fixed
+        // cost per tile, so it loses below ~100 taps (64 taps: 192 vs 214 GS/s) and overlap-save wins
+        // above: never picked automatically, kept selectable (algorithm = 5 / B200_FIR_ALGO=5)
+        if (const char* e = getenv("B200_FIR_ALGO"))
+            if (p->algorithm == 0)
+                want5 = atoi(e) == 5;
+        if (p->algorithm == 5 && !can5) {
+            b200_fir_destroy(h);
+            return set_err(B200_ERR_UNSUPPORTED, "fir_create: the 2-parallel form needs decimation 1 and 4..2048 taps");
+        }
+        if (want5 && can5) {
+            int rc = ffa_create(p->taps, h->T, h->vec == 1, h->ep.fuse, h->ep.kre, h->ep.kim, &h->ffa);
+            if (rc != B200_OK) {
+                b200_fir_destroy(h);
+                return rc;
+            }
+            h->algorithm = 5;
+        }
+    } else if (p->algorithm == 5) {
+        b200_fir_destroy(h);
+        return set_err(B200_ERR_UNSUPPORTED, "fir_create: the 2-parallel form needs decimation 1");
     }
 
 #define FIR_CUDA(call)                                                                   \

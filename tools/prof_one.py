@@ -25,6 +25,8 @@ elif what.startswith("fftn"):
     op = nb.FFT(Nn, True, w2); out = torch.empty_like(x); fn = lambda: op.work(x, out)
 elif what == "fir64":
     op = nb.FirFilter((rng.uniform(-1, 1, 64) / 64).astype(np.float32)); out = torch.empty_like(x); fn = lambda: op.work_segment(x, None, out)
+elif what == "ffa64":
+    op = nb.FirFilter((rng.uniform(-1, 1, 64) / 64).astype(np.float32), algorithm=5); out = torch.empty_like(x); fn = lambda: op.work_segment(x, None, out)
 elif what == "fir1024d4":
     op = nb.FirFilter((rng.uniform(-1, 1, 1024) / 1024).astype(np.float32), 4); out = torch.empty(n // 4, dtype=torch.complex64, device="cuda"); fn = lambda: op.work_segment(x, None, out)
 elif what == "fir4096":
