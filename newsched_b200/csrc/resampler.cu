@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(RS_NT)
 {
     extern __shared__ __align__(16) float rs_sm[];
     float* sT = rs_sm;                     // [L][TqP]
-    float* sX = rs_sm + g.L * g.TqP;       // [span][VEC]
+    float* sX = rs_sm + ((g.L * g.TqP + 3) & ~3); // [span][VEC]
     const int tid = threadIdx.x;
     for (int i = tid; i < g.L * g.TqP; i += RS_NT)
         sT[i] = __ldg(taps_pp + i);
@@ -105,6 +105,118 @@ __global__ void __launch_bounds__(RS_NT)
     }
 }
 
+// Register-blocked form for D <= 4 and L <= 256.  Outputs that share a residue rho = m mod L share
+// the tap row phi = rho*D mod L and their input index advances by exactly D per output, so a thread
+// that owns R such outputs (m = m_base + r*L) runs a plain D-strided FIR: per chunk of 8 taps it
+// loads (R-1)*D + 8 samples and 8 taps once and issues 8R packed FMAs on them (D = 1, R = 15:
+// 120 FFMA2 per 30 LDS instead of 1 per 1).  Lanes walk the residues, i.e. adjacent lanes read the
+// same or neighbouring samples (broadcast) and different tap rows (odd row stride: conflict-free).
+// Outputs go back through shared memory so global stores are whole lines.
+template <int VEC, int D, int R>
+__global__ void __launch_bounds__(RS_NT)
+    resample_rb_kernel(const float* __restrict__ x, const float* __restrict__ hist, float* __restrict__ y,
+                       const float* __restrict__ taps_pp, rs_geom g, int tpt /* active threads, multiple of L */)
+{
+    constexpr int WL = (R - 1) * D + 8; // window samples per chunk
+    extern __shared__ __align__(16) float rs_sm[];
+    float* sT = rs_sm;               // [L][TqP], zero padded to a multiple of 8 taps
+    float* sX = rs_sm + ((g.L * g.TqP + 3) & ~3); // [span][VEC], 16-byte aligned; reused for the output tile
+    const int tid = threadIdx.x;
+    for (int i = tid; i < g.L * g.TqP; i += RS_NT)
+        sT[i] = __ldg(taps_pp + i);
+    const int TqPad = (g.Tq + 7) & ~7;
+    const long long MTt = (long long)tpt * R;
+    const long long m0 = (long long)blockIdx.x * MTt; // multiple of L
+    const long long j_lo = (m0 * D) / g.L - (TqPad - 1);
+    const long long j_hi = ((m0 + MTt - 1) * D) / g.L;
+    const int span = (int)(j_hi - j_lo + 1);
+    const int nh = g.Tq - 1;
+    if (j_lo >= 0 && j_lo + span <= g.n_in) {
+        // interior tile: asynchronous global -> shared copies, all of a thread's in flight at once
+        const float* src = x + j_lo * VEC;
+        for (int i = tid; i < span; i += RS_NT) {
+            if (VEC == 2)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sX + 2 * i)), "l"(src + 2 * i)
+                             : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sX + i)), "l"(src + i)
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int i = tid; i < span; i += RS_NT) {
+            float v[VEC];
+            rs_load<VEC>(v, x, hist, nh, j_lo + i, g.n_in);
+#pragma unroll
+            for (int c = 0; c < VEC; c++)
+                sX[i * VEC + c] = v[c];
+        }
+    }
+    __syncthreads();
+    float acc[R * VEC];
+#pragma unroll
+    for (int l = 0; l < R * VEC; l++)
+        acc[l] = 0.f;
+    const int rho = tid % g.L, kb = tid / g.L;
+    if (tid < tpt) {
+        const long long i0 = (m0 + (long long)kb * R * g.L + rho) * D; // m_base * D
+        const int phi = (int)(i0 % g.L);
+        const int jj = (int)(i0 / g.L - j_lo); // x[j_0] = sX[jj]; output r uses x[j_0 + r D - q]
+        const float* h = sT + phi * g.TqP;
+        for (int q0 = 0; q0 < TqPad; q0 += 8) {
+            float hv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                hv[u] = h[q0 + u];
+            float w[WL * VEC];
+            const float* wp = sX + (jj - q0 - 7) * VEC; // w[i] = x[j_0 - q0 - 7 + i]
+#pragma unroll
+            for (int i = 0; i < WL; i++) {
+                if (VEC == 2) {
+                    const float2 t = *reinterpret_cast<const float2*>(wp + 2 * i);
+                    w[2 * i] = t.x;
+                    w[2 * i + 1] = t.y;
+                } else
+                    w[i] = wp[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int i = r * D - u + 7;
+                    if (VEC == 2) {
+                        const float2 a = __ffma2_rn(make_float2(w[2 * i], w[2 * i + 1]), make_float2(hv[u], hv[u]),
+                                                    make_float2(acc[2 * r], acc[2 * r + 1]));
+                        acc[2 * r] = a.x;
+                        acc[2 * r + 1] = a.y;
+                    } else
+                        acc[r] = fmaf(hv[u], w[i], acc[r]);
+                }
+        }
+    }
+    __syncthreads(); // input tile consumed: the output tile goes on top of it
+    if (tid < tpt) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int o = (kb * R + r) * g.L + rho; // output index within the tile
+            if (VEC == 2)
+                *reinterpret_cast<float2*>(sX + 2 * o) = make_float2(acc[2 * r], acc[2 * r + 1]);
+            else
+                sX[o] = acc[r];
+        }
+    }
+    __syncthreads();
+    const long long left = g.n_out - m0;
+    const int n_tile = (int)(left < MTt ? left : MTt);
+    for (int i = tid; i < n_tile; i += RS_NT) {
+        if (VEC == 2)
+            __stcs(reinterpret_cast<float2*>(y) + m0 + i, *reinterpret_cast<const float2*>(sX + 2 * i));
+        else
+            __stcs(y + m0 + i, sX[i]);
+    }
+}
+
 // new history = last nh samples of [old history | first n_cons input samples]
 __global__ void rs_hist_kernel(const float* __restrict__ x, const float* __restrict__ h_old,
                                float* __restrict__ h_new, long long n_cons, int nh, int vec)
@@ -128,7 +240,31 @@ struct b200_resampler {
     float* d_taps_pp = nullptr;
     float* d_hist[2] = { nullptr, nullptr };
     int cur = 0;
+    int rb_R = 0;   // > 0: register-blocked kernel with R outputs per thread
+    int rb_tpt = 0; // its active threads per CTA (multiple of L)
+    size_t rb_smem = 0;
 };
+
+template <int VEC>
+static int rs_launch_rb(b200_resampler* h, const float* d_hist, const void* d_in, void* d_out, rs_geom g,
+                        cudaStream_t s)
+{
+    const long long per = (long long)h->rb_tpt * h->rb_R;
+    const long long tiles = (g.n_out + per - 1) / per;
+    if (tiles > 0x7fffffffLL)
+        return set_err(B200_ERR_ARG, "resampler: too many items for one call");
+#define RS_GO(DD, RR)                                                                                     \
+    B200_LAUNCH((resample_rb_kernel<VEC, DD, RR>), (unsigned)tiles, RS_NT, h->rb_smem, s, (const float*)d_in, \
+                d_hist, (float*)d_out, h->d_taps_pp, g, h->rb_tpt)
+    switch (h->D) {
+    case 1: RS_GO(1, 15); break;
+    case 2: RS_GO(2, 7); break;
+    case 3: RS_GO(3, 6); break;
+    default: RS_GO(4, 3); break;
+    }
+#undef RS_GO
+    return B200_OK;
+}
 
 static int rs_launch(b200_resampler* h, const float* d_hist, const void* d_in, void* d_out, long long n_in,
                      long long n_out, cudaStream_t s)
@@ -138,6 +274,8 @@ static int rs_launch(b200_resampler* h, const float* d_hist, const void* d_in, v
     rs_geom g = h->g;
     g.n_in = n_in;
     g.n_out = n_out;
+    if (h->rb_R > 0)
+        return h->vec == 2 ? rs_launch_rb<2>(h, d_hist, d_in, d_out, g, s) : rs_launch_rb<1>(h, d_hist, d_in, d_out, g, s);
     const long long tiles = (n_out + g.MT - 1) / g.MT;
     if (tiles > 0x7fffffffLL)
         return set_err(B200_ERR_ARG, "resampler: too many items for one call");
@@ -179,7 +317,7 @@ int b200_resampler_create(const b200_resampler_params* p, b200_resampler** out)
     g.L = h->L;
     g.D = h->D;
     g.Tq = (h->T + h->L - 1) / h->L;
-    g.TqP = g.Tq | 1;
+    g.TqP = ((g.Tq + 7) & ~7) | 1; // rows zero-padded to whole 8-tap chunks, odd stride
     // outputs per tile: as many as keep the staged input span within RS_SPAN samples
     const long long room = (long long)(RS_SPAN - g.Tq - 2) * h->L / h->D;
     if ((long long)g.L * g.TqP > RS_MAX_TAPS || room < 32) {
@@ -190,7 +328,23 @@ int b200_resampler_create(const b200_resampler_params* p, b200_resampler** out)
                        h->T, h->L, h->D);
     }
     g.MT = (int)std::min<long long>(4 * RS_NT, room);
-    h->smem = sizeof(float) * ((size_t)g.L * g.TqP + (size_t)RS_SPAN * h->vec);
+    h->smem = sizeof(float) * ((size_t)g.L * g.TqP + 4 + (size_t)RS_SPAN * h->vec);
+    // register-blocked kernel: D <= 4, L <= 256, and the tile's input span / output tile fit
+    if (h->D <= 4 && h->L <= RS_NT && !getenv("B200_RESAMPLER_SIMPLE")) {
+        // R*D is the distance (in samples) between the windows of adjacent threads of a residue: kept
+        // off multiples of 16 samples (128 B) so that their LDS.64 window reads hit different banks
+        static const int Rtab[5] = { 0, 15, 7, 6, 3 };
+        const int R = Rtab[h->D];
+        const int tpt = RS_NT / h->L * h->L;
+        const long long mt = (long long)tpt * R;
+        const long long span = (mt * h->D) / h->L + ((g.Tq + 7) & ~7) + 2;
+        const long long cells = std::max(span, mt);
+        if (cells <= 3 * RS_SPAN) {
+            h->rb_R = R;
+            h->rb_tpt = tpt;
+            h->rb_smem = sizeof(float) * ((size_t)g.L * g.TqP + 4 + (size_t)cells * h->vec);
+        }
+    }
 #define RS_CUDA(call)                                                                        \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \
@@ -215,6 +369,17 @@ int b200_resampler_create(const b200_resampler_params* p, b200_resampler** out)
     }
     RS_CUDA(cudaFuncSetAttribute(resample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     RS_CUDA(cudaFuncSetAttribute(resample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define RS_ATTR(V, DD, RR) \
+    RS_CUDA(cudaFuncSetAttribute(resample_rb_kernel<V, DD, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+    RS_ATTR(2, 1, 15);
+    RS_ATTR(2, 2, 7);
+    RS_ATTR(2, 3, 6);
+    RS_ATTR(2, 4, 3);
+    RS_ATTR(1, 1, 15);
+    RS_ATTR(1, 2, 7);
+    RS_ATTR(1, 3, 6);
+    RS_ATTR(1, 4, 3);
+#undef RS_ATTR
 #undef RS_CUDA
     *out = h;
     return B200_OK;

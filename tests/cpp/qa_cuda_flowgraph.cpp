@@ -15,6 +15,7 @@
 #include <gnuradio/blocklib/cuda/null_source.hpp>
 #include <gnuradio/blocklib/cuda/pfb_channelizer.hpp>
 #include <gnuradio/blocklib/cuda/rational_resampler.hpp>
+#include <gnuradio/blocklib/cuda/stream_to_vector.hpp>
 #include <gnuradio/cudabuffer.hpp>
 #include <gnuradio/cudabuffer_pinned.hpp>
 #include <gnuradio/flowgraph.hpp>
@@ -346,6 +347,33 @@ QA_TEST(Config2, FftMag)
         EXPECT_EQ(snk->data().size(), exp.size());
         EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
     }
+}
+
+// stream -> vector -> fft (vector input) -> vector -> stream: the item-size adapters around a
+// vector block; equals the stream-input fft bit for bit
+QA_TEST(Adapters, StreamToVectorAndBack)
+{
+    const int N = 1024, nv = 200;
+    auto in = noise((size_t)N * nv + 77, 17); // 77 trailing samples never fill a vector
+    std::vector<float> w(N);
+    orc_window_blackmanharris(w.data(), N);
+    std::vector<gr_complex> exp((size_t)N * nv);
+    orc_fft_f64((float*)exp.data(), (const float*)in.data(), nv, N, 1, w.data(), 0);
+    auto src = blocks::vector_source_c::make(in);
+    auto s2v = cuda::stream_to_vector::make(sizeof(gr_complex), N);
+    auto f = cuda::fft::make(N, true, w);
+    auto v2s = cuda::vector_to_stream::make(sizeof(gr_complex), N);
+    auto snk = blocks::vector_sink_c::make();
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, s2v, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 1u << 20));
+    fg->connect(s2v, 0, f, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2D, 1u << 20));
+    fg->connect(f, 0, v2s, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2D, 1u << 20));
+    fg->connect(v2s, 0, snk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 1u << 20));
+    fg->set_scheduler(schedulers::scheduler_mt::make());
+    fg->validate();
+    fg->run();
+    EXPECT_EQ(snk->data().size(), exp.size());
+    EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
 }
 
 // config 2 as written: device null_source (finite) -> fft -> complex_to_mag -> null_sink, nothing on the host
