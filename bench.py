@@ -378,7 +378,9 @@ def run_b200(args):
                     ("config2_fft4096_mag_1Gi_stream", ["--config", "2", "--samples", str(1 << 30)]),
                     ("config2_unfused_fft_then_mag_1Gi", ["--config", "2", "--samples", str(1 << 30), "--fused", "0"]),
                     ("config1_fir_ccf_64taps_1Gi", ["--config", "1", "--samples", str(1 << 30)]),
+                    ("config1_fir_ccf_64taps_8Gi_stream", ["--config", "1", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_1Gi", ["--config", "3", "--samples", str(1 << 30)]),
+                    ("config3_fir1024d4_mulc_fft_8Gi_stream", ["--config", "3", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
                     ("cuda_copy_x4_1Gi", ["--config", "0", "--samples", str(1 << 30)])):
                 best = None
                 for _ in range(3):
