@@ -116,6 +116,12 @@ public:
     std::string type() { return _type; }
     uint64_t total_written() const { return _total_written; }
     uint64_t total_read() const { return _total_read; }
+    // items written but not yet read, sampled under the buffer's own lock (safe from any thread)
+    uint64_t items_pending()
+    {
+        std::scoped_lock g(_buf_mutex);
+        return _total_written - _total_read;
+    }
 
     // end-of-stream: set by the scheduler when the block feeding this edge has finished
     void set_writer_done() { _writer_done.store(true, std::memory_order_release); }

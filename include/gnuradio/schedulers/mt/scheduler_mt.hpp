@@ -206,7 +206,7 @@ class thread_wrapper : public neighbor_interface
                 bool output_pending = false;
                 for (auto& p : out_ports)
                     for (auto& buf : _bufman->get_output_buffers(p))
-                        output_pending |= !buf->reader_done() && buf->total_written() != buf->total_read();
+                        output_pending |= !buf->reader_done() && buf->items_pending() != 0;
                 if (output_pending)
                     return executor_iteration_status::BLKD_OUT;
                 finish_block(bi);

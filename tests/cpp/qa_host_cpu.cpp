@@ -162,6 +162,62 @@ QA_TEST(SchedulerMTTest, NullSourceHeadCounts)
     EXPECT_TRUE(all_zero);
 }
 
+// test-only interpolator: every input item repeated L times; needs L free output items per input,
+// so it returns 0/0 whenever downstream has left it fewer than L
+class cpu_repeat : public block
+{
+    int L;
+
+public:
+    static std::shared_ptr<cpu_repeat> make(int L_)
+    {
+        auto p = std::make_shared<cpu_repeat>(L_);
+        p->add_port(port<float>::make("input", port_direction_t::INPUT));
+        p->add_port(port<float>::make("output", port_direction_t::OUTPUT));
+        return p;
+    }
+    explicit cpu_repeat(int L_) : block("repeat"), L(L_) {}
+    work_return_code_t work(std::vector<block_work_input>& in, std::vector<block_work_output>& out) override
+    {
+        int n = std::min(in[0].n_items, out[0].n_items / L);
+        auto* i = (const float*)in[0].buffer->read_ptr();
+        auto* o = (float*)out[0].buffer->write_ptr();
+        for (int m = 0; m < n; m++)
+            for (int r = 0; r < L; r++)
+                o[m * L + r] = i[m];
+        in[0].n_consumed = n;
+        out[0].n_produced = n * L;
+        return work_return_code_t::WORK_OK;
+    }
+};
+
+// A block with an output multiple must not be retired at end of stream just because downstream
+// momentarily left it fewer than L free items (0/0 work with all inputs done): every input item
+// has to come out L times.  Small rings make the 0/0-while-output-pending case certain.
+QA_TEST(SchedulerMTTest, OutputMultipleDrain)
+{
+    for (int L : { 2, 5, 64, 1000 }) {
+        std::vector<float> in(20011);
+        for (size_t i = 0; i < in.size(); i++)
+            in[i] = (float)i;
+        auto src = blocks::vector_source_f::make(in);
+        auto rep = cpu_repeat::make(L);
+        auto snk = blocks::vector_sink_f::make();
+        auto fg = flowgraph::make();
+        fg->connect(src, 0, rep, 0);
+        fg->connect(rep, 0, snk, 0);
+        fg->set_scheduler(schedulers::scheduler_mt::make("s", 8192));
+        fg->validate();
+        fg->run();
+        auto out = snk->data();
+        EXPECT_EQ(out.size(), in.size() * (size_t)L);
+        bool ok = out.size() == in.size() * (size_t)L;
+        for (size_t m = 0; ok && m < out.size(); m++)
+            ok &= out[m] == in[m / L];
+        EXPECT_TRUE(ok);
+    }
+}
+
 // rate-changing gr::block (n_consumed != n_produced), 0/0 work calls and the tail shorter than D
 QA_TEST(SchedulerMTTest, RateChangeAndDrain)
 {
