@@ -3,6 +3,13 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef B200_PK_ROT
+#define B200_PK_ROT 1 // +-j rotations as one packed add: bit-identical results, +0.5-1 % (measured)
+#endif
+#ifndef B200_PK_W16
+#define B200_PK_W16 0 // packed constant twiddles: within +-2 % either way per kernel (measured), off
+#endif
+
 namespace b200 {
 
 constexpr float C8 = 0.92387953251128674f;  // cos(pi/8)
@@ -25,6 +32,12 @@ __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d)
     float2 t0 = a + c, t1 = a - c, t2 = b + d, t3 = b - d;
     a = t0 + t2;
     c = t0 - t2;
+#if B200_PK_ROT
+    // t1 -/+ j t3: one packed add each, the rotated operand is a swap + negate modifier (FADD2 ... LO_HI.NP)
+    const float2 mj = make_float2(t3.y, -t3.x), pj = make_float2(-t3.y, t3.x);
+    b = __fadd2_rn(t1, FWD ? mj : pj);
+    d = __fadd2_rn(t1, FWD ? pj : mj);
+#else
     if (FWD) {
         b = make_float2(t1.x + t3.y, t1.y - t3.x);
         d = make_float2(t1.x - t3.y, t1.y + t3.x);
@@ -32,6 +45,7 @@ __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d)
         b = make_float2(t1.x - t3.y, t1.y + t3.x);
         d = make_float2(t1.x + t3.y, t1.y - t3.x);
     }
+#endif
 }
 
 // multiply by W16^m (forward: e^{-j 2 pi m/16}; reverse: conjugate), m compile-time
@@ -46,7 +60,13 @@ __device__ __forceinline__ float2 mul_w16(float2 z)
         return z;
     if (M == 4)
         return FWD ? make_float2(z.y, -z.x) : make_float2(-z.y, z.x);
+#if B200_PK_W16
+    // z * (wr + j wi) in two packed instructions (see cmul in common.cuh)
+    const float2 r = __fmul2_rn(z, make_float2(wr, wr));
+    return __ffma2_rn(make_float2(-z.y, z.x), make_float2(wi, wi), r);
+#else
     return make_float2(fmaf(-z.y, wi, z.x * wr), fmaf(z.x, wi, z.y * wr));
+#endif
 }
 
 // 16-point DFT in registers.  Input natural order v[n]; output X[k] lands in v[pos16(k)].

@@ -38,11 +38,6 @@ struct ols_geom {
     long long n_in, n_out, n_blocks;
 };
 
-__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) // a * conj(b)
-{
-    return make_float2(fmaf(a.y, b.y, a.x * b.x), fmaf(-a.x, b.y, a.y * b.x));
-}
-
 __device__ __forceinline__ float2 ols_fetch(const float2* __restrict__ x, const float2* __restrict__ hist,
                                             int Tm1, long long g, long long n_in)
 {
@@ -392,8 +387,7 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
                 for (int k2 = 0; k2 < 16; k2++) {
                     const float2 w = __ldg(G + k2 * 256), a = v[pos16(k2)];
-                    acc[k2].x = fmaf(a.x, w.x, fmaf(-a.y, w.y, acc[k2].x));
-                    acc[k2].y = fmaf(a.x, w.y, fmaf(a.y, w.x, acc[k2].y));
+                    acc[k2] = cmac(a, w, acc[k2]);
                 }
             }
             __syncthreads(); // pass-3 reads of sA done before the next transform's pass-1 writes

@@ -19,6 +19,13 @@
 
 #include "common.cuh"
 
+#ifndef B200_PK_ROT
+#define B200_PK_ROT 1 // +-j rotations as one packed add: bit-identical results, +0.5-1 % (measured)
+#endif
+#ifndef B200_PK_W16
+#define B200_PK_W16 0 // packed constant twiddles: within +-2 % either way per kernel (measured), off
+#endif
+
 namespace b200 {
 
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
@@ -30,13 +37,23 @@ __device__ __forceinline__ void idft4(float2& a, float2& b, float2& c, float2& d
     float2 t0 = f2add(a, c), t1 = f2sub(a, c), t2 = f2add(b, d), t3 = f2sub(b, d);
     a = f2add(t0, t2);
     c = f2sub(t0, t2);
+#if B200_PK_ROT
+    b = __fadd2_rn(t1, make_float2(-t3.y, t3.x)); // t1 + j t3: one packed add, swap + negate operand modifier
+    d = __fadd2_rn(t1, make_float2(t3.y, -t3.x));
+#else
     b = make_float2(t1.x - t3.y, t1.y + t3.x);
     d = make_float2(t1.x + t3.y, t1.y - t3.x);
+#endif
 }
 
 __device__ __forceinline__ float2 cmulc(float2 z, float wr, float wi)
 {
+#if B200_PK_W16
+    const float2 r = __fmul2_rn(z, make_float2(wr, wr)); // two packed instructions, see cmul (common.cuh)
+    return __ffma2_rn(make_float2(-z.y, z.x), make_float2(wi, wi), r);
+#else
     return make_float2(fmaf(-z.y, wi, z.x * wr), fmaf(z.x, wi, z.y * wr));
+#endif
 }
 
 // reverse 16-point DFT, output X[k] in v[4*(k&3) + (k>>2)]
