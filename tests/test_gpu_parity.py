@@ -529,6 +529,57 @@ def test_fir_config1_size_linearity(cuda):
         assert o.rel_rms(host(y1[s:s + 4096]), ref) < TOL_RMS
 
 
+@pytest.mark.parametrize("T,D,log2n", [(1024, 4, 28), (4096, 1, 27), (256, 1, 26)])
+def test_fir_long_filters_full_size_properties(cuda, T, D, log2n):
+    """BASELINE config 3 head (2^28 samples, 1024 taps, decim 4: polyphase overlap-save), config 5
+    per-GPU segment (2^27 samples, 4096 taps: two-phase overlap-save) and a one-phase overlap-save
+    size, through size-independent properties: linearity, oracle spot checks on windows at the
+    start / middle / end of the stream, and the response to impulses placed deep in the stream
+    (output index = input index / D exactly: decimation phase and 64-bit indexing)."""
+    import newsched_b200 as nb
+    n = 1 << log2n
+    g = cuda.Generator(device="cuda").manual_seed(T + D)
+    x1 = cuda.view_as_complex(cuda.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    x2 = cuda.view_as_complex(cuda.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    rng = np.random.default_rng(T)
+    taps = (rng.uniform(-1, 1, T) / np.sqrt(T)).astype(np.float32)
+    f = nb.FirFilter(taps, D)
+    assert f.algorithm == 3
+    y1 = f.work_segment(x1)
+    y2 = f.work_segment(x2)
+    x1 += x2
+    y12 = f.work_segment(x1)
+    x1 -= x2                                     # (fp32: x1 is back to within 1 ulp; only used for windows below)
+    y1 += y2
+    err = (y12 - y1).abs().pow(2).mean().sqrt() / y12.abs().pow(2).mean().sqrt()
+    assert float(err) < TOL_RMS
+    del y1, y12
+    # oracle on windows: outputs [m0, m0 + 2048) need inputs [m0*D - (T-1), (m0 + 2048)*D)
+    for m0 in (0, (n // D) // 2 + 12345, n // D - 2048):
+        skip = -(-(T - 1) // D) if m0 else 0        # whole outputs of lead-in, so the window starts on phase 0
+        lo = (m0 - skip) * D
+        seg = host(x2[lo:(m0 + 2048) * D])
+        ref = o.fir(seg, taps, D)
+        assert o.rel_rms(host(y2[m0:m0 + 2048]), ref[skip:skip + 2048]) < TOL_RMS
+    del y2
+    # impulses deep in the stream: h[k] appears at output (g0 + k) / D when D divides g0 + k
+    x1.zero_()
+    spots = [7, n // 2 + 3 * D + 1, n - 2 * T - 5]
+    for i, g0 in enumerate(spots):
+        x1[g0] = complex(1 + i, -(1 + i))
+    y = f.work_segment(x1)
+    hn = float(np.sqrt(np.sum(taps.astype(np.float64) ** 2)))   # FFT rounding scales with ||h||_2 * |amplitude|
+    for i, g0 in enumerate(spots):
+        m_lo = -(-g0 // D)
+        k = np.arange(m_lo * D - g0, T, D)
+        exp = taps[k].astype(np.complex64) * np.complex64(complex(1 + i, -(1 + i)))
+        got = host(y[m_lo:m_lo + k.size])
+        assert np.max(np.abs(got - exp)) < 2e-6 * hn * (1 + i) * np.sqrt(2), (T, D, g0)
+    # and nothing anywhere else (between the second and third response)
+    quiet = y[(spots[1] + T) // D + 4096:(spots[2]) // D - 4096]
+    assert float(quiet.abs().max()) < 1e-6 * hn
+
+
 # ------------------------------------------------------------------------------- FFT
 @pytest.mark.parametrize("key,fwd,shift", [("fft_fwd", True, False), ("fft_fwd_shift", True, True),
                                            ("fft_rev", False, False), ("fft_rev_shift", False, True)])
