@@ -32,6 +32,9 @@
 
 namespace b200 {
 
+#ifndef FIR_MINB
+#define FIR_MINB 5
+#endif
 constexpr int FIR_NT = 128;  // threads per CTA
 constexpr int FIR_ACC = 32;  // fp32 accumulators per thread
 constexpr int FIR_RING = 64; // register window (floats)
@@ -153,7 +156,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // edge tiles).  DECIM = true: decimating filters -- phase de-interleave with cp.async.  (Keeping
 // the cp.async path out of the D == 1 kernel is worth ~10 % on short filters: measured A/B.)
 template <int VEC, bool DECIM>
-__global__ void __launch_bounds__(FIR_NT, 5)
+__global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
                       const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
