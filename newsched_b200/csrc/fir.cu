@@ -559,7 +559,10 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         // beats the direct kernel from ~96 taps per output; the polyphase form of a decimating
         // complex filter already from ~40 (even D, TMA-staged; at 32 the two are within 5 %) / ~64 (odd D)
         const int poly = can ? ols_polyphase(h->T, h->D, h->vec == 1) : 0;
-        const int cross = poly == 1 ? 40 : poly == 2 ? 64 : 96;
+        // full-rate filters: the direct kernel pays for taps in pairs of 16-tap steps (64, 96, 128 ...), so
+        // 65..96 taps cost 1.5x 64 taps (151 vs 214 GS/s at 16 Mi samples) while overlap-save stays at
+        // ~185 (tools/cross_ab.py): switch right after 64 taps, complex and real alike
+        const int cross = poly == 1 ? 40 : poly == 2 ? 64 : h->D == 1 ? 65 : 96;
         if (p->algorithm == 0 && can && h->T / h->D >= cross)
             want = true;
         if (const char* e = getenv("B200_FIR_ALGO"))
