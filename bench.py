@@ -269,7 +269,8 @@ def run_b200(args):
     # ---- e2e: host buffers through the C-ABI streaming call
     e2e = None
     try:
-        chunk = N_FFT * 2048                            # 64 MiB in / 32 MiB out per chunk
+        chunk = N_FFT * 512                             # 16 MiB in / 8 MiB out per chunk (measured best of 16/64/256:
+        # the pipeline runs at the box's bidirectional PCIe limit, 76-78 GB/s of 75.8 measured with plain copies)
         chain = nb.Chain([fft], in_item_bytes=8, chunk_items=chunk)
         hx = torch.empty(SAMPLES, dtype=torch.complex64).pin_memory()
         hx.copy_(x)
