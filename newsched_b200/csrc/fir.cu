@@ -91,7 +91,9 @@ __device__ __forceinline__ void fir_fetch(const float* __restrict__ x, const flo
 // One step of CH taps against the register ring.  OFF = ring offset (floats) of the thread's row;
 // tap q' of the step meets ring element (q'+1): the window is read from one sample early so that
 // BOTH the input window and the output tile start on 128-byte rows (TMA load and TMA store).
-template <int VEC, int CH, int OFF>
+// DD > 1 (decimation folded into the full-rate kernel): only every DD-th output position of the
+// window owns an accumulator, the taps stay in natural order.
+template <int VEC, int CH, int OFF, int DD = 1>
 __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)[FIR_RING],
                                          const float* __restrict__ hs)
 {
@@ -107,7 +109,7 @@ __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)
                 // other resident warps issue underneath the FMA pipe
                 const float2 h2 = make_float2(hv[u], hv[u]);
 #pragma unroll
-                for (int l = 0; l < FIR_ACC; l += 2) {
+                for (int l = 0; l < FIR_ACC; l += 2 * DD) {
                     const int i = (OFF + (q4 + u + 1) * VEC + l) % FIR_RING;
                     float2 a = __ffma2_rn(make_float2(W[i], W[i + 1]), h2, make_float2(acc[l], acc[l + 1]));
                     acc[l] = a.x;
@@ -115,7 +117,7 @@ __device__ __forceinline__ void fir_step(float (&acc)[FIR_ACC], const float (&W)
                 }
             } else {
 #pragma unroll
-                for (int l = 0; l < FIR_ACC; l++)
+                for (int l = 0; l < FIR_ACC; l += DD)
                     acc[l] = fmaf(hv[u], W[(OFF + (q4 + u + 1) * VEC + l) % FIR_RING], acc[l]);
             }
         }
@@ -155,16 +157,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // DECIM = false: D == 1 instantiation (TMA for interior tiles, register-staged loads for the few
 // edge tiles).  DECIM = true: decimating filters -- phase de-interleave with cp.async.  (Keeping
 // the cp.async path out of the D == 1 kernel is worth ~10 % on short filters: measured A/B.)
-template <int VEC, bool DECIM>
+// DD > 1 (with DECIM = false): decimation by a divisor of the 16 (32) window positions of a thread.
+// The tile is the SAME 2048-sample (4096 for fff) input tile as for D = 1, staged by the same single
+// TMA tensor load with the taps in natural order; a thread simply keeps accumulators only for the
+// positions 0, DD, 2 DD ... of its row, i.e. 16/DD outputs, and the output tile shrinks to 128/DD rows.
+// No phase planes, no per-sample de-interleaving copies: a short decimating filter becomes HBM-bound
+// like a short full-rate one (64 taps, decimation 4: 197 -> 400+ GS/s input rate).
+template <int VEC, bool DECIM, int DD = 1>
 __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
                       const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
                       fir_geom gm, fir_epilogue ep)
 {
-    constexpr int R = FIR_ACC / VEC;  // outputs per thread
+    constexpr int R = FIR_ACC / VEC;  // window positions per thread (= outputs per thread for DD == 1)
     constexpr int CH = FIR_ACC / VEC; // taps per step
-    constexpr int MT = FIR_NT * R;    // outputs per tile
+    constexpr int MT = FIR_NT * R;    // input-rate positions per tile
+    constexpr int MTO = MT / DD;      // outputs per tile
+    static_assert(!DECIM || DD == 1, "DD applies to the TMA-staged full-rate kernel only");
+    static_assert(R % DD == 0, "decimation must divide the positions per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* hs = reinterpret_cast<float*>(smem_raw + 16);
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     const int tid = threadIdx.x;
     const long long tile = blockIdx.x;
     const long long B0 = tile * MT - TQ; // x_p index of plane element 0
-    const long long O0 = tile * MT;      // first output of this tile
+    const long long O0 = tile * MTO;     // first output of this tile
     const int PLs = (gm.plane_rows << 5) / VEC;            // samples per plane
 
     // interior tile of a D == 1 filter: one TMA tensor copy stages the whole window
@@ -271,9 +282,9 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         fir_load_half<0>(W, plane, tid);
         for (int b = 0; b < nsteps; b += 2) {
             fir_load_half<1>(W, plane, tid + b + 1);
-            fir_step<VEC, CH, 0>(acc, W, hp + b * CH);
+            fir_step<VEC, CH, 0, DD>(acc, W, hp + b * CH);
             fir_load_half<0>(W, plane, tid + b + 2);
-            fir_step<VEC, CH, 32>(acc, W, hp + (b + 1) * CH);
+            fir_step<VEC, CH, 32, DD>(acc, W, hp + (b + 1) * CH);
         }
     }
     __syncthreads();
@@ -282,27 +293,44 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     if (ep.fuse) {
         if (VEC == 2) {
 #pragma unroll
-            for (int l = 0; l < FIR_ACC; l += 2) {
+            for (int l = 0; l < FIR_ACC; l += 2 * DD) {
                 float2 v = cmul_nofma(make_float2(acc[l], acc[l + 1]), ep.kre, ep.kim);
                 acc[l] = v.x;
                 acc[l + 1] = v.y;
             }
         } else {
 #pragma unroll
-            for (int l = 0; l < FIR_ACC; l++)
+            for (int l = 0; l < FIR_ACC; l += DD)
                 acc[l] = __fmul_rn(acc[l], ep.kre);
         }
     }
-    {
+    if (DD == 1) {
         float* rb = planes + (tid << 5);
         const int s = (tid & 7) << 2;
 #pragma unroll
         for (int j = 0; j < 8; j++)
             *reinterpret_cast<float4*>(rb + ((j << 2) ^ s)) =
                 make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    } else {
+        // the thread's FIR_ACC/DD output floats, compacted, at their place in the (swizzled) output tile
+        constexpr int NF = FIR_ACC / DD; // floats per thread
+        float o[NF];
+#pragma unroll
+        for (int j = 0; j < NF; j++)
+            o[j] = acc[(j / VEC) * DD * VEC + (j % VEC)];
+        const int f0 = tid * NF;
+        if (NF >= 4) {
+#pragma unroll
+            for (int j = 0; j < NF; j += 4)
+                *reinterpret_cast<float4*>(planes + swz(f0 + j)) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+                planes[swz(f0 + j)] = o[j];
+        }
     }
-    const long long orow0 = tile * FIR_NT; // 128 output rows per tile
-    if (gm.tma_out_ok && orow0 + FIR_NT <= gm.full_out_rows) {
+    const long long orow0 = tile * (FIR_NT / DD); // output rows per tile
+    if (FIR_NT / DD >= 8 && gm.tma_out_ok && orow0 + FIR_NT / DD <= gm.full_out_rows) {
         // whole tile inside the output: one TMA tensor store from the swizzled rows
         fence_proxy_async();
         __syncthreads();
@@ -318,7 +346,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     }
     __syncthreads();
 #pragma unroll 4
-    for (int i = tid; i < MT; i += FIR_NT) {
+    for (int i = tid; i < MTO; i += FIR_NT) {
         const long long m = O0 + i;
         if (m >= gm.n_out)
             break;
@@ -382,6 +410,7 @@ struct b200_fir {
     int plane_rows = 0, box_rows = 0, n_boxes = 0; // smem plane geometry (rows of 128 B)
     size_t smem = 0;
     int use_tma = 1;
+    int dd = 0;      // > 1: decimation folded into the TMA-staged full-rate kernel (geometry as for D = 1)
     ols_plan* ols = nullptr; // algorithm 3
     ffa_plan* ffa = nullptr; // algorithm 5
     int algorithm = 1;
@@ -440,13 +469,13 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
     if (h->algorithm == 5)
         return ffa_launch(h->ffa, d_hist, d_in, d_out, n_in, n_out, s);
     if (h->algorithm == 1) {
-        const int MT = FIR_NT * (FIR_ACC / h->vec);
+        const int MT = FIR_NT * (FIR_ACC / h->vec) / (h->dd ? h->dd : 1); // outputs per tile
         long long tiles = (n_out + MT - 1) / MT;
         if (tiles > 0x7fffffffLL)
             return set_err(B200_ERR_ARG, "fir: too many items for one call");
         fir_geom gm{};
         gm.Tm1 = h->T - 1;
-        gm.D = h->D;
+        gm.D = h->dd ? 1 : h->D;
         gm.TQ = h->TQ;
         gm.plane_rows = h->plane_rows;
         gm.box_rows = h->box_rows;
@@ -457,7 +486,7 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         gm.tma_ok = 0;
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
-        if (h->use_tma && h->D == 1 && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0) {
+        if (h->use_tma && (h->D == 1 || h->dd) && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0) {
             int rc = fir_make_tmap(&tmap, d_in, gm.full_rows, h->box_rows);
             if (rc != B200_OK)
                 return rc;
@@ -467,14 +496,36 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         memset(&tmap_out, 0, sizeof(tmap_out));
         gm.full_out_rows = n_out * h->vec / 32;
         gm.tma_out_ok = 0;
-        if (h->use_tma && gm.full_out_rows >= FIR_NT && (uintptr_t)d_out % 16 == 0) {
-            int rc = fir_make_tmap(&tmap_out, d_out, gm.full_out_rows, FIR_NT);
+        const int out_rows = FIR_NT / (h->dd ? h->dd : 1); // rows of the output tile
+        if (h->use_tma && out_rows >= 8 && gm.full_out_rows >= out_rows && (uintptr_t)d_out % 16 == 0) {
+            int rc = fir_make_tmap(&tmap_out, d_out, gm.full_out_rows, out_rows);
             if (rc != B200_OK)
                 return rc;
             gm.tma_out_ok = 1;
         }
         const bool decim = h->D > 1;
-        if (h->vec == 2) {
+        if (h->dd) {
+#define FIR_DD(V, DDV)                                                                                     \
+    B200_LAUNCH((fir_direct_kernel<V, false, DDV>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,     \
+                h->d_taps_pp, tmap, tmap_out, gm, h->ep)
+            if (h->vec == 2) {
+                switch (h->dd) {
+                case 2: FIR_DD(2, 2); break;
+                case 4: FIR_DD(2, 4); break;
+                case 8: FIR_DD(2, 8); break;
+                default: FIR_DD(2, 16); break;
+                }
+            } else {
+                switch (h->dd) {
+                case 2: FIR_DD(1, 2); break;
+                case 4: FIR_DD(1, 4); break;
+                case 8: FIR_DD(1, 8); break;
+                case 16: FIR_DD(1, 16); break;
+                default: FIR_DD(1, 32); break;
+                }
+            }
+#undef FIR_DD
+        } else if (h->vec == 2) {
             if (decim)
                 B200_LAUNCH((fir_direct_kernel<2, true>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
                             h->d_taps_pp, tmap, tmap_out, gm, h->ep);
@@ -535,7 +586,11 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
 
     const int CH = FIR_ACC / h->vec;
     const int MT = FIR_NT * (FIR_ACC / h->vec);
-    int tq = (h->T + h->D - 1) / h->D;
+    // decimations that divide the 16 (32) window positions of a thread run in the full-rate kernel
+    if (h->D > 1 && (FIR_ACC / h->vec) % h->D == 0 && !getenv("B200_FIR_PLANES"))
+        h->dd = h->D;
+    const int Dg = h->dd ? 1 : h->D; // decimation the plane / tap geometry is built for
+    int tq = (h->T + Dg - 1) / Dg;
     h->TQ = (tq + 2 * CH - 1) / (2 * CH) * (2 * CH);
     (void)MT;
     {
@@ -544,7 +599,7 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         h->box_rows = (need + h->n_boxes - 1) / h->n_boxes;
         h->plane_rows = h->box_rows * h->n_boxes;
     }
-    h->smem = 16 + sizeof(float) * ((size_t)h->D * h->TQ + (size_t)h->D * (h->plane_rows * 32 + 8)) + 1024;
+    h->smem = 16 + sizeof(float) * ((size_t)Dg * h->TQ + (size_t)Dg * (h->plane_rows * 32 + 8)) + 1024;
     if (const char* e = getenv("B200_FIR_TMA"))
         h->use_tma = atoi(e);
     h->algorithm = 1;
@@ -565,6 +620,18 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         const int cross = poly == 1 ? 40 : poly == 2 ? 64 : h->D == 1 ? 65 : 96;
         if (p->algorithm == 0 && can && h->T / h->D >= cross)
             want = true;
+        if (p->algorithm == 0 && h->dd) {
+            // decimation folded into the full-rate kernel (dd): short filters are HBM-bound there and
+            // its cost grows with T, not T/D; measured crossovers against overlap-save
+            // (tools/decim_ab.py, taps): complex 96 / 160 / 192 / 384 for D = 2 / 4 / 8 / 16, real
+            // 256 / 512 / 768 / 768 / 768 for D = 2 / 4 / 8 / 16 / 32
+            int tx;
+            if (h->vec == 2)
+                tx = h->dd == 2 ? 96 : h->dd == 4 ? 160 : h->dd == 8 ? 192 : 384;
+            else
+                tx = h->dd == 2 ? 256 : h->dd == 4 ? 512 : 768;
+            want = can && h->T > tx;
+        }
         if (const char* e = getenv("B200_FIR_ALGO"))
             if (p->algorithm == 0)
                 want = atoi(e) == 3;
@@ -620,10 +687,10 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         }                                                                                \
     } while (0)
 
-    std::vector<float> pp((size_t)h->D * h->TQ, 0.f);
-    for (int ph = 0; ph < h->D; ph++)
+    std::vector<float> pp((size_t)Dg * h->TQ, 0.f);
+    for (int ph = 0; ph < Dg; ph++)
         for (int qr = 0; qr < h->TQ; qr++) {
-            long long k = (long long)(h->TQ - 1 - qr) * h->D + ph;
+            long long k = (long long)(h->TQ - 1 - qr) * Dg + ph;
             pp[(size_t)ph * h->TQ + qr] = (k < h->T) ? p->taps[k] : 0.f;
         }
     FIR_CUDA(cudaMalloc(&h->d_taps_pp, pp.size() * sizeof(float)));
@@ -634,6 +701,20 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     for (int i = 0; i < 2; i++) {
         FIR_CUDA(cudaMalloc(&h->d_hist[i], hb));
         FIR_CUDA(cudaMemset(h->d_hist[i], 0, hb));
+    }
+    if (h->algorithm == 1 && h->dd) {
+#define FIR_DD_ATTR(V, DDV) \
+    FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<V, false, DDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        FIR_DD_ATTR(2, 2);
+        FIR_DD_ATTR(2, 4);
+        FIR_DD_ATTR(2, 8);
+        FIR_DD_ATTR(2, 16);
+        FIR_DD_ATTR(1, 2);
+        FIR_DD_ATTR(1, 4);
+        FIR_DD_ATTR(1, 8);
+        FIR_DD_ATTR(1, 16);
+        FIR_DD_ATTR(1, 32);
+#undef FIR_DD_ATTR
     }
     if (h->algorithm == 1) {
         if (h->vec == 2)

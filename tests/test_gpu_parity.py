@@ -459,6 +459,58 @@ def test_fir_two_parallel_form(cuda, T, cplxin):
     assert np.array_equal(host(buf[1:]), one) and buf[0].item() == 0
 
 
+@pytest.mark.parametrize("T,D,cplxin", [(16, 2, True), (64, 2, True), (96, 4, True), (160, 4, True), (33, 8, True),
+                                        (192, 8, True), (64, 16, True), (384, 16, True), (64, 2, False),
+                                        (256, 4, False), (100, 8, False), (500, 16, False), (64, 32, False)])
+def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
+    """Decimations that divide a thread's window (2/4/8/16, 32 for fff) run in the TMA-staged
+    full-rate kernel, which keeps accumulators only for every D-th position: bit-identical to the
+    phase-plane kernel (same products, same order), exact decimation phase, chunk- and
+    segment-invariant."""
+    import os
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T * 7 + D + cplxin)
+    n = 2048 * 37 + 1234
+    x = cplx(rng, n) if cplxin else rng.uniform(-1, 1, n).astype(np.float32)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)
+    f = nb.FirFilter(taps, D, is_complex=cplxin, algorithm=1)
+    y, nc = f.work(dx)
+    ref = o.fir(x, taps, D)
+    assert y.numel() == n // D and nc == (n // D) * D
+    assert o.rel_rms(host(y), ref) < TOL_RMS
+    one = host(y)
+    # decimation phase: y[m] is the full-rate output at m*D, bit for bit
+    full = host(nb.FirFilter(taps, 1, is_complex=cplxin, algorithm=1).work(dx)[0])
+    assert np.array_equal(one, full[::D][: one.size])
+    # ragged chunks (unaligned pointers -> the non-TMA staging path) and segments with a halo
+    f2 = nb.FirFilter(taps, D, is_complex=cplxin, algorithm=1)
+    outs, pos = [], 0
+    for chunk in (4099 * D, D, 33333, 7 * D + 1, 10 ** 9):
+        if n - pos < D:
+            break
+        yy, c = f2.work(dx[pos:min(pos + max(chunk, D), n)])
+        outs.append(host(yy))
+        pos += c
+    assert np.array_equal(np.concatenate(outs), one), "chunked != one-shot"
+    L = (n // 3) // D * D
+    parts = []
+    for g in range(3):
+        lo, hi = g * L, (n if g == 2 else (g + 1) * L)
+        halo = None if g == 0 else dx[lo - (T - 1):lo]
+        parts.append(host(f.work_segment(dx[lo:hi], halo)))
+    assert np.array_equal(np.concatenate(parts), one), "time segments + halo != one stream"
+    k = 0.5 - 0.25j if cplxin else 3.25
+    yk, _ = nb.FirFilter(taps, D, is_complex=cplxin, multiply_const=k, algorithm=1).work(dx)
+    exp = o.multiply_const(one, k) if cplxin else one * np.float32(k)
+    assert np.array_equal(host(yk), exp), "fused epilogue != two-block chain"
+    # output pointer 8 bytes past a 16-byte boundary: plain store loop instead of the TMA store
+    buf = cuda.zeros(n // D + 4, dtype=dx.dtype, device="cuda")
+    off = 1 if cplxin else 3
+    f.work_segment(dx, None, buf[off:off + n // D])
+    assert np.array_equal(host(buf[off:off + n // D]), one) and buf[0].item() == 0 and buf[-1].item() == 0
+
+
 def test_fir_auto_algorithm_choice(cuda):
     import newsched_b200 as nb
     t = np.ones(64, np.float32)
@@ -466,8 +518,10 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
     assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 3
     assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 4   # huge D: fallback kernel
-    assert nb.FirFilter(np.ones(256, np.float32), 4).algorithm == 3    # polyphase overlap-save from T/D = 40
-    assert nb.FirFilter(np.ones(128, np.float32), 4).algorithm == 1
+    assert nb.FirFilter(np.ones(256, np.float32), 4).algorithm == 3    # polyphase overlap-save beyond 160 taps at D = 4
+    assert nb.FirFilter(np.ones(128, np.float32), 4).algorithm == 1    # decimation folded into the full-rate kernel
+    assert nb.FirFilter(np.ones(256, np.float32), 16).algorithm == 1
+    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # odd D: phase-plane kernel below T/D = 64
 
 
 def test_fir_empty_and_short(cuda):
