@@ -287,6 +287,218 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---- M = 16, 32, 128, 256: the same single-pass structure as pfb64_kernel -----------------------
+// 4096-sample tiles (TT = 4096/M frames), branch filters with register-resident taps and a
+// 16-frame sliding window per thread, then the M-point reverse DFT across branches as radix 16
+// (over i1, i = S i1 + i0, S = M/16; thread = frame x i0, twiddles W_M^{i0 c1} in registers) followed by
+// radix S over i0 with thread = (frame, c1): 16 consecutive channels on 16 consecutive lanes, i.e.
+// whole-line output stores.  Stage 1 leaves A_{i0}[c1] at row[17 i0 + c1] (row stride 17 S): both its
+// 4-lane-contiguous accesses and stage 2's lane-contiguous LDS.64 reads are bank-conflict free.
+// One HBM read and one HBM write per sample (the two-kernel form it replaces made two round trips).
+template <int M>
+struct pfbm {
+    static constexpr int S = M / 16;
+    static constexpr int TT = 4096 / M;
+    static constexpr int RS = 17 * S;
+};
+
+// reverse 8-point DFT, natural order in and out
+__device__ __forceinline__ void idft8(float2 (&z)[8])
+{
+    constexpr float R2 = 0.70710678118654752f;
+    float2 e0 = z[0], e1 = z[2], e2 = z[4], e3 = z[6];
+    float2 o0 = z[1], o1 = z[3], o2 = z[5], o3 = z[7];
+    idft4(e0, e1, e2, e3);
+    idft4(o0, o1, o2, o3);
+    o1 = cmulc(o1, R2, R2);                 // W8^-1 = e^{+j pi/4}
+    o2 = make_float2(-o2.y, o2.x);          // e^{+j pi/2}
+    o3 = cmulc(o3, -R2, R2);                // e^{+j 3 pi/4}
+    z[0] = f2add(e0, o0), z[4] = f2sub(e0, o0);
+    z[1] = f2add(e1, o1), z[5] = f2sub(e1, o1);
+    z[2] = f2add(e2, o2), z[6] = f2sub(e2, o2);
+    z[3] = f2add(e3, o3), z[7] = f2sub(e3, o3);
+}
+
+template <int M, int P4T>
+__global__ void __launch_bounds__(256, (M >= 128 ? 1 : 2))
+    pfbm_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
+                const float* __restrict__ taps_rm /* [P4][M] */, int P4, int Ptrue, long long n_frames,
+                long long n_in, int ch_begin, int ch_count, int tma_ok)
+{
+    constexpr int S = pfbm<M>::S, TT = pfbm<M>::TT, RS = pfbm<M>::RS;
+    extern __shared__ __align__(128) float2 sm[];
+    const int rows = TT + P4 - 1;
+    float2* X = sm;
+    float2* U = X + rows * M;
+    float* hT = reinterpret_cast<float*>(U + TT * RS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + P4 * M);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < P4 * M; i += 256)
+        hT[i] = __ldg(taps_rm + i);
+    // stage-1 twiddles e^{+j 2 pi i0 c1 / M} of this thread (i0 = tid % S): register resident
+    float2 twr[16];
+#pragma unroll
+    for (int c1 = 0; c1 < 16; c1++) {
+        float sn, cs_;
+        sincospif(2.0f * (float)(((tid % S) * c1) % M) / (float)M, &sn, &cs_);
+        twr[c1] = make_float2(cs_, sn);
+    }
+    const long long nh = (long long)(Ptrue - 1) * M;
+    const long long n_tiles = (n_frames + TT - 1) / TT;
+    const uint32_t tile_bytes = (uint32_t)rows * (uint32_t)M * 8u;
+    auto tma_tile = [&](long long t) {
+        const long long g0 = (t * TT - (P4 - 1)) * M;
+        return tma_ok && g0 >= 0 && g0 + (long long)rows * M <= n_in;
+    };
+    __syncthreads();
+    long long tile = blockIdx.x;
+    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
+        mbar_arrive_expect_tx(bar, tile_bytes);
+        bulk_copy_g2s(X, x + (tile * TT - (P4 - 1)) * M, tile_bytes, bar);
+    }
+    uint32_t phase = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const long long f0 = tile * TT;
+        if (tma_tile(tile)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            const long long g0 = (f0 - (P4 - 1)) * M;
+            for (int i0 = tid; i0 < rows * M; i0 += 256 * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * M)
+                        v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * M)
+                        X[i0 + u * 256] = v[u];
+            }
+            __syncthreads();
+        }
+        // ---- branch filters: thread = (branch i, 16 consecutive frames)
+        {
+            const int i = tid % M, tg = tid / M;
+            const float2* col = X + (M - 1 - i) + (tg * 16) * M;
+            float2 acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                acc[j] = make_float2(0.f, 0.f);
+            if (P4T > 0) {
+                float hreg[P4T > 0 ? P4T : 1];
+#pragma unroll
+                for (int r = 0; r < P4T; r++)
+                    hreg[r] = hT[r * M + i];
+#pragma unroll
+                for (int rho = 0; rho < 16 + P4T - 1; rho++) {
+                    const float2 v = col[rho * M];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int r = j + P4T - 1 - rho;
+                        if (r >= 0 && r < P4T)
+                            acc[j] = __ffma2_rn(v, make_float2(hreg[r], hreg[r]), acc[j]);
+                    }
+                }
+            } else {
+                for (int rc = 0; rc < P4; rc += 4) {
+                    const float h0 = hT[(rc + 0) * M + i], h1 = hT[(rc + 1) * M + i];
+                    const float h2 = hT[(rc + 2) * M + i], h3 = hT[(rc + 3) * M + i];
+                    const float2* base = col + (P4 - 1 - rc - 3) * M;
+                    float2 w[19];
+#pragma unroll
+                    for (int q = 0; q < 19; q++)
+                        w[q] = base[q * M];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        acc[j] = __ffma2_rn(w[j + 3], make_float2(h0, h0), acc[j]);
+                        acc[j] = __ffma2_rn(w[j + 2], make_float2(h1, h1), acc[j]);
+                        acc[j] = __ffma2_rn(w[j + 1], make_float2(h2, h2), acc[j]);
+                        acc[j] = __ffma2_rn(w[j], make_float2(h3, h3), acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                U[(tg * 16 + j) * RS + i] = acc[j];
+        }
+        __syncthreads(); // U complete; X fully consumed
+        {
+            const long long nxt = tile + gridDim.x;
+            if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
+                mbar_arrive_expect_tx(bar, tile_bytes);
+                bulk_copy_g2s(X, x + (nxt * TT - (P4 - 1)) * M, tile_bytes, bar);
+            }
+        }
+        // ---- stage 1: radix 16 over i1 (rows are warp-local: a warp owns 32/S whole frames)
+        {
+            const int t = tid / S, i0 = tid % S;
+            float2* row = U + t * RS;
+            float2 v[16];
+#pragma unroll
+            for (int i1 = 0; i1 < 16; i1++)
+                v[i1] = row[S * i1 + i0];
+            idft16(v); // A[c1] in v[4*(c1&3) + (c1>>2)]
+            __syncwarp();
+#pragma unroll
+            for (int c1 = 0; c1 < 16; c1++) {
+                const float2 a = v[4 * (c1 & 3) + (c1 >> 2)];
+                row[17 * i0 + c1] = (S > 1 && c1 > 0) ? cmulc(a, twr[c1].x, twr[c1].y) : a;
+            }
+            __syncwarp();
+        }
+        const int lane = tid & 31, warp = tid >> 5;
+        if (S == 1) {
+            // M = 16: the row already is the frame's 16 channels; the warp stores its 32 frames
+            // (4 KiB contiguous in the output) cooperatively
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int idx = k * 32 + lane, fr = warp * 32 + (idx >> 4), ch = idx & 15;
+                const long long f = f0 + fr;
+                if (f < n_frames && ch >= ch_begin && ch < ch_begin + ch_count)
+                    __stcs(out + f * ch_count - ch_begin + ch, U[fr * RS + ch]);
+            }
+        } else {
+            // ---- stage 2: radix S over i0, thread = (frame, c1)
+            constexpr int FW = 32 / S; // frames per warp
+            const int c1 = lane & 15;
+#pragma unroll
+            for (int q = 0; q < FW / 2; q++) {
+                const int fr = warp * FW + (lane >> 4) + 2 * q;
+                const float2* row = U + fr * RS + c1;
+                float2 z[S > 1 ? S : 2];
+#pragma unroll
+                for (int i0 = 0; i0 < S; i0++)
+                    z[i0] = row[17 * i0];
+                if constexpr (S == 2) {
+                    const float2 a = f2add(z[0], z[1]), b = f2sub(z[0], z[1]);
+                    z[0] = a, z[1] = b;
+                } else if constexpr (S == 8) {
+                    idft8(z);
+                } else if constexpr (S == 16) {
+                    idft16(z);
+                }
+                const long long f = f0 + fr;
+                if (f < n_frames) {
+                    float2* y = out + f * ch_count - ch_begin;
+#pragma unroll
+                    for (int c0 = 0; c0 < S; c0++) {
+                        const int ch = c1 + 16 * c0;
+                        const float2 r = (S == 16) ? z[4 * (c0 & 3) + (c0 >> 2)] : z[c0];
+                        if (ch >= ch_begin && ch < ch_begin + ch_count)
+                            __stcs(y + ch, r);
+                    }
+                }
+            }
+        }
+        __syncthreads(); // U free for the next tile's branch filters
+    }
+}
+
 // generic M (power of two, 4..256): straightforward shared-memory version
 __global__ void __launch_bounds__(256)
     pfb_generic_kernel(const float2* __restrict__ x, const float2* __restrict__ halo,
@@ -395,6 +607,7 @@ struct b200_pfb {
     size_t smem = 0;
     int TT = 0;
     int grid = 296;
+    int fusedM = 0; // M = 16 / 32 / 128 / 256 on the single-pass kernel (pfbm_kernel)
     // generic M >= 16: branch filters -> scratch -> the library's own reverse FFT of length M
     b200_fft* ifft = nullptr;
     float2* d_u = nullptr;    // [chunk_frames][M] branch outputs
@@ -424,6 +637,29 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         default: PFB64_GO(0); break;
         }
 #undef PFB64_GO
+    } else if (h->fusedM) {
+        const int TT = 4096 / h->M;
+        long long tiles = (n_frames + TT - 1) / TT;
+        long long g = tiles < h->grid ? tiles : h->grid;
+#define PFBM_GO(MM, PT)                                                                               \
+    B200_LAUNCH((pfbm_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
+                (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
+                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
+#define PFBM_P(MM)                         \
+    switch (h->P4) {                       \
+    case 4: PFBM_GO(MM, 4); break;         \
+    case 8: PFBM_GO(MM, 8); break;         \
+    case 16: PFBM_GO(MM, 16); break;       \
+    default: PFBM_GO(MM, 0); break;        \
+    }
+        switch (h->M) {
+        case 16: PFBM_P(16); break;
+        case 32: PFBM_P(32); break;
+        case 128: PFBM_P(128); break;
+        default: PFBM_P(256); break;
+        }
+#undef PFBM_P
+#undef PFBM_GO
     } else if (h->ifft) {
         // branch filters into a scratch tile, then the M-point reverse FFT of fft.cu; chunked so the
         // scratch allocated at create time is enough for any call
@@ -524,6 +760,28 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->grid = 2 * sm_count();
+    } else if ((M == 16 || M == 32 || M == 128 || M == 256) && !getenv("B200_PFB_TWOPASS") &&
+               sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)(4096 / M) * 17 * (M / 16)) +
+                       sizeof(float) * (size_t)h->P4 * M + 16 <= 220 * 1024) {
+        h->fusedM = 1;
+        h->smem = sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)(4096 / M) * 17 * (M / 16)) +
+                  sizeof(float) * (size_t)h->P4 * M + 16;
+#define PFBM_ATTR(MM)                                                                                          \
+    PFB_CUDA(cudaFuncSetAttribute(pfbm_kernel<MM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
+    PFB_CUDA(cudaFuncSetAttribute(pfbm_kernel<MM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
+    PFB_CUDA(cudaFuncSetAttribute(pfbm_kernel<MM, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
+    PFB_CUDA(cudaFuncSetAttribute(pfbm_kernel<MM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem))
+        if (M == 16) {
+            PFBM_ATTR(16);
+        } else if (M == 32) {
+            PFBM_ATTR(32);
+        } else if (M == 128) {
+            PFBM_ATTR(128);
+        } else {
+            PFBM_ATTR(256);
+        }
+#undef PFBM_ATTR
+        h->grid = (M >= 128 ? 1 : 2) * sm_count();
     } else {
         h->TT = 4096 / M;
         if (h->TT < 1)

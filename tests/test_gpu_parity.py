@@ -723,20 +723,23 @@ def test_pfb_golden(cuda, golden, name):
     assert o.rel_rms(host(y), golden[name + "_y64"]) < TOL_RMS
 
 
-@pytest.mark.parametrize("M,P", [(64, 16), (64, 3), (64, 32), (16, 8), (256, 4), (4, 7)])
+@pytest.mark.parametrize("M,P", [(64, 16), (64, 3), (64, 32), (16, 8), (256, 4), (4, 7), (16, 16), (16, 5),
+                                 (32, 16), (32, 4), (128, 8), (128, 13), (256, 16), (8, 12)])
 def test_pfb_matches_oracle_and_streams(cuda, M, P):
     import scipy.signal as sig
     import newsched_b200 as nb
     rng = np.random.default_rng(M + P)
     taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
-    x = cplx(rng, M * 333 + 5)
+    x = cplx(rng, M * max(333, 3 * 4096 // M + 77) + 5)     # several 4096-sample tiles for every M
     dx = dev(cuda, x)
     ref = o.pfb_channelizer(x, taps, M)
     y, nc = nb.PfbChannelizer(taps, M).work(dx)
     assert nc == (x.size // M) * M and o.rel_rms(host(y), ref) < TOL_RMS
     ch = nb.PfbChannelizer(taps, M)
     outs, pos = [], 0
-    for n_fr in (1, 2, 64, 100, 166):
+    for n_fr in (1, 2, 64, 100, 166, 4096 // M + 3, 10 ** 6):
+        if pos + M > x.size:
+            break
         yy, c = ch.work(dx[pos:pos + n_fr * M])
         outs.append(host(yy))
         pos += c
@@ -750,12 +753,12 @@ def test_pfb_matches_oracle_and_streams(cuda, M, P):
 def test_pfb_tone(cuda):
     import scipy.signal as sig
     import newsched_b200 as nb
-    M, P, c0 = 64, 16, 5
-    taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
-    x = np.exp(2j * np.pi * c0 / M * np.arange(M * 300)).astype(np.complex64)
-    y = host(nb.PfbChannelizer(taps, M).work(dev(cuda, x))[0])
-    p = (np.abs(y[P:]) ** 2).mean(axis=0)
-    assert int(np.argmax(p)) == c0 and p[c0] > 1e3 * np.delete(p, c0).max()
+    for M, P, c0 in ((64, 16, 5), (16, 8, 3), (32, 8, 21), (128, 8, 77), (256, 4, 200)):
+        taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
+        x = np.exp(2j * np.pi * c0 / M * np.arange(M * 600)).astype(np.complex64)
+        y = host(nb.PfbChannelizer(taps, M).work(dev(cuda, x))[0])
+        p = (np.abs(y[P:]) ** 2).mean(axis=0)
+        assert int(np.argmax(p)) == c0 and p[c0] > 1e3 * np.delete(p, c0).max(), (M, c0)
 
 
 # ------------------------------------------------------------------------ ring / chain
