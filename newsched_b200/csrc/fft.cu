@@ -283,6 +283,193 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---- N = 8192: one radix-2 decimation-in-frequency stage in front of two 4096-point transforms ---
+//   a[n] = x'[n] + x'[n+4096]                    ->  X[2k]   = FFT4096(a)[k]
+//   b[n] = (x'[n] - x'[n+4096]) W8192^n          ->  X[2k+1] = FFT4096(b)[k]        (x' = windowed input)
+// One CTA per vector: the 64 KiB vector arrives in two halves by TMA; every thread forms its 16 a's
+// (kept in registers) and b's (parked in the first half of the input buffer, own slots), runs the
+// three radix-16 passes on a, then on b, and stores (X[2k], X[2k+1]) pairs as one 16-byte store each,
+// so the output is written in whole lines.  The second half of the buffer is refilled for the
+// next vector right after the first barrier, the first half as soon as the b's have been read back.
+// W8192^{tid + 256 i} = W8192^{tid} * W32^{i}: one per-thread register pair times compile-time
+// constants.  One HBM read and one HBM write per sample (the generic radix-2 kernel it replaces for
+// this size was latency-bound at 11 % of HBM).
+constexpr size_t F8K_SMEM = 8192 * 8 + 16 * F4K_STRIDE * 8 + 256 * 8 + 32;
+
+template <bool FWD, int I>
+__device__ __forceinline__ float2 mul_w32(float2 z) // z * e^{-+ j 2 pi I / 32}
+{
+    constexpr double kPi = 3.14159265358979323846;
+    // cos / sin of 2 pi I / 32 for I = 0..15 as compile-time constants
+    constexpr float cr[16] = { 1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                               0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                               0.19509032201612825f, 0.f, -0.19509032201612825f, -0.38268343236508977f,
+                               -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                               -0.92387953251128674f, -0.98078528040323043f };
+    constexpr float si[16] = { 0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                               0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
+                               0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f,
+                               0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                               0.38268343236508977f, 0.19509032201612825f };
+    (void)kPi;
+    if (I == 0)
+        return z;
+    constexpr float wr = cr[I], wi = FWD ? -si[I] : si[I];
+    return make_float2(fmaf(-z.y, wi, z.x * wr), fmaf(z.x, wi, z.y * wr));
+}
+
+template <bool FWD, int I = 0>
+__device__ __forceinline__ void f8k_split(float2 (&a)[16], float2* sIn, const float* __restrict__ w0,
+                                          const float* __restrict__ w1, float2 wt, int tid)
+{
+    if constexpr (I < 16) {
+        const float2 x0 = __fmul2_rn(sIn[I * 256 + tid], make_float2(w0[I], w0[I]));
+        const float2 x1 = __fmul2_rn(sIn[4096 + I * 256 + tid], make_float2(w1[I], w1[I]));
+        a[I] = x0 + x1;
+        sIn[I * 256 + tid] = cmul(mul_w32<FWD, I>(x0 - x1), wt);
+        f8k_split<FWD, I + 1>(a, sIn, w0, w1, wt, tid);
+    }
+}
+
+template <bool FWD, int OUT>
+__global__ void __launch_bounds__(256, 2)
+    fft8192_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec,
+                   const float* __restrict__ weff, const float2* __restrict__ tw1,
+                   const float2* __restrict__ tw2, float odd_sign)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sIn = reinterpret_cast<float2*>(smem_raw);
+    float2* sA = sIn + 8192;
+    float2* sT2 = sA + 16 * F4K_STRIDE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + 256); // [0]: first half, [1]: second half
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        fence_mbar_init();
+    }
+    float2 t1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        t1[i] = __ldg(tw1 + i * 256 + tid);
+    sT2[tid] = __ldg(tw2 + tid);
+    float2 wt; // W8192^{tid}, with the sign of the odd bins of a reverse-shifted transform folded in
+    {
+        float sn, cs_;
+        sincospif((float)tid / 4096.0f, &sn, &cs_);
+        wt = make_float2(cs_ * odd_sign, (FWD ? -sn : sn) * odd_sign);
+    }
+    __syncthreads();
+    long long vec = blockIdx.x;
+    if (tid == 0 && vec < n_vec) {
+        mbar_arrive_expect_tx(bar, 4096 * 8);
+        bulk_copy_g2s(sIn, in + vec * 8192, 4096 * 8, bar);
+        mbar_arrive_expect_tx(bar + 1, 4096 * 8);
+        bulk_copy_g2s(sIn + 4096, in + vec * 8192 + 4096, 4096 * 8, bar + 1);
+    }
+    uint32_t phase = 0;
+    for (; vec < n_vec; vec += gridDim.x) {
+        float2 e[16], v[16];
+        {
+            float w0[16], w1[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                w0[i] = __ldg(weff + i * 256 + tid);
+                w1[i] = __ldg(weff + 4096 + i * 256 + tid);
+            }
+            mbar_wait(bar, phase);
+            mbar_wait(bar + 1, phase);
+            phase ^= 1;
+            f8k_split<FWD>(e, sIn, w0, w1, wt, tid);
+        }
+        // ---- even bins: three passes on a (in e[])
+        dft16<FWD>(e);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++)
+            sA[k0 * F4K_STRIDE + tid] = cmul(e[pos16(k0)], t1[k0]);
+        __syncthreads(); // every thread is done with the second half of sIn
+        const long long nxt = vec + gridDim.x;
+        if (tid == 0 && nxt < n_vec) {
+            mbar_arrive_expect_tx(bar + 1, 4096 * 8);
+            bulk_copy_g2s(sIn + 4096, in + nxt * 8192 + 4096, 4096 * 8, bar + 1);
+        }
+        {
+            const int k0 = tid >> 4, n0 = tid & 15;
+            float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                e[i] = row[i * 16];
+            dft16<FWD>(e);
+            row[0] = e[pos16(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++)
+                row[k1 * 16] = cmul(e[pos16(k1)], sT2[k1 * 16 + n0]);
+        }
+        __syncthreads();
+        {
+            const int k0 = tid & 15, k1 = tid >> 4;
+            const float2* row = sA + k0 * F4K_STRIDE + k1 * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                e[i] = row[i];
+            dft16<FWD>(e); // X[2 (tid + 256 k2)] in e[pos16(k2)]
+        }
+        __syncthreads(); // pass-3 reads of sA done
+        // ---- odd bins: the b's come back from this thread's own slots
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            v[i] = sIn[i * 256 + tid];
+        dft16<FWD>(v);
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0++)
+            sA[k0 * F4K_STRIDE + tid] = cmul(v[pos16(k0)], t1[k0]);
+        __syncthreads(); // every thread has read its b's: the first half of sIn is free
+        if (tid == 0 && nxt < n_vec) {
+            mbar_arrive_expect_tx(bar, 4096 * 8);
+            bulk_copy_g2s(sIn, in + nxt * 8192, 4096 * 8, bar);
+        }
+        {
+            const int k0 = tid >> 4, n0 = tid & 15;
+            float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i * 16];
+            dft16<FWD>(v);
+            row[0] = v[pos16(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++)
+                row[k1 * 16] = cmul(v[pos16(k1)], sT2[k1 * 16 + n0]);
+        }
+        __syncthreads();
+        {
+            const int k0 = tid & 15, k1 = tid >> 4;
+            const float2* row = sA + k0 * F4K_STRIDE + k1 * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i];
+            dft16<FWD>(v); // X[2 (tid + 256 k2) + 1] in v[pos16(k2)]
+        }
+        if (OUT == B200_FFT_OUT_COMPLEX) {
+            float4* y = reinterpret_cast<float4*>(out) + vec * 4096;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                const float2 p = e[pos16(k2)], q = v[pos16(k2)];
+                __stcs(y + k2 * 256 + tid, make_float4(p.x, p.y, q.x, q.y));
+            }
+        } else {
+            float2* y = reinterpret_cast<float2*>(out) + vec * 4096;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                const float2 p = e[pos16(k2)], q = v[pos16(k2)];
+                const float pe = fmaf(p.x, p.x, p.y * p.y), po = fmaf(q.x, q.x, q.y * q.y);
+                __stcs(y + k2 * 256 + tid, OUT == B200_FFT_OUT_MAG ? make_float2(sqrt_approx(pe), sqrt_approx(po))
+                                                                   : make_float2(pe, po));
+            }
+        }
+        __syncthreads(); // pass-3 reads done before the next vector's pass-1 writes
+    }
+}
+
 // ---- N = 256, 512, 1024, 2048: same machinery, N = R0 * 256 ------------------------------------
 // A CTA always works on 4096 contiguous samples = V = 16/R0 vectors.  Pass 1 is V radix-R0
 // butterflies per thread (16 points in registers, as before) with twiddle W_N^{L k0}; that leaves
@@ -685,6 +872,10 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
         default: FFT_R0_GO(8); break;
         }
 #undef FFT_R0_GO
+    } else if (h->N == 8192 && h->d_tw1 && (uintptr_t)d_in % 16 == 0 && (uintptr_t)d_out % 16 == 0) {
+        long long g = n_vec < h->grid_4k ? n_vec : h->grid_4k;
+        B200_LAUNCH((fft8192_kernel<FWD, OUT>), (unsigned)g, 256, F8K_SMEM, s, (const float2*)d_in, d_out, n_vec,
+                    h->d_weff, h->d_tw1, h->d_tw2, h->flip ? -1.f : 1.f);
     } else {
         long long blocks = (n_vec + h->vpb - 1) / h->vpb;
         if (blocks > 0x7fffffffLL)
@@ -927,6 +1118,38 @@ int b200_fft_create(const b200_fft_params* p, b200_fft** out)
         FFT_CUDA((fft_generic_attr<false, 0>()));
         FFT_CUDA((fft_generic_attr<false, 1>()));
         FFT_CUDA((fft_generic_attr<false, 2>()));
+        if (N == 8192 && !getenv("B200_FFT_GENERIC")) {
+            // tables of the two 4096-point sub-transforms of fft8192_kernel: the output phasor of a
+            // fused upstream multiply_const is folded in; the reverse-shift (-1)^k is the parity of the
+            // radix-2 split and goes into the odd branch's twiddle (odd_sign), not into these
+            std::vector<float2> t1(16 * 256), t2(256);
+            for (int k0 = 0; k0 < 16; k0++)
+                for (int L = 0; L < 256; L++) {
+                    double ang = sgn * 2.0 * M_PI * (double)((L * k0) % 4096) / 4096.0;
+                    double wr = std::cos(ang), wi = std::sin(ang);
+                    t1[k0 * 256 + L] =
+                        make_float2((float)(wr * kph_re - wi * kph_im), (float)(wr * kph_im + wi * kph_re));
+                }
+            for (int k1 = 0; k1 < 16; k1++)
+                for (int n0 = 0; n0 < 16; n0++) {
+                    double ang = sgn * 2.0 * M_PI * (double)(n0 * k1) / 256.0;
+                    t2[k1 * 16 + n0] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+                }
+            FFT_CUDA(cudaMalloc(&h->d_tw1, sizeof(float2) * t1.size()));
+            FFT_CUDA(cudaMemcpy(h->d_tw1, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
+            FFT_CUDA(cudaMalloc(&h->d_tw2, sizeof(float2) * t2.size()));
+            FFT_CUDA(cudaMemcpy(h->d_tw2, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
+            h->grid_4k = 2 * sm_count();
+#define F8K_ATTR(FW, O) \
+    FFT_CUDA(cudaFuncSetAttribute(fft8192_kernel<FW, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F8K_SMEM))
+            F8K_ATTR(true, 0);
+            F8K_ATTR(true, 1);
+            F8K_ATTR(true, 2);
+            F8K_ATTR(false, 0);
+            F8K_ATTR(false, 1);
+            F8K_ATTR(false, 2);
+#undef F8K_ATTR
+        }
     }
 #undef FFT_CUDA
     *out = h;

@@ -677,7 +677,7 @@ def test_fft_impulse_tone_exact_structure(cuda):
     assert int(np.argmax(np.abs(ys))) == (k0 + N // 2) % N   # DC lands on N/2
 
 
-@pytest.mark.parametrize("N", [16, 64, 128, 256, 1024, 2048, 4096])
+@pytest.mark.parametrize("N", [8, 16, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
 def test_fft_mag_fused_and_premultiply(cuda, golden, N):
     import newsched_b200 as nb
     rng = np.random.default_rng(N + 1)
@@ -711,6 +711,35 @@ def test_fft_config2_size_roundtrip(cuda):
     # last vector against the oracle (tail handling at full size)
     ref = o.fft(host(x[-N:]), N)
     assert o.rel_rms(host(X[-N:]), ref) < TOL_RMS
+
+
+def test_fft8192_many_vectors_roundtrip(cuda):
+    """N = 8192 (radix-2 split in front of two 4096-point transforms): more vectors than CTAs, so the
+    persistent loop and the two-half TMA refill run; forward -> reverse returns N x; Parseval;
+    first / middle / last vectors against the oracle, with a window, shift and fused |.|."""
+    import newsched_b200 as nb
+    N, nv = 8192, 1000
+    g = cuda.Generator(device="cuda").manual_seed(8)
+    x = cuda.view_as_complex(cuda.rand(nv * N, 2, device="cuda", generator=g) * 2 - 1)
+    X = nb.FFT(N, True).work(x)
+    e_t = x.abs().pow(2).sum().double()
+    e_f = X.abs().pow(2).sum().double() / N
+    assert abs(float(e_t / e_f) - 1) < 1e-5
+    xr = nb.FFT(N, False).work(X)
+    err = (xr / N - x).abs().pow(2).mean().sqrt() / x.abs().pow(2).mean().sqrt()
+    assert float(err) < TOL_RMS
+    w = o.window_blackmanharris(N)
+    for shift in (False, True):
+        Y = nb.FFT(N, True, w, shift).work(x)
+        M = nb.FFT(N, True, w, shift, output=nb.OUT_MAG).work(x)
+        for v in (0, 499, nv - 1):
+            ref = o.fft(host(x[v * N:(v + 1) * N]), N, True, w, shift)
+            assert o.rel_rms(host(Y[v * N:(v + 1) * N]), ref) < TOL_RMS
+            assert o.rel_rms(host(M[v * N:(v + 1) * N]), np.abs(ref.astype(np.complex128))) < TOL_RMS
+    # unaligned input pointer: falls back to the generic kernel, same numbers within tolerance
+    xo = cuda.empty(4 * N + 1, dtype=cuda.complex64, device="cuda")
+    xo[1:] = x[: 4 * N]
+    assert o.rel_rms(host(nb.FFT(N, True).work(xo[1:])), host(X[: 4 * N])) < TOL_RMS
 
 
 # ------------------------------------------------------------------------ channelizer
