@@ -750,6 +750,55 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---- N = 8: one thread per vector ---------------------------------------------------------------
+// A vector is 64 contiguous bytes: four 16-byte loads, the 8-point DFT in registers, four 16-byte
+// stores (two for |.|).  Neighbouring threads touch neighbouring 64-byte blocks, so every sector is
+// used; several independent vectors per thread keep enough loads in flight.
+template <bool FWD, int OUT>
+__global__ void __launch_bounds__(256)
+    fft8_kernel(const float2* __restrict__ in, void* __restrict__ out, long long n_vec,
+                const float* __restrict__ weff, float2 post, int flip)
+{
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        w[i] = __ldg(weff + i);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += stride) {
+        const float4* src = reinterpret_cast<const float4*>(in + v * 8);
+        float2 z[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 t = __ldcs(src + i);
+            z[2 * i] = make_float2(t.x * w[2 * i], t.y * w[2 * i]);
+            z[2 * i + 1] = make_float2(t.z * w[2 * i + 1], t.w * w[2 * i + 1]);
+        }
+        dft8<FWD>(z);
+        if (OUT == B200_FFT_OUT_COMPLEX) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                z[k] = cmul(z[k], post);
+                if (flip && (k & 1))
+                    z[k] = make_float2(-z[k].x, -z[k].y);
+            }
+            float4* dst = reinterpret_cast<float4*>(out) + v * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                __stcs(dst + i, make_float4(z[2 * i].x, z[2 * i].y, z[2 * i + 1].x, z[2 * i + 1].y));
+        } else {
+            float m[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float pw = fmaf(z[k].x, z[k].x, z[k].y * z[k].y);
+                m[k] = OUT == B200_FFT_OUT_MAG ? sqrt_approx(pw) : pw;
+            }
+            float4* dst = reinterpret_cast<float4*>(out) + v * 2;
+            __stcs(dst, make_float4(m[0], m[1], m[2], m[3]));
+            __stcs(dst + 1, make_float4(m[4], m[5], m[6], m[7]));
+        }
+    }
+}
+
 // ---- generic power-of-two radix-2 Stockham (N = 8 .. 8192) ----------------------------------
 template <bool FWD, int OUT>
 __global__ void __launch_bounds__(512)
@@ -872,6 +921,11 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
         default: FFT_R0_GO(8); break;
         }
 #undef FFT_R0_GO
+    } else if (h->N == 8 && (uintptr_t)d_in % 16 == 0 && (uintptr_t)d_out % 16 == 0) {
+        long long blocks = (n_vec + 255) / 256;
+        const long long cap = 16LL * sm_count();
+        B200_LAUNCH((fft8_kernel<FWD, OUT>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (const float2*)d_in,
+                    d_out, n_vec, h->d_weff, h->post, h->flip);
     } else if (h->N == 8192 && h->d_tw1 && (uintptr_t)d_in % 16 == 0 && (uintptr_t)d_out % 16 == 0) {
         long long g = n_vec < h->grid_4k ? n_vec : h->grid_4k;
         B200_LAUNCH((fft8192_kernel<FWD, OUT>), (unsigned)g, 256, F8K_SMEM, s, (const float2*)d_in, d_out, n_vec,
