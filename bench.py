@@ -328,6 +328,18 @@ def run_b200(args):
             "algorithm": fir.algorithm, "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 256 / 1e3,
             "frac_of_measured_fp32": gs * 256 / 1e3 / fp32_tf, "hbm_gbs": gs * 16, "frac_of_hbm": gs * 16 / peak_gbs}
         del y1b
+        # short decimating filters run folded into the same TMA-staged kernel: HBM-bound (10 B per input at D = 4)
+        for Td, Dd in ((32, 4), (64, 4), (64, 8)):
+            taps = (rng.uniform(-1, 1, Td) / Td).astype(np.float32)
+            fir = nb.FirFilter(taps, Dd)
+            yd = torch.empty(SAMPLES // Dd, dtype=torch.complex64, device=dev)
+            t = timed(torch, lambda: fir.work_segment(x, None, yd), 5, 2, lambda: None) / 5
+            gs = SAMPLES / (t * 1e-3) / 1e9
+            extras[f"fir_ccf_{Td}taps_decim{Dd}_128Mi"] = {
+                "algorithm": fir.algorithm, "Msamples_s": gs * 1e3, "ms": t,
+                "hbm_gbs": gs * (8 + 8 / Dd), "frac_of_hbm": gs * (8 + 8 / Dd) / peak_gbs,
+                "frac_of_measured_fp32": gs * 4 * Td / Dd / 1e3 / fp32_tf}
+            del yd
         taps = (rng.uniform(-1, 1, 1024) / 1024).astype(np.float32)
         fir = nb.FirFilter(taps, 4, multiply_const=0.5 - 0.25j)
         n3 = 1 << 26
