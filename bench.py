@@ -106,6 +106,25 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def sample_now(self, n=3):
+        """A few synchronous samples from the caller's thread (the timed region of a fast kernel can be
+        shorter than the background thread's period)."""
+        if self._h is None:
+            return
+        nv = self._nv
+        for _ in range(n):
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self._NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
     def start(self):
         if self._h is not None:
             self._t = threading.Thread(target=self._run, daemon=True)
@@ -185,8 +204,10 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def timed(torch, fn, steps, warmup, barrier):
-    """W warm-ups, then exactly `steps` calls between CUDA events on the current stream."""
+def timed(torch, fn, steps, warmup, barrier, during=None):
+    """W warm-ups, then exactly `steps` calls between CUDA events on the current stream.  `during`
+    runs on the host after everything (closing event included) has been enqueued and before the
+    synchronize, i.e. while the GPU is still inside the timed region."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -196,6 +217,8 @@ def timed(torch, fn, steps, warmup, barrier):
     for _ in range(steps):
         fn()
     e1.record()
+    if during is not None:
+        during()
     torch.cuda.synchronize()
     barrier()
     return e0.elapsed_time(e1)
@@ -247,7 +270,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     l_warm = nb.launch_count()
     sampler.start()
-    ms = timed(torch, lambda: fft.work(x, out), steps, 0, barrier)
+    ms = timed(torch, lambda: fft.work(x, out), steps, 0, barrier, during=sampler.sample_now)
     sampler.stop()
     launches = nb.launch_count() - l_warm
     ms = max_over_ranks(ms)
