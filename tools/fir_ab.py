@@ -10,7 +10,7 @@ for logn in (24, 27):
     n = 1 << logn
     x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
     out = torch.empty_like(x)
-    for T in (32, 64, 95):
+    for T in (16, 32, 48, 64):
         f = nb.FirFilter((rng.uniform(-1, 1, T) / T).astype(np.float32), 1, algorithm=1)
         for _ in range(3): f.work_segment(x, None, out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
