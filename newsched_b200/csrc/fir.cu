@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "fir_ffa.cuh"
+#include "fir_interp.cuh"
 #include "fir_ols.cuh"
 
 namespace b200 {
@@ -165,7 +166,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // positions 0, DD, 2 DD ... of its row, i.e. 16/DD outputs, and the output tile shrinks to 128/DD rows.
 // No phase planes, no per-sample de-interleaving copies: a short decimating filter becomes HBM-bound
 // like a short full-rate one (64 taps, decimation 4: 197 -> 400+ GS/s input rate).
-template <int VEC, bool DECIM, int DD = 1>
+// LL > 1 (with DECIM = false, DD = 1): interpolation by LL folded into the same kernel.  Output
+// phase r of an interpolator, y[n LL + r] = sum_q h[q LL + r] x[n - q], is a full-rate filter over the
+// SAME input tile with the taps of phase r: LL passes of the register-blocked loop over one
+// TMA-staged tile, each scattering its 16 results per thread into the thread's own LL rows of a
+// separate output tile (16 LL consecutive outputs), which then leaves by LL TMA tensor stores.
+template <int VEC, bool DECIM, int DD = 1, int LL = 1>
 __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
@@ -178,15 +184,17 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     constexpr int MTO = MT / DD;      // outputs per tile
     static_assert(!DECIM || DD == 1, "DD applies to the TMA-staged full-rate kernel only");
     static_assert(R % DD == 0, "decimation must divide the positions per thread");
+    static_assert(LL == 1 || (!DECIM && DD == 1), "LL applies to the TMA-staged full-rate kernel only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* hs = reinterpret_cast<float*>(smem_raw + 16);
     const int D = DECIM ? gm.D : 1, TQ = gm.TQ;
+    const int NTAPROWS = LL > 1 ? LL : D; // tap rows: one per decimation phase / interpolation phase
     float* planes;
     {
-        uint32_t a = smem_u32(hs + D * TQ);
+        uint32_t a = smem_u32(hs + NTAPROWS * TQ);
         uint32_t aligned = (a + 1023u) & ~1023u;
-        planes = hs + D * TQ + (aligned - a) / 4;
+        planes = hs + NTAPROWS * TQ + (aligned - a) / 4;
     }
     // phase planes are skewed by 32 B each so that the de-interleaving stores of one warp (same
     // element, different phase) land in different banks
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
             tma_load_2d(planes + (size_t)bx * gm.box_rows * 32, &tmap, 0, (int)(row0 + (long long)bx * gm.box_rows),
                         bar);
     }
-    for (int i = tid; i < D * TQ; i += FIR_NT)
+    for (int i = tid; i < NTAPROWS * TQ; i += FIR_NT)
         hs[i] = __ldg(taps_pp + i);
     if (DECIM) {
         // decimating filters: every sample inside the input goes global -> shared with cp.async
@@ -278,6 +286,69 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         acc[l] = 0.f;
     float W[FIR_RING];
     const int nsteps = TQ / CH; // any count >= 1: an odd tail step runs alone
+    if (LL > 1) {
+        // output tile: LL * FIR_NT rows behind the input plane (1024-byte aligned for the TMA stores)
+        float* otile = planes + (((gm.plane_rows << 5) + 255) & ~255);
+#pragma unroll 1
+        for (int r = 0; r < LL; r++) {
+#pragma unroll
+            for (int l = 0; l < FIR_ACC; l++)
+                acc[l] = 0.f;
+            const float* hp = hs + r * TQ;
+            fir_load_half<0>(W, planes, tid);
+            int b = 0;
+            for (; b + 1 < nsteps; b += 2) {
+                fir_load_half<1>(W, planes, tid + b + 1);
+                fir_step<VEC, CH, 0, 1>(acc, W, hp + b * CH);
+                fir_load_half<0>(W, planes, tid + b + 2);
+                fir_step<VEC, CH, 32, 1>(acc, W, hp + (b + 1) * CH);
+            }
+            if (b < nsteps) {
+                fir_load_half<1>(W, planes, tid + b + 1);
+                fir_step<VEC, CH, 0, 1>(acc, W, hp + b * CH);
+            }
+            // position p of the thread is output (tid R + p) LL + r of the tile
+#pragma unroll
+            for (int pz = 0; pz < R; pz++) {
+                const int f = ((tid * R + pz) * LL + r) * VEC;
+                if (VEC == 2)
+                    *reinterpret_cast<float2*>(otile + swz(f)) = make_float2(acc[2 * pz], acc[2 * pz + 1]);
+                else
+                    otile[swz(f)] = acc[pz];
+            }
+        }
+        const long long orow0 = tile * (FIR_NT * LL);
+        if (gm.tma_out_ok && orow0 + FIR_NT * LL <= gm.full_out_rows) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll 1
+                for (int r = 0; r < LL; r++)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                     &tmap_out),
+                                 "r"(0), "r"((int)(orow0 + (long long)r * FIR_NT)),
+                                 "r"(smem_u32(otile + (size_t)r * FIR_NT * 32))
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            return;
+        }
+        __syncthreads();
+        const long long OL = tile * (long long)(MT * LL);
+#pragma unroll 4
+        for (int i = tid; i < MT * LL; i += FIR_NT) {
+            const long long m = OL + i;
+            if (m >= gm.n_out)
+                break;
+            const float* src = otile + swz(i * VEC);
+            if (VEC == 2)
+                __stcs(reinterpret_cast<float2*>(y) + m, *reinterpret_cast<const float2*>(src));
+            else
+                __stcs(y + m, src[0]);
+        }
+        return;
+    }
     for (int p = 0; p < D; p++) {
         const float* plane = planes + p * plane_f;
         const float* hp = hs + p * TQ;
@@ -417,6 +488,7 @@ struct b200_fir {
     int plane_rows = 0, box_rows = 0, n_boxes = 0; // smem plane geometry (rows of 128 B)
     size_t smem = 0;
     int use_tma = 1;
+    int interp = 0;  // > 1: interpolation folded into the full-rate kernel (created by fir_interp_create)
     int dd = 0;      // > 1: decimation folded into the TMA-staged full-rate kernel (geometry as for D = 1)
     ols_plan* ols = nullptr; // algorithm 3
     ffa_plan* ffa = nullptr; // algorithm 5
@@ -558,6 +630,123 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
     }
     return B200_OK;
 }
+
+namespace b200 {
+
+bool fir_interp_supported(int T, int L, int is_complex)
+{
+    if (L < 2 || L > 4 || T < 1 || getenv("B200_INTERP_RB"))
+        return false;
+    // measured against the register-blocked resampler kernel (tools/resampler_sweep.py): +22..47 % for
+    // L = 2, 3 at any length; at L = 4 the 64 KiB output tile leaves 2 CTAs per SM and short phases lose
+    // (128 taps: 230 vs 259 GS/s out), so L = 4 folds only once the phases are FMA-bound
+    if (L == 4 && T < 192)
+        return false;
+    const int vec = is_complex ? 2 : 1, CH = FIR_ACC / vec;
+    const int TQ = ((T + L - 1) / L + CH - 1) / CH * CH;
+    return TQ / CH <= 64;
+}
+
+int fir_interp_create(const float* taps, int T, int L, int is_complex, b200_fir** out)
+{
+    *out = nullptr;
+    if (!fir_interp_supported(T, L, is_complex))
+        return set_err(B200_ERR_UNSUPPORTED, "fir interpolation fold: L = %d, %d taps not supported", L, T);
+    b200_fir* h = new b200_fir();
+    h->T = T;
+    h->D = 1;
+    h->interp = L;
+    h->vec = is_complex ? 2 : 1;
+    const int CH = FIR_ACC / h->vec;
+    h->TQ = ((T + L - 1) / L + CH - 1) / CH * CH;
+    const int need = FIR_NT + h->TQ / CH;
+    h->n_boxes = (need + 255) / 256;
+    h->box_rows = (need + h->n_boxes - 1) / h->n_boxes;
+    h->plane_rows = h->box_rows * h->n_boxes;
+    h->smem = 16 + sizeof(float) * ((size_t)L * h->TQ + (size_t)h->plane_rows * 32 + 256) + 2048 +
+              (size_t)L * FIR_NT * 128;
+    std::vector<float> pp((size_t)L * h->TQ, 0.f);
+    for (int ph = 0; ph < L; ph++)
+        for (int qr = 0; qr < h->TQ; qr++) {
+            const long long k = (long long)(h->TQ - 1 - qr) * L + ph;
+            pp[(size_t)ph * h->TQ + qr] = k < T ? taps[k] : 0.f;
+        }
+    cudaError_t e = cudaMalloc(&h->d_taps_pp, pp.size() * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h->d_taps_pp, pp.data(), pp.size() * sizeof(float), cudaMemcpyHostToDevice);
+#define FIR_LL_ATTR(V, LLV)                                                                                  \
+    if (e == cudaSuccess)                                                                                    \
+    e = cudaFuncSetAttribute(fir_direct_kernel<V, false, 1, LLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             227 * 1024)
+    FIR_LL_ATTR(2, 2);
+    FIR_LL_ATTR(2, 3);
+    FIR_LL_ATTR(2, 4);
+    FIR_LL_ATTR(1, 2);
+    FIR_LL_ATTR(1, 3);
+    FIR_LL_ATTR(1, 4);
+#undef FIR_LL_ATTR
+    if (e != cudaSuccess) {
+        b200_fir_destroy(h);
+        return set_err(B200_ERR_CUDA, "fir interpolation fold: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return B200_OK;
+}
+
+int fir_interp_launch(b200_fir* h, const float* d_hist, const void* d_in, void* d_out, long long n_in,
+                      cudaStream_t s)
+{
+    if (n_in <= 0)
+        return B200_OK;
+    const int L = h->interp;
+    const int MT = FIR_NT * (FIR_ACC / h->vec);
+    const long long tiles = (n_in + MT - 1) / MT;
+    if (tiles > 0x7fffffffLL)
+        return set_err(B200_ERR_ARG, "resampler: too many items for one call");
+    fir_geom gm{};
+    gm.Tm1 = (h->T + L - 1) / L - 1; // history is counted in input samples of a phase filter
+    gm.D = 1;
+    gm.TQ = h->TQ;
+    gm.plane_rows = h->plane_rows;
+    gm.box_rows = h->box_rows;
+    gm.n_boxes = h->n_boxes;
+    gm.n_in = n_in;
+    gm.n_out = n_in * L;
+    gm.full_rows = n_in * h->vec / 32;
+    gm.full_out_rows = gm.n_out * h->vec / 32;
+    CUtensorMap tmap, tmap_out;
+    memset(&tmap, 0, sizeof(tmap));
+    memset(&tmap_out, 0, sizeof(tmap_out));
+    if (h->use_tma && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0 &&
+        fir_make_tmap(&tmap, d_in, gm.full_rows, h->box_rows) == B200_OK)
+        gm.tma_ok = 1;
+    if (h->use_tma && gm.full_out_rows >= FIR_NT && (uintptr_t)d_out % 16 == 0 &&
+        fir_make_tmap(&tmap_out, d_out, gm.full_out_rows, FIR_NT) == B200_OK)
+        gm.tma_out_ok = 1;
+    const float* x = (const float*)d_in;
+    float* y = (float*)d_out;
+    fir_epilogue ep{ 0, 1.f, 0.f };
+#define FIR_LL(V, LLV)                                                                                        \
+    B200_LAUNCH((fir_direct_kernel<V, false, 1, LLV>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,     \
+                h->d_taps_pp, tmap, tmap_out, gm, ep)
+    if (h->vec == 2) {
+        switch (L) {
+        case 2: FIR_LL(2, 2); break;
+        case 3: FIR_LL(2, 3); break;
+        default: FIR_LL(2, 4); break;
+        }
+    } else {
+        switch (L) {
+        case 2: FIR_LL(1, 2); break;
+        case 3: FIR_LL(1, 3); break;
+        default: FIR_LL(1, 4); break;
+        }
+    }
+#undef FIR_LL
+    return B200_OK;
+}
+
+} // namespace b200
 
 extern "C" {
 

@@ -17,6 +17,9 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fir_interp.cuh"
+
+extern "C" int b200_fir_destroy(b200_fir* h);
 
 namespace b200 {
 
@@ -240,6 +243,7 @@ struct b200_resampler {
     float* d_taps_pp = nullptr;
     float* d_hist[2] = { nullptr, nullptr };
     int cur = 0;
+    b200_fir* fold = nullptr; // D == 1, L <= 4: interpolation folded into the TMA-staged direct FIR kernel
     int rb_R = 0;   // > 0: register-blocked kernel with R outputs per thread
     int rb_tpt = 0; // its active threads per CTA (multiple of L)
     size_t rb_smem = 0;
@@ -271,6 +275,8 @@ static int rs_launch(b200_resampler* h, const float* d_hist, const void* d_in, v
 {
     if (n_out <= 0)
         return B200_OK;
+    if (h->fold)
+        return fir_interp_launch(h->fold, d_hist, d_in, d_out, n_in, s);
     rs_geom g = h->g;
     g.n_in = n_in;
     g.n_out = n_out;
@@ -297,6 +303,8 @@ int b200_resampler_destroy(b200_resampler* h)
     cudaFree(h->d_taps_pp);
     cudaFree(h->d_hist[0]);
     cudaFree(h->d_hist[1]);
+    if (h->fold)
+        b200_fir_destroy(h->fold);
     delete h;
     return B200_OK;
 }
@@ -380,6 +388,13 @@ int b200_resampler_create(const b200_resampler_params* p, b200_resampler** out)
     RS_ATTR(1, 3, 6);
     RS_ATTR(1, 4, 3);
 #undef RS_ATTR
+    if (h->D == 1 && fir_interp_supported(h->T, h->L, h->vec == 2)) {
+        int rc = fir_interp_create(p->taps, h->T, h->L, h->vec == 2, &h->fold);
+        if (rc != B200_OK) {
+            b200_resampler_destroy(h);
+            return rc;
+        }
+    }
 #undef RS_CUDA
     *out = h;
     return B200_OK;

@@ -349,7 +349,8 @@ def test_fir_overlap_save_real_stream(cuda, T, D):
 @pytest.mark.parametrize("T,L,D,cplxin", [(48, 4, 1, True), (49, 3, 2, True), (160, 8, 5, False),
                                           (7, 1, 3, True), (33, 5, 5, False), (3, 7, 2, True),
                                           (1024, 16, 1, True), (2048, 4, 3, True), (256, 2, 9, False),
-                                          (96, 3, 64, True)])
+                                          (96, 3, 64, True), (64, 2, 1, True), (100, 3, 1, False),
+                                          (33, 4, 1, False), (2000, 4, 1, True), (5, 3, 1, True)])
 def test_resampler_matches_oracle(cuda, T, L, D, cplxin):
     """interp_fir_filter (D = 1) / rational_resampler against the fp64 oracle; streaming in ragged
     chunks (history on the device) and time segments with a halo are bit-identical to one shot."""
