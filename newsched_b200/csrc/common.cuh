@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for libb200dsp (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdarg>
@@ -38,6 +39,13 @@ inline cudaStream_t cs(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(
     } while (0)
 
 int sm_count();
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda);
+// nullptr when the driver does not provide it
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tmap_encode_fn tmap_encode_tiled();
 
 // non-fused complex product (matches the oracle / VOLK generic kernel): each product is
 // rounded to fp32 before the add.

@@ -502,26 +502,9 @@ struct b200_fir {
 };
 
 // 2-D view of the input stream for TMA: rows of 32 floats (128 B), SWIZZLE_128B, box = box_rows
-typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-static encode_tiled_fn get_encode_tiled()
-{
-    static encode_tiled_fn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return (encode_tiled_fn)p;
-    }();
-    return fn;
-}
-
 static int fir_make_tmap(CUtensorMap* tmap, const void* d_in, long long full_rows, int box_rows)
 {
-    encode_tiled_fn enc = get_encode_tiled();
+    tmap_encode_fn enc = tmap_encode_tiled();
     if (!enc)
         return set_err(B200_ERR_CUDA, "fir: cuTensorMapEncodeTiled unavailable");
     cuuint64_t gdim[2] = { 32, (cuuint64_t)full_rows };

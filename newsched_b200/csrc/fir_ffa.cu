@@ -441,22 +441,6 @@ int ffa_create(const float* taps, int T, int real, int fuse, float kre, float ki
     return B200_OK;
 }
 
-typedef CUresult (*ffa_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static ffa_encode_fn ffa_encode_tiled()
-{
-    static ffa_encode_fn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return (ffa_encode_fn)p;
-    }();
-    return fn;
-}
-
 int ffa_launch(ffa_plan* p, const float* d_hist, const void* d_in, void* d_out, long long n_in, long long n_out,
                cudaStream_t s)
 {
@@ -477,7 +461,7 @@ int ffa_launch(ffa_plan* p, const float* d_hist, const void* d_in, void* d_out, 
     g.full_in_rows = n_in * p->vec / 32;
     g.tma_out_ok = g.tma_in_ok = 0;
     if (g.full_in_rows >= 2 * g.plane_rows && (uintptr_t)d_in % 16 == 0) {
-        if (ffa_encode_fn enc = ffa_encode_tiled()) {
+        if (tmap_encode_fn enc = tmap_encode_tiled()) {
             cuuint64_t gdim[2] = { 32, (cuuint64_t)g.full_in_rows };
             cuuint64_t gstride[1] = { 128 };
             cuuint32_t box[2] = { 32, 2 * FFA_NT };
@@ -496,7 +480,7 @@ int ffa_launch(ffa_plan* p, const float* d_hist, const void* d_in, void* d_out, 
         if (atoi(e) == 0)
             g.tma_in_ok = 0;
     if (g.full_out_rows >= 2 * FFA_NT && (uintptr_t)d_out % 16 == 0) {
-        if (ffa_encode_fn enc = ffa_encode_tiled()) {
+        if (tmap_encode_fn enc = tmap_encode_tiled()) {
             cuuint64_t gdim[2] = { 32, (cuuint64_t)g.full_out_rows };
             cuuint64_t gstride[1] = { 128 };
             cuuint32_t box[2] = { 32, 2 * FFA_NT };

@@ -646,22 +646,6 @@ static bool ols2_supported(int T, int D, int real)
     return T >= min_taps && OLS_N - 1 - Tq >= 1024;
 }
 
-typedef CUresult (*ols_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static ols_encode_fn ols_encode_tiled()
-{
-    static ols_encode_fn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return (ols_encode_fn)p;
-    }();
-    return fn;
-}
-
 int ols_polyphase(int T, int D, int real) { return olsd_supported(T, D, real) ? ((D & 1) ? 2 : 1) : 0; }
 
 bool ols_supported(int T, int D, int real)
@@ -844,7 +828,7 @@ static int olsd_launch(ols_plan* p, const float* d_hist, const void* d_in, void*
     const long long nrows = (n_in + off) / D;
     g.tma_ok = 0;
     if (a % 8 == 0 && (D & 1) == 0 && nrows >= OLS_N && nrows < (1LL << 31)) {
-        if (ols_encode_fn enc = ols_encode_tiled()) {
+        if (tmap_encode_fn enc = tmap_encode_tiled()) {
             cuuint64_t gdim[2] = { (cuuint64_t)D, (cuuint64_t)nrows };
             cuuint64_t gstride[1] = { (cuuint64_t)D * 8 };
             cuuint32_t box[2] = { 2, 256 };

@@ -47,6 +47,19 @@ int sm_count()
     return cached;
 }
 
+tmap_encode_fn tmap_encode_tiled()
+{
+    static tmap_encode_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (tmap_encode_fn)p;
+    }();
+    return fn;
+}
+
 // ---- driver entry points resolved through the runtime (no link-time libcuda dependency,
 // so the library still loads on a machine without a driver) ------------------------------
 struct drv_api {
