@@ -799,6 +799,18 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         const int cross = poly == 1 ? 40 : poly == 2 ? 64 : h->D == 1 ? 65 : 96;
         if (p->algorithm == 0 && can && h->T / h->D >= cross)
             want = true;
+        if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
+            // decimations that cannot fold (tools/decim_ab.py with DS=3,5,6,7,10,12): the phase-plane kernel
+            // stages with per-sample copies and sits at 150-290 GS/s; the polyphase overlap-save is flat at
+            // 170-280.  D = 6 (TMA-staged polyphase form): from 64 taps; D = 3, 5, 7: beyond 96 taps;
+            // larger D: from 192 taps, and whenever the phase planes would not fit shared memory
+            if (poly == 1)
+                want = h->T >= 64; // (shorter filters stay on the direct kernel: exact impulse response)
+            else if (poly == 2)
+                want = h->T > 96;
+            else
+                want = h->T >= 192 || h->algorithm == 4;
+        }
         if (p->algorithm == 0 && h->dd) {
             // decimation folded into the full-rate kernel (dd): short filters are HBM-bound there and
             // its cost grows with T, not T/D; measured crossovers against overlap-save

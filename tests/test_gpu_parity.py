@@ -518,11 +518,14 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(t, 1).algorithm == 1                      # short: direct FFMA2 form
     assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
     assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 3
-    assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 4   # huge D: fallback kernel
+    assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 3   # huge D: overlap-save instead of the fallback
+    assert nb.FirFilter(np.ones(100, np.float32), 40, algorithm=4).algorithm == 4   # the fallback stays selectable
     assert nb.FirFilter(np.ones(256, np.float32), 4).algorithm == 3    # polyphase overlap-save beyond 160 taps at D = 4
     assert nb.FirFilter(np.ones(128, np.float32), 4).algorithm == 1    # decimation folded into the full-rate kernel
     assert nb.FirFilter(np.ones(256, np.float32), 16).algorithm == 1
-    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # odd D: phase-plane kernel below T/D = 64
+    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # odd D: phase-plane kernel up to 96 taps
+    assert nb.FirFilter(np.ones(64, np.float32), 3).algorithm == 1
+    assert nb.FirFilter(np.ones(64, np.float32), 6).algorithm == 3     # even D that cannot fold: polyphase overlap-save
 
 
 def test_fir_empty_and_short(cuda):

@@ -20,7 +20,8 @@ CPLX = os.environ.get("REAL", "0") != "1"
 if not CPLX:
     x = torch.rand(2 * n, device="cuda", generator=g) * 2 - 1
     n = 2 * n
-for D in (2, 4, 8, 16) + (() if CPLX else (32,)):
+DS = tuple(int(d) for d in os.environ["DS"].split(",")) if "DS" in os.environ else (2, 4, 8, 16) + (() if CPLX else (32,))
+for D in DS:
     line = f"{'ccf' if CPLX else 'fff'} D={D:2d}:"
     for T in (32, 64, 128, 192, 256, 384, 512, 768):
         taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
