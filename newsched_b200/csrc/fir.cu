@@ -802,12 +802,12 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
             // decimations that cannot fold (tools/decim_ab.py with DS=3,5,6,7,10,12): the phase-plane kernel
             // stages with per-sample copies and sits at 150-290 GS/s; the polyphase overlap-save is flat at
-            // 170-280.  D = 6 (TMA-staged polyphase form): from 64 taps; D = 3, 5, 7: beyond 96 taps;
+            // 130-280.  Even D = 6, 10, 12, 14 (TMA-staged polyphase form): from 64 taps; D = 3, 5, 7: beyond 96 taps;
             // larger D: from 192 taps, and whenever the phase planes would not fit shared memory
             if (poly == 1)
                 want = h->T >= 64; // (shorter filters stay on the direct kernel: exact impulse response)
             else if (poly == 2)
-                want = h->T > 96;
+                want = h->D <= 7 ? h->T > 96 : h->T >= 192;
             else
                 want = h->T >= 192 || h->algorithm == 4;
         }

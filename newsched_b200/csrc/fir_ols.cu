@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256, 2)
 
 
 // ---------------------------------------------------------------------------------------------
-// Decimating complex filters, even D <= 8: polyphase overlap-save.
+// Decimating complex filters, D <= 16 (TMA-staged for even D): polyphase overlap-save.
 //   y[m] = sum_p (h_p * x_p)[m],  h_p[q] = h[qD + p],  x_p[j] = x[jD - p]
 // so one block = D forward transforms (one per phase stream, each at the OUTPUT rate), the sum
 // sum_p X_p G_p accumulated in registers, and ONE inverse transform: (D + 1) transforms per
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, 2)
 // requested exactly twice per block (once per pair), all requests 16-byte aligned.  A phase whose
 // sample falls into the next row is read one output period late and its spectrum table G_p is
 // advanced by one sample to compensate (tables for both cases are built at create time).
-constexpr int OLSD_MAXD = 8;
+constexpr int OLSD_MAXD = 16;
 constexpr size_t OLSD_SMEM = OLS_N * 16 + 16 * F4K_STRIDE * 8 + 256 * 8 + 16;
 
 struct olsd_geom {
@@ -283,7 +283,7 @@ struct olsd_geom {
     int tma_ok;
     int rmin;  // row of circular sample 0 relative to (b V - Ov)
     int gbase; // sample index of (row r, slot s) = r D + s + gbase
-    unsigned gidx; // 4 bits per slot: spectrum table (phase * 2 + late)
+    int off;   // samples of the 16-byte granule that precede x[0] (0 or 1): fixes the slot -> phase map
     long long n_in, n_out, n_blocks;
 };
 
@@ -395,7 +395,10 @@ __global__ void __launch_bounds__(256, 2)
                 for (int i = 0; i < 16; i++)
                     v[i] = row[i];
                 dft16<true>(v);
-                const float2* G = Gtab + (size_t)((g.gidx >> (4 * slot)) & 15u) * OLS_N + tid;
+                // slot -> (phase, late): x_ph[j] sits at row j + floor((off - ph) / D), slot (off - ph) mod D
+                const int ph = slot <= g.off ? g.off - slot : g.off - slot + g.D;
+                const int late = (slot <= g.off ? 0 : -1) - g.rmin;
+                const float2* G = Gtab + (size_t)(ph * 2 + late) * OLS_N + tid;
 #pragma unroll
                 for (int k2 = 0; k2 < 16; k2++) {
                     const float2 w = __ldg(G + k2 * 256), a = v[pos16(k2)];
@@ -791,6 +794,11 @@ int ols_create(const float* taps, int T, int D, int real, int fuse, float kre, f
                                   (int)OLS_SMEM));
 #undef OLS_CUDA
     p->grid = 2 * sm_count();
+    // polyphase form with D > 10: a block's input span is D * 32 KiB and every pair plane pass re-reads it
+    // through L2; with 2 CTAs per SM the spans of all CTAs (D = 16: 151 MB) no longer fit the 126 MB L2
+    // and each pass goes back to HBM (measured 96 GS/s).  One CTA per SM keeps the working set resident.
+    if (p->poly && D > 10)
+        p->grid = sm_count();
     *out = p;
     return B200_OK;
 }
@@ -812,17 +820,8 @@ static int olsd_launch(ols_plan* p, const float* d_hist, const void* d_in, void*
     const uintptr_t a = (uintptr_t)d_in;
     const int off = (a % 16 == 8) ? 1 : 0;
     g.gbase = -off;
-    int rs[OLSD_MAXD], slot[OLSD_MAXD];
-    g.rmin = 0;
-    for (int ph = 0; ph < D; ph++) {
-        const int z = off - ph; // x_ph[j] sits at row j + floor(z / D), slot z mod D
-        rs[ph] = z >= 0 ? 0 : -1;
-        slot[ph] = z >= 0 ? z : z + D;
-        g.rmin = std::min(g.rmin, rs[ph]);
-    }
-    g.gidx = 0;
-    for (int ph = 0; ph < D; ph++)
-        g.gidx |= (unsigned)(ph * 2 + (rs[ph] - g.rmin)) << (4 * slot[ph]);
+    g.off = off;
+    g.rmin = (D - 1 > off) ? -1 : 0; // some phase sits one row earlier unless D == 2 and off == 1
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     const long long nrows = (n_in + off) / D;

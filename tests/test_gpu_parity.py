@@ -238,7 +238,7 @@ def test_fir_streaming_equals_oneshot(cuda, T, D):
 @pytest.mark.parametrize("T,D", [(2, 1), (64, 1), (65, 2), (256, 1), (1024, 4), (1000, 7), (3073, 1), (3000, 3),
                                  (3074, 1), (4096, 1), (4096, 4), (6001, 2), (1024, 8), (96, 2),
                                  (12288, 4), (13000, 4), (1024, 1), (1025, 1), (2048, 1), (6142, 1),
-                                 (6143, 1)])
+                                 (6143, 1), (1024, 10), (800, 12), (2048, 16), (900, 9), (1500, 14)])
 def test_fir_overlap_save_matches_oracle_and_direct(cuda, T, D):
     """algorithm 3 (FFT overlap-save) against the fp64 oracle, the direct form, and itself when
     the stream is chunked or time-segmented (FFT rounding differs per blocking -> tolerance)."""
@@ -282,7 +282,7 @@ def test_fir_overlap_save_matches_oracle_and_direct(cuda, T, D):
     assert o.rel_rms(host(yk), o.multiply_const(ref.astype(np.complex64), k)) < TOL_RMS
 
 
-@pytest.mark.parametrize("T,D", [(1024, 4), (257, 2), (700, 8), (2048, 1), (4095, 1)])
+@pytest.mark.parametrize("T,D", [(1024, 4), (257, 2), (700, 8), (2048, 1), (4095, 1), (640, 10), (1600, 16)])
 @pytest.mark.parametrize("start", [1, 2, 3])
 def test_fir_polyphase_overlap_save_any_pointer_alignment(cuda, T, D, start):
     """Even-D complex filters run the polyphase overlap-save kernel, whose TMA row view depends on
