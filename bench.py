@@ -428,6 +428,7 @@ def run_b200(args):
                     ("config1_fir_ccf_64taps_8Gi_stream", ["--config", "1", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_1Gi", ["--config", "3", "--samples", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_8Gi_stream", ["--config", "3", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
+                    ("config0_vector_source_fir64_vector_sink_16Mi", ["--config", "10", "--samples", str(1 << 24), "--buffer_size", str(1 << 26)]),
                     ("cuda_copy_x4_1Gi", ["--config", "0", "--samples", str(1 << 30)])):
                 best = None
                 for _ in range(3):
@@ -436,6 +437,23 @@ def run_b200(args):
                     if best is None or rec["Msamples_s"] > best["Msamples_s"]:
                         best = rec
                 fgx[name] = {k: best[k] for k in ("Msamples_s", "seconds", "kernel_launches", "buffer_size")}
+            # the reference's own CPU-runnable case (configs[0]) beside it: the oracle's fp32 FIR on all host cores
+            try:
+                import oracle as o
+                o.set_num_threads(len(os.sched_getaffinity(0)))
+                rngc = np.random.default_rng(0)
+                nc0 = 1 << 22
+                xc0 = (rngc.uniform(-1, 1, nc0) + 1j * rngc.uniform(-1, 1, nc0)).astype(np.complex64)
+                tc0 = np.full(64, 1.0 / 64, np.float32)
+                o.fir(xc0, tc0, 1, precise=False, mt=True)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    o.fir(xc0, tc0, 1, precise=False, mt=True)
+                fgx["config0_cpu_oracle_fir64"] = {
+                    "Msamples_s": 3 * nc0 / (time.perf_counter() - t0) / 1e6, "cores": o.num_threads(),
+                    "sample": "4 Mi complex64 samples x 3, oracle.c fp32 64-tap FIR, OpenMP over outputs (kernel only, no scheduler)"}
+            except Exception as e:  # pragma: no cover
+                fgx["config0_cpu_oracle_error"] = repr(e)
             fgx["how"] = ("newsched_b200/host/bm_flowgraph: cuda::null_source -> blocks -> null_sink on D2D "
                           "device_buffer edges under scheduler_mt; wall clock start()->wait(), best of 3")
             extras["flowgraph"] = fgx

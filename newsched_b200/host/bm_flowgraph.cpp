@@ -8,7 +8,11 @@
 //   --config 2  cuda::null_source -> fft(veclen, Blackman-Harris)[+ fused |.|] -> null_sink
 //   --config 3  cuda::null_source -> fir_filter_ccf(1024 taps, decim 4)[+ fused k] -> fft -> null_sink
 //   --config 0  cuda::null_source -> nblocks x cuda::copy -> null_sink       (bm_mt_cuda_copy shape)
+//   --config 10 BASELINE configs[0] as written: vector_source (host std::vector) -> fir_filter_ccf(ntaps)
+//               -> vector_sink (host), H2D / D2H staging edges, single mt scheduler
 #include <gnuradio/blocklib/blocks/null_sink.hpp>
+#include <gnuradio/blocklib/blocks/vector_sink.hpp>
+#include <gnuradio/blocklib/blocks/vector_source.hpp>
 #include <gnuradio/blocklib/cuda/complex_to_mag.hpp>
 #include <gnuradio/blocklib/cuda/copy.hpp>
 #include <gnuradio/blocklib/cuda/fft.hpp>
@@ -61,6 +65,35 @@ int main(int argc, char** argv)
     auto dev = [&](edge_sptr e) { e->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2D, buffer_size)); };
     std::shared_ptr<blocks::null_sink> snk;
     uint64_t expect_items = 0;
+    if (config == 10) {
+        std::vector<gr_complex> data(samples);
+        for (size_t i = 0; i < data.size(); i++)
+            data[i] = gr_complex((float)((i * 2654435761u) & 0xffff) / 32768.f - 1.f,
+                                 (float)((i * 40503u) & 0xffff) / 32768.f - 1.f);
+        auto src = blocks::vector_source_c::make(data);
+        std::vector<float> taps(ntaps, 1.0f / ntaps);
+        auto f = cuda::fir_filter_ccf::make(1, taps);
+        auto vsnk = blocks::vector_sink_c::make(1, samples);
+        fg->connect(src, 0, f, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, buffer_size));
+        fg->connect(f, 0, vsnk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, buffer_size));
+        fg->set_scheduler(sched);
+        fg->validate();
+        b200_device_synchronize();
+        int64_t l0 = b200_launch_count();
+        auto t1 = std::chrono::steady_clock::now();
+        fg->start();
+        fg->wait();
+        b200_device_synchronize();
+        auto t2 = std::chrono::steady_clock::now();
+        double sec = std::chrono::duration<double>(t2 - t1).count();
+        std::printf("[PROFILE_TIME]%f[PROFILE_TIME]\n", sec);
+        std::printf("{\"config\": 10, \"samples\": %llu, \"seconds\": %.6f, \"Msamples_s\": %.1f, \"sink_items\": %llu, "
+                    "\"expected_items\": %llu, \"kernel_launches\": %lld, \"fused\": 0, \"buffer_size\": %zu, "
+                    "\"source_clears\": 0}\n",
+                    (unsigned long long)samples, sec, samples / sec / 1e6, (unsigned long long)vsnk->data().size(),
+                    (unsigned long long)samples, (long long)(b200_launch_count() - l0), buffer_size);
+        return vsnk->data().size() == samples ? 0 : 2;
+    }
     if (config == 2) {
         auto src = cuda::null_source::make(veclen * sizeof(gr_complex), samples / veclen, clear != 0);
         auto w = blackman_harris(veclen);
