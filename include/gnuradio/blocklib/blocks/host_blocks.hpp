@@ -122,7 +122,10 @@ public:
     }
     explicit vector_sink(size_t vlen = 1, size_t reserve_items = 1024) : sync_block("vector_sink"), d_vlen(vlen)
     {
-        d_store.reserve(d_vlen * reserve_items);
+        // reserve AND touch: a reserve alone leaves every page to be faulted in by the first append,
+        // inside the flowgraph's run (16 Mi complex samples = 32768 page faults on the sink thread)
+        d_store.resize(d_vlen * reserve_items);
+        d_store.clear();
     }
     work_return_code_t work(std::vector<block_work_input>& wi, std::vector<block_work_output>&) override
     {
