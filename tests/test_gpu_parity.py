@@ -794,6 +794,56 @@ def test_pfb_tone(cuda):
         assert int(np.argmax(p)) == c0 and p[c0] > 1e3 * np.delete(p, c0).max(), (M, c0)
 
 
+def test_small_and_ragged_sizes_for_the_tiled_kernels(cuda):
+    """Sizes around the tile / grid granularities of the single-pass kernels: fewer items than one tile,
+    one more than a whole number of tiles, one more vector than resident CTAs."""
+    import scipy.signal as sig
+    import newsched_b200 as nb
+    rng = np.random.default_rng(77)
+    # decimation folded into the full-rate kernel: tiles of 2048 inputs
+    for D, T in ((4, 64), (16, 33), (2, 5)):
+        taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+        for n in (0, 1, D - 1, D, D + 1, 2047, 2048, 2049, 2048 * 3 + D + 1):
+            x = cplx(rng, n)
+            y, nc = nb.FirFilter(taps, D, algorithm=1).work(dev(cuda, x))
+            assert y.numel() == n // D and nc == (n // D) * D
+            if n >= D:
+                assert o.rel_rms(host(y), o.fir(x, taps, D)) < TOL_RMS
+    # interpolation folded into the full-rate kernel
+    for L, T in ((2, 64), (3, 10)):
+        taps = rng.uniform(-1, 1, T).astype(np.float32)
+        for n in (1, 17, 2047, 2049, 4096 + 5):
+            x = cplx(rng, n)
+            y, nc = nb.RationalResampler(taps, L, 1).work(dev(cuda, x))
+            assert y.numel() == n * L and nc == n
+            assert o.rel_rms(host(y), o.resample(x, taps, L, 1)) < TOL_RMS
+    # single-pass channelizers: tiles of 4096 samples
+    for M, P in ((16, 8), (32, 4), (128, 8), (256, 4), (64, 16)):
+        taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
+        TT = 4096 // M
+        for nf in (1, TT - 1, TT, TT + 1, 3 * TT + 2):
+            x = cplx(rng, nf * M + M // 2)
+            y, nc = nb.PfbChannelizer(taps, M).work(dev(cuda, x))
+            assert y.shape[0] == nf and nc == nf * M
+            assert o.rel_rms(host(y), o.pfb_channelizer(x, taps, M)) < TOL_RMS
+    # FFT 8192 / 8: one vector, and one more than a multiple of the resident grid
+    sms = cuda.cuda.get_device_properties(0).multi_processor_count
+    for N, counts in ((8192, (1, 2, 2 * sms + 1)), (8, (1, 255, 256 * 16 * sms + 3))):
+        w = rng.uniform(0.1, 1, N).astype(np.float32)
+        for nv in counts:
+            x = cplx(rng, nv * N)
+            y = host(nb.FFT(N, True, w).work(dev(cuda, x)))
+            pick = sorted({0, nv // 2, nv - 1})
+            for v in pick:
+                assert o.rel_rms(y[v * N:(v + 1) * N], o.fft(x[v * N:(v + 1) * N], N, True, w)) < TOL_RMS
+    # polyphase overlap-save at a large decimation, fewer outputs than one block
+    taps = (rng.uniform(-1, 1, 2000) / 2000).astype(np.float32)
+    for n in (16, 16 * 100 + 3, 16 * 5000 + 1):
+        x = cplx(rng, n)
+        y, _ = nb.FirFilter(taps, 16, algorithm=3).work(dev(cuda, x))
+        assert y.numel() == n // 16 and o.rel_rms(host(y), o.fir(x, taps, 16)) < TOL_RMS
+
+
 # ------------------------------------------------------------------------ ring / chain
 def test_ring_double_mapping(cuda):
     import newsched_b200 as nb
