@@ -67,6 +67,7 @@ struct fir_geom {
     long long full_rows;     // rows of the input that are completely inside [0, n_in)
     long long full_out_rows; // rows of the output completely inside [0, n_out)
     long long n_in, n_out;
+    long long n_in_f, n_out_f; // RP mode: bounds in floats (n_in / n_out are in float PAIRS there)
 };
 
 // x value at global sample index g (may be negative -> history, or >= n_in -> 0)
@@ -171,7 +172,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // SAME input tile with the taps of phase r: LL passes of the register-blocked loop over one
 // TMA-staged tile, each scattering its 16 results per thread into the thread's own LL rows of a
 // separate output tile (16 LL consecutive outputs), which then leaves by LL TMA tensor stores.
-template <int VEC, bool DECIM, int DD = 1, int LL = 1>
+// RP ("real pairs", with VEC = 2, DECIM = false): a REAL stream f[] run through the packed
+// complex x real loop.  With the float pairs P0[j] = (f[2j], f[2j+1]) (the stream itself) and
+// P1[j] = (f[2j-1], f[2j]) (the stream one float later), (y[2m], y[2m+1]) = h_e * P0 + h_o * P1 with the
+// even / odd taps: two passes of the FFMA2 loop, i.e. half the issue slots of the scalar fff loop.
+// P0 is staged by the same TMA tensor load as a complex stream; P1 is derived from it in shared memory
+// (each thread shifts its own row by one float).
+template <int VEC, bool DECIM, int DD = 1, int LL = 1, bool RP = false>
 __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
@@ -185,11 +192,12 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     static_assert(!DECIM || DD == 1, "DD applies to the TMA-staged full-rate kernel only");
     static_assert(R % DD == 0, "decimation must divide the positions per thread");
     static_assert(LL == 1 || (!DECIM && DD == 1), "LL applies to the TMA-staged full-rate kernel only");
+    static_assert(!RP || (VEC == 2 && !DECIM && DD == 1 && LL == 1), "RP is the full-rate real-stream mode");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* hs = reinterpret_cast<float*>(smem_raw + 16);
     const int D = DECIM ? gm.D : 1, TQ = gm.TQ;
-    const int NTAPROWS = LL > 1 ? LL : D; // tap rows: one per decimation phase / interpolation phase
+    const int NTAPROWS = RP ? 2 : LL > 1 ? LL : D; // tap rows: one per decimation / interpolation phase
     float* planes;
     {
         uint32_t a = smem_u32(hs + NTAPROWS * TQ);
@@ -259,8 +267,16 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int i = i0 + u * FIR_NT;
-                if (i < total)
-                    fir_fetch<VEC>(x, hist, gm.Tm1, g_lo + i, gm.n_in, v[u]);
+                if (i < total) {
+                    if (RP) { // pair g = floats 2g, 2g+1 of the real stream, each with its own bounds
+                        float t0[2], t1_[2];
+                        fir_fetch<1>(x, hist, gm.Tm1, 2 * (g_lo + i), gm.n_in_f, t0);
+                        fir_fetch<1>(x, hist, gm.Tm1, 2 * (g_lo + i) + 1, gm.n_in_f, t1_);
+                        v[u][0] = t0[0];
+                        v[u][1] = t1_[0];
+                    } else
+                        fir_fetch<VEC>(x, hist, gm.Tm1, g_lo + i, gm.n_in, v[u]);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
@@ -278,6 +294,30 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     __syncthreads();
     if (use_tma)
         mbar_wait(bar, 0);
+    if (RP) {
+        // plane 1 = plane 0 one float later: row r = [last float of row r-1, first 31 floats of row r]
+        float first[2];
+        fir_fetch<1>(x, hist, gm.Tm1, 2 * B0 - 1, gm.n_in_f, first); // the float in front of the tile
+        float* P1 = planes + plane_f;
+        for (int r = tid; r < gm.plane_rows; r += FIR_NT) {
+            const float* rb = planes + (r << 5);
+            const int sw = (r & 7) << 2;
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 t = *reinterpret_cast<const float4*>(rb + ((j << 2) ^ sw));
+                a[4 * j] = t.x, a[4 * j + 1] = t.y, a[4 * j + 2] = t.z, a[4 * j + 3] = t.w;
+            }
+            const float prev = r > 0 ? planes[swz(32 * r - 1)] : first[0];
+            float* wb = P1 + (r << 5);
+            *reinterpret_cast<float4*>(wb + (0 ^ sw)) = make_float4(prev, a[0], a[1], a[2]);
+#pragma unroll
+            for (int j = 1; j < 8; j++)
+                *reinterpret_cast<float4*>(wb + ((j << 2) ^ sw)) =
+                    make_float4(a[4 * j - 1], a[4 * j], a[4 * j + 1], a[4 * j + 2]);
+        }
+        __syncthreads();
+    }
 
     // ---- register-blocked multiply-accumulate -----------------------------------------
     float acc[FIR_ACC];
@@ -349,7 +389,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         }
         return;
     }
-    for (int p = 0; p < D; p++) {
+    for (int p = 0; p < (RP ? 2 : D); p++) {
         const float* plane = planes + p * plane_f;
         const float* hp = hs + p * TQ;
         fir_load_half<0>(W, plane, tid);
@@ -368,7 +408,11 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     __syncthreads();
 
     // ---- outputs: registers -> shared (swizzled row per thread) -> global ----------------------
-    if (ep.fuse) {
+    if (ep.fuse && RP) {
+#pragma unroll
+        for (int l = 0; l < FIR_ACC; l++)
+            acc[l] = __fmul_rn(acc[l], ep.kre);
+    } else if (ep.fuse) {
         if (VEC == 2) {
 #pragma unroll
             for (int l = 0; l < FIR_ACC; l += 2 * DD) {
@@ -429,7 +473,11 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         if (m >= gm.n_out)
             break;
         const float* src = planes + swz(i * VEC);
-        if (VEC == 2)
+        if (RP) { // the last pair of an odd-length real stream is half a pair
+            __stcs(y + 2 * m, src[0]);
+            if (2 * m + 1 < gm.n_out_f)
+                __stcs(y + 2 * m + 1, src[1]);
+        } else if (VEC == 2)
             __stcs(reinterpret_cast<float2*>(y) + m, *reinterpret_cast<const float2*>(src));
         else
             __stcs(y + m, src[0]);
@@ -488,6 +536,7 @@ struct b200_fir {
     int plane_rows = 0, box_rows = 0, n_boxes = 0; // smem plane geometry (rows of 128 B)
     size_t smem = 0;
     int use_tma = 1;
+    int rp = 0;      // real stream through the packed complex x real loop (fir_direct_kernel<..., RP>)
     int interp = 0;  // > 1: interpolation folded into the full-rate kernel (created by fir_interp_create)
     int dd = 0;      // > 1: decimation folded into the TMA-staged full-rate kernel (geometry as for D = 1)
     ols_plan* ols = nullptr; // algorithm 3
@@ -530,6 +579,39 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         return ols_launch(h->ols, d_hist, d_in, d_out, n_in, n_out, s);
     if (h->algorithm == 5)
         return ffa_launch(h->ffa, d_hist, d_in, d_out, n_in, n_out, s);
+    if (h->algorithm == 1 && h->rp) {
+        // real stream as float pairs: tiles of 2048 pairs = 4096 real outputs
+        const long long pairs_out = (n_out + 1) / 2, pairs_in = (n_in + 1) / 2;
+        const int MTp = FIR_NT * (FIR_ACC / 2);
+        const long long tiles = (pairs_out + MTp - 1) / MTp;
+        if (tiles > 0x7fffffffLL)
+            return set_err(B200_ERR_ARG, "fir: too many items for one call");
+        fir_geom gm{};
+        gm.Tm1 = h->T - 1;
+        gm.D = 1;
+        gm.TQ = h->TQ;
+        gm.plane_rows = h->plane_rows;
+        gm.box_rows = h->box_rows;
+        gm.n_boxes = h->n_boxes;
+        gm.n_in = pairs_in;
+        gm.n_out = pairs_out;
+        gm.n_in_f = n_in;
+        gm.n_out_f = n_out;
+        gm.full_rows = n_in / 32;
+        gm.full_out_rows = n_out / 32;
+        CUtensorMap tmap, tmap_out;
+        memset(&tmap, 0, sizeof(tmap));
+        memset(&tmap_out, 0, sizeof(tmap_out));
+        if (h->use_tma && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0 &&
+            fir_make_tmap(&tmap, d_in, gm.full_rows, h->box_rows) == B200_OK)
+            gm.tma_ok = 1;
+        if (h->use_tma && gm.full_out_rows >= FIR_NT && (uintptr_t)d_out % 16 == 0 &&
+            fir_make_tmap(&tmap_out, d_out, gm.full_out_rows, FIR_NT) == B200_OK)
+            gm.tma_out_ok = 1;
+        B200_LAUNCH((fir_direct_kernel<2, false, 1, 1, true>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,
+                    h->d_taps_pp, tmap, tmap_out, gm, h->ep);
+        return B200_OK;
+    }
     if (h->algorithm == 1) {
         const int MT = FIR_NT * (FIR_ACC / h->vec) / (h->dd ? h->dd : 1); // outputs per tile
         long long tiles = (n_out + MT - 1) / MT;
@@ -763,12 +845,15 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     h->ep = fir_epilogue{ p->fuse_multiply_const ? 1 : 0, p->k_re, p->k_im };
     cudaGetDevice(&h->device);
 
-    const int CH = FIR_ACC / h->vec;
+    // full-rate real streams run as float pairs through the packed complex x real loop
+    if (h->vec == 1 && h->D == 1 && !getenv("B200_FIR_REAL_SCALAR"))
+        h->rp = 1;
+    const int CH = FIR_ACC / (h->rp ? 2 : h->vec);
     const int MT = FIR_NT * (FIR_ACC / h->vec);
     // decimations that divide the 16 (32) window positions of a thread run in the full-rate kernel
     if (h->D > 1 && (FIR_ACC / h->vec) % h->D == 0 && !getenv("B200_FIR_PLANES"))
         h->dd = h->D;
-    const int Dg = h->dd ? 1 : h->D; // decimation the plane / tap geometry is built for
+    const int Dg = h->rp ? 2 : h->dd ? 1 : h->D; // phases the plane / tap geometry is built for
     int tq = (h->T + Dg - 1) / Dg;
     h->TQ = (tq + CH - 1) / CH * CH; // whole 16- (32-) tap steps
     (void)MT;
@@ -907,6 +992,9 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         FIR_DD_ATTR(1, 32);
 #undef FIR_DD_ATTR
     }
+    if (h->algorithm == 1 && h->rp)
+        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (h->algorithm == 1) {
         if (h->vec == 2)
         {

@@ -482,7 +482,11 @@ def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     assert o.rel_rms(host(y), ref) < TOL_RMS
     one = host(y)
     # decimation phase: y[m] is the full-rate output at m*D, bit for bit
-    full = host(nb.FirFilter(taps, 1, is_complex=cplxin, algorithm=1).work(dx)[0])
+    os.environ["B200_FIR_REAL_SCALAR"] = "1"     # (full-rate fff normally runs the float-pair form: other sum order)
+    try:
+        full = host(nb.FirFilter(taps, 1, is_complex=cplxin, algorithm=1).work(dx)[0])
+    finally:
+        os.environ.pop("B200_FIR_REAL_SCALAR", None)
     assert np.array_equal(one, full[::D][: one.size])
     # ragged chunks (unaligned pointers -> the non-TMA staging path) and segments with a halo
     f2 = nb.FirFilter(taps, D, is_complex=cplxin, algorithm=1)
@@ -510,6 +514,59 @@ def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     off = 1 if cplxin else 3
     f.work_segment(dx, None, buf[off:off + n // D])
     assert np.array_equal(host(buf[off:off + n // D]), one) and buf[0].item() == 0 and buf[-1].item() == 0
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 16, 31, 32, 33, 64, 100, 128, 255])
+def test_fir_real_stream_as_float_pairs(cuda, T):
+    """Full-rate fff runs as float pairs through the packed complex x real loop (even taps on the
+    stream, odd taps on the stream one float later): oracle parity, odd lengths, any chunking
+    bit-identical (the sum order of an output does not depend on where it falls), history, segments,
+    fused constant, unaligned pointers; and within rounding of the scalar kernel it replaces."""
+    import os
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T)
+    n = 4096 * 9 + 777          # odd
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    dx = dev(cuda, x)
+    f = nb.FirFilter(taps, 1, is_complex=False, algorithm=1)
+    y, nc = f.work(dx)
+    ref = o.fir(x, taps, 1)
+    assert y.numel() == n and nc == n
+    assert o.rel_rms(host(y), ref) < TOL_RMS
+    assert np.max(np.abs(host(y) - ref)) < 1e-5 * max(1e-3, np.max(np.abs(ref)))
+    one = host(y)
+    f2 = nb.FirFilter(taps, 1, is_complex=False, algorithm=1)
+    outs, pos = [], 0
+    for chunk in (5001, 1, 4096, 33333, 7, 2, 10 ** 9):
+        if pos >= n:
+            break
+        yy, c = f2.work(dx[pos:min(pos + chunk, n)])
+        outs.append(host(yy))
+        pos += c
+    assert np.array_equal(np.concatenate(outs), one), "chunked != one-shot"
+    if T > 1:
+        L = n // 3
+        parts = []
+        for g in range(3):
+            lo, hi = g * L, (n if g == 2 else (g + 1) * L)
+            halo = None if g == 0 else dx[lo - (T - 1):lo]
+            parts.append(host(f.work_segment(dx[lo:hi], halo)))
+        assert np.array_equal(np.concatenate(parts), one), "time segments + halo != one stream"
+    yk, _ = nb.FirFilter(taps, 1, is_complex=False, multiply_const=3.25, algorithm=1).work(dx)
+    assert np.array_equal(host(yk), one * np.float32(3.25))
+    for off_in, off_out in ((1, 0), (0, 3), (3, 1)):
+        xb = cuda.zeros(n + 4, dtype=cuda.float32, device="cuda")
+        xb[off_in:off_in + n] = dx
+        ob = cuda.zeros(n + 8, dtype=cuda.float32, device="cuda")
+        f.work_segment(xb[off_in:off_in + n], None, ob[off_out:off_out + n])
+        assert np.array_equal(host(ob[off_out:off_out + n]), one) and ob[off_out + n].item() == 0
+    os.environ["B200_FIR_REAL_SCALAR"] = "1"
+    try:
+        ys, _ = nb.FirFilter(taps, 1, is_complex=False, algorithm=1).work(dx)
+    finally:
+        os.environ.pop("B200_FIR_REAL_SCALAR", None)
+    assert o.rel_rms(one, host(ys)) < TOL_RMS
 
 
 def test_fir_auto_algorithm_choice(cuda):
