@@ -455,7 +455,8 @@ def run_b200(args):
             except Exception as e:  # pragma: no cover
                 fgx["config0_cpu_oracle_error"] = repr(e)
             fgx["how"] = ("newsched_b200/host/bm_flowgraph: cuda::null_source -> blocks -> null_sink on D2D "
-                          "device_buffer edges under scheduler_mt; wall clock start()->wait(), best of 3")
+                          "device_buffer edges under scheduler_mt; wall clock start()->wait() of the second run in the process (a short "
+                          "untimed run first loads the kernels' modules, which costs milliseconds once), best of 3")
             extras["flowgraph"] = fgx
         except Exception as e:  # pragma: no cover
             extras["flowgraph_error"] = repr(e)

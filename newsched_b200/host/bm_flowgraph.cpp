@@ -23,6 +23,7 @@
 #include <gnuradio/flowgraph.hpp>
 #include <gnuradio/schedulers/mt/scheduler_mt.hpp>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -60,22 +61,106 @@ int main(int argc, char** argv)
         else if (k == "--clear") clear = atoi(v);
         else if (k == "--buffer_size") buffer_size = strtoull(v, nullptr, 10);
     }
+    int warm = 1;
+    for (int i = 1; i + 1 < argc; i += 2)
+        if (std::string(argv[i]) == "--warm")
+            warm = atoi(argv[i + 1]);
+    // One flowgraph run.  The timed run is preceded by a short untimed one of the same flowgraph
+    // (--warm 0 disables it): CUDA loads a kernel's module at its first launch, and for a run of a
+    // few milliseconds those one-off loads (they grow with the size of the library, not with the
+    // work) would be most of the wall clock.
+    auto run = [&](uint64_t samples, bool quiet) -> int {
     auto fg = flowgraph::make();
-    auto sched = schedulers::scheduler_mt::make("sched", 32768);
-    auto dev = [&](edge_sptr e) { e->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2D, buffer_size)); };
-    std::shared_ptr<blocks::null_sink> snk;
-    uint64_t expect_items = 0;
-    if (config == 10) {
-        std::vector<gr_complex> data(samples);
-        for (size_t i = 0; i < data.size(); i++)
-            data[i] = gr_complex((float)((i * 2654435761u) & 0xffff) / 32768.f - 1.f,
-                                 (float)((i * 40503u) & 0xffff) / 32768.f - 1.f);
-        auto src = blocks::vector_source_c::make(data);
-        std::vector<float> taps(ntaps, 1.0f / ntaps);
-        auto f = cuda::fir_filter_ccf::make(1, taps);
-        auto vsnk = blocks::vector_sink_c::make(1, samples);
-        fg->connect(src, 0, f, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, buffer_size));
-        fg->connect(f, 0, vsnk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, buffer_size));
+        auto sched = schedulers::scheduler_mt::make("sched", 32768);
+        auto dev = [&](edge_sptr e) { e->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2D, buffer_size)); };
+        std::shared_ptr<blocks::null_sink> snk;
+        uint64_t expect_items = 0;
+        if (config == 10) {
+            std::vector<gr_complex> data(samples);
+            for (size_t i = 0; i < data.size(); i++)
+                data[i] = gr_complex((float)((i * 2654435761u) & 0xffff) / 32768.f - 1.f,
+                                     (float)((i * 40503u) & 0xffff) / 32768.f - 1.f);
+            auto src = blocks::vector_source_c::make(data);
+            std::vector<float> taps(ntaps, 1.0f / ntaps);
+            auto f = cuda::fir_filter_ccf::make(1, taps);
+            auto vsnk = blocks::vector_sink_c::make(1, samples);
+            fg->connect(src, 0, f, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, buffer_size));
+            fg->connect(f, 0, vsnk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, buffer_size));
+            fg->set_scheduler(sched);
+            fg->validate();
+            b200_device_synchronize();
+            int64_t l0 = b200_launch_count();
+            auto t1 = std::chrono::steady_clock::now();
+            fg->start();
+            fg->wait();
+            b200_device_synchronize();
+            auto t2 = std::chrono::steady_clock::now();
+            double sec = std::chrono::duration<double>(t2 - t1).count();
+            if (!quiet) std::printf("[PROFILE_TIME]%f[PROFILE_TIME]\n", sec);
+            if (!quiet) std::printf("{\"config\": 10, \"samples\": %llu, \"seconds\": %.6f, \"Msamples_s\": %.1f, \"sink_items\": %llu, "
+                        "\"expected_items\": %llu, \"kernel_launches\": %lld, \"fused\": 0, \"buffer_size\": %zu, "
+                        "\"source_clears\": 0}\n",
+                        (unsigned long long)samples, sec, samples / sec / 1e6, (unsigned long long)vsnk->data().size(),
+                        (unsigned long long)samples, (long long)(b200_launch_count() - l0), buffer_size);
+            return vsnk->data().size() == samples ? 0 : 2;
+        }
+        if (config == 2) {
+            auto src = cuda::null_source::make(veclen * sizeof(gr_complex), samples / veclen, clear != 0);
+            auto w = blackman_harris(veclen);
+            if (fused) {
+                auto f = cuda::fft::make(veclen, true, w, false, cuda::fft_output_t::MAG);
+                snk = blocks::null_sink::make(veclen * sizeof(float));
+                dev(fg->connect(src, 0, f, 0));
+                dev(fg->connect(f, 0, snk, 0));
+            } else {
+                auto f = cuda::fft::make(veclen, true, w);
+                auto m = cuda::complex_to_mag::make(veclen);
+                snk = blocks::null_sink::make(veclen * sizeof(float));
+                dev(fg->connect(src, 0, f, 0));
+                dev(fg->connect(f, 0, m, 0));
+                dev(fg->connect(m, 0, snk, 0));
+            }
+            expect_items = samples / veclen;
+        } else if (config == 1) {
+            auto src = cuda::null_source::make(sizeof(gr_complex), samples, clear != 0);
+            std::vector<float> taps(ntaps, 1.0f / ntaps);
+            auto f = cuda::fir_filter_ccf::make(1, taps);
+            snk = blocks::null_sink::make(sizeof(gr_complex));
+            dev(fg->connect(src, 0, f, 0));
+            dev(fg->connect(f, 0, snk, 0));
+            expect_items = samples;
+        } else if (config == 3) {
+            auto src = cuda::null_source::make(sizeof(gr_complex), samples, clear != 0);
+            std::vector<float> taps(1024, 1.0f / 1024);
+            auto f = cuda::fir_filter_ccf::make(4, taps);
+            auto w = blackman_harris(veclen);
+            snk = blocks::null_sink::make(veclen * sizeof(gr_complex));
+            dev(fg->connect(src, 0, f, 0));
+            if (fused) {
+                f->set_fused_multiply_const(gr_complex(0.5f, -0.25f));
+                auto t = cuda::fft::make(veclen, true, w, false, cuda::fft_output_t::COMPLEX, true);
+                dev(fg->connect(f, 0, t, 0));
+                dev(fg->connect(t, 0, snk, 0));
+            } else {
+                auto mul = cuda::multiply_const_cc::make(gr_complex(0.5f, -0.25f));
+                auto t = cuda::fft::make(veclen, true, w, false, cuda::fft_output_t::COMPLEX, true);
+                dev(fg->connect(f, 0, mul, 0));
+                dev(fg->connect(mul, 0, t, 0));
+                dev(fg->connect(t, 0, snk, 0));
+            }
+            expect_items = samples / 4 / veclen;
+        } else {
+            auto src = cuda::null_source::make(veclen * sizeof(gr_complex), samples / veclen, clear != 0);
+            node_sptr last = src;
+            for (int b = 0; b < nblocks; b++) {
+                auto c = cuda::copy::make(veclen);
+                dev(fg->connect(last, 0, c, 0));
+                last = c;
+            }
+            snk = blocks::null_sink::make(veclen * sizeof(gr_complex));
+            dev(fg->connect(last, 0, snk, 0));
+            expect_items = samples / veclen;
+        }
         fg->set_scheduler(sched);
         fg->validate();
         b200_device_synchronize();
@@ -86,86 +171,19 @@ int main(int argc, char** argv)
         b200_device_synchronize();
         auto t2 = std::chrono::steady_clock::now();
         double sec = std::chrono::duration<double>(t2 - t1).count();
-        std::printf("[PROFILE_TIME]%f[PROFILE_TIME]\n", sec);
-        std::printf("{\"config\": 10, \"samples\": %llu, \"seconds\": %.6f, \"Msamples_s\": %.1f, \"sink_items\": %llu, "
-                    "\"expected_items\": %llu, \"kernel_launches\": %lld, \"fused\": 0, \"buffer_size\": %zu, "
-                    "\"source_clears\": 0}\n",
-                    (unsigned long long)samples, sec, samples / sec / 1e6, (unsigned long long)vsnk->data().size(),
-                    (unsigned long long)samples, (long long)(b200_launch_count() - l0), buffer_size);
-        return vsnk->data().size() == samples ? 0 : 2;
+        if (!quiet) std::printf("[PROFILE_TIME]%f[PROFILE_TIME]\n", sec);
+        if (!quiet) std::printf("{\"config\": %d, \"samples\": %llu, \"seconds\": %.6f, \"Msamples_s\": %.1f, \"sink_items\": %llu, "
+                    "\"expected_items\": %llu, \"kernel_launches\": %lld, \"fused\": %d, \"buffer_size\": %zu, "
+                    "\"source_clears\": %d}\n",
+                    config, (unsigned long long)samples, sec, samples / sec / 1e6, (unsigned long long)snk->n_items(),
+                    (unsigned long long)expect_items, (long long)(b200_launch_count() - l0), fused, buffer_size, clear);
+        return snk->n_items() == expect_items ? 0 : 2;
+    };
+    if (warm) {
+        const uint64_t unit = (uint64_t)veclen * 4 * 64;
+        uint64_t ws = std::min<uint64_t>(samples, (uint64_t)1 << 24) / unit * unit;
+        if (ws >= unit)
+            (void)run(ws, true);
     }
-    if (config == 2) {
-        auto src = cuda::null_source::make(veclen * sizeof(gr_complex), samples / veclen, clear != 0);
-        auto w = blackman_harris(veclen);
-        if (fused) {
-            auto f = cuda::fft::make(veclen, true, w, false, cuda::fft_output_t::MAG);
-            snk = blocks::null_sink::make(veclen * sizeof(float));
-            dev(fg->connect(src, 0, f, 0));
-            dev(fg->connect(f, 0, snk, 0));
-        } else {
-            auto f = cuda::fft::make(veclen, true, w);
-            auto m = cuda::complex_to_mag::make(veclen);
-            snk = blocks::null_sink::make(veclen * sizeof(float));
-            dev(fg->connect(src, 0, f, 0));
-            dev(fg->connect(f, 0, m, 0));
-            dev(fg->connect(m, 0, snk, 0));
-        }
-        expect_items = samples / veclen;
-    } else if (config == 1) {
-        auto src = cuda::null_source::make(sizeof(gr_complex), samples, clear != 0);
-        std::vector<float> taps(ntaps, 1.0f / ntaps);
-        auto f = cuda::fir_filter_ccf::make(1, taps);
-        snk = blocks::null_sink::make(sizeof(gr_complex));
-        dev(fg->connect(src, 0, f, 0));
-        dev(fg->connect(f, 0, snk, 0));
-        expect_items = samples;
-    } else if (config == 3) {
-        auto src = cuda::null_source::make(sizeof(gr_complex), samples, clear != 0);
-        std::vector<float> taps(1024, 1.0f / 1024);
-        auto f = cuda::fir_filter_ccf::make(4, taps);
-        auto w = blackman_harris(veclen);
-        snk = blocks::null_sink::make(veclen * sizeof(gr_complex));
-        dev(fg->connect(src, 0, f, 0));
-        if (fused) {
-            f->set_fused_multiply_const(gr_complex(0.5f, -0.25f));
-            auto t = cuda::fft::make(veclen, true, w, false, cuda::fft_output_t::COMPLEX, true);
-            dev(fg->connect(f, 0, t, 0));
-            dev(fg->connect(t, 0, snk, 0));
-        } else {
-            auto mul = cuda::multiply_const_cc::make(gr_complex(0.5f, -0.25f));
-            auto t = cuda::fft::make(veclen, true, w, false, cuda::fft_output_t::COMPLEX, true);
-            dev(fg->connect(f, 0, mul, 0));
-            dev(fg->connect(mul, 0, t, 0));
-            dev(fg->connect(t, 0, snk, 0));
-        }
-        expect_items = samples / 4 / veclen;
-    } else {
-        auto src = cuda::null_source::make(veclen * sizeof(gr_complex), samples / veclen, clear != 0);
-        node_sptr last = src;
-        for (int b = 0; b < nblocks; b++) {
-            auto c = cuda::copy::make(veclen);
-            dev(fg->connect(last, 0, c, 0));
-            last = c;
-        }
-        snk = blocks::null_sink::make(veclen * sizeof(gr_complex));
-        dev(fg->connect(last, 0, snk, 0));
-        expect_items = samples / veclen;
-    }
-    fg->set_scheduler(sched);
-    fg->validate();
-    b200_device_synchronize();
-    int64_t l0 = b200_launch_count();
-    auto t1 = std::chrono::steady_clock::now();
-    fg->start();
-    fg->wait();
-    b200_device_synchronize();
-    auto t2 = std::chrono::steady_clock::now();
-    double sec = std::chrono::duration<double>(t2 - t1).count();
-    std::printf("[PROFILE_TIME]%f[PROFILE_TIME]\n", sec);
-    std::printf("{\"config\": %d, \"samples\": %llu, \"seconds\": %.6f, \"Msamples_s\": %.1f, \"sink_items\": %llu, "
-                "\"expected_items\": %llu, \"kernel_launches\": %lld, \"fused\": %d, \"buffer_size\": %zu, "
-                "\"source_clears\": %d}\n",
-                config, (unsigned long long)samples, sec, samples / sec / 1e6, (unsigned long long)snk->n_items(),
-                (unsigned long long)expect_items, (long long)(b200_launch_count() - l0), fused, buffer_size, clear);
-    return snk->n_items() == expect_items ? 0 : 2;
+    return run(samples, false);
 }
