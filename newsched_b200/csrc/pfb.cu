@@ -499,6 +499,147 @@ __global__ void __launch_bounds__(256, (M >= 128 ? 1 : 2))
     }
 }
 
+// ---- M = 4, 8: same tiles and branch filters, the whole DFT in one thread --------------------------
+// 4096-sample tiles (TT = 4096/M frames); the branch outputs go to shared memory branch-major
+// (U[i][frame], row stride TT + 1), so the DFT thread of a frame reads its M values with lane-contiguous
+// LDS.64 and writes the frame's M channels as 16-byte stores (neighbouring lanes = neighbouring frames:
+// whole lines).
+template <int M, int P4T>
+__global__ void __launch_bounds__(256, 2)
+    pfbs_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
+                const float* __restrict__ taps_rm /* [P4][M] */, int P4, int Ptrue, long long n_frames,
+                long long n_in, int ch_begin, int ch_count, int tma_ok, int out16)
+{
+    constexpr int TT = 4096 / M, US = TT + 1;
+    extern __shared__ __align__(128) float2 sm[];
+    const int rows = TT + P4 - 1;
+    float2* X = sm;
+    float2* U = X + rows * M;
+    float* hT = reinterpret_cast<float*>(U + M * US);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + P4 * M + ((P4 * M) & 1));
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < P4 * M; i += 256)
+        hT[i] = __ldg(taps_rm + i);
+    const long long nh = (long long)(Ptrue - 1) * M;
+    const long long n_tiles = (n_frames + TT - 1) / TT;
+    const uint32_t tile_bytes = (uint32_t)rows * (uint32_t)M * 8u;
+    auto tma_tile = [&](long long t) {
+        const long long g0 = (t * TT - (P4 - 1)) * M;
+        return tma_ok && g0 >= 0 && g0 + (long long)rows * M <= n_in;
+    };
+    __syncthreads();
+    long long tile = blockIdx.x;
+    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
+        mbar_arrive_expect_tx(bar, tile_bytes);
+        bulk_copy_g2s(X, x + (tile * TT - (P4 - 1)) * M, tile_bytes, bar);
+    }
+    uint32_t phase = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const long long f0 = tile * TT;
+        if (tma_tile(tile)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            const long long g0 = (f0 - (P4 - 1)) * M;
+            for (int i0 = tid; i0 < rows * M; i0 += 256 * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * M)
+                        v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * M)
+                        X[i0 + u * 256] = v[u];
+            }
+            __syncthreads();
+        }
+        {
+            const int i = tid % M, tg = tid / M; // 256 / M groups of 16 frames = TT frames
+            const float2* col = X + (M - 1 - i) + (tg * 16) * M;
+            float2 acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                acc[j] = make_float2(0.f, 0.f);
+            if (P4T > 0) {
+                float hreg[P4T > 0 ? P4T : 1];
+#pragma unroll
+                for (int r = 0; r < P4T; r++)
+                    hreg[r] = hT[r * M + i];
+#pragma unroll
+                for (int rho = 0; rho < 16 + P4T - 1; rho++) {
+                    const float2 v = col[rho * M];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int r = j + P4T - 1 - rho;
+                        if (r >= 0 && r < P4T)
+                            acc[j] = __ffma2_rn(v, make_float2(hreg[r], hreg[r]), acc[j]);
+                    }
+                }
+            } else {
+                for (int rc = 0; rc < P4; rc += 4) {
+                    const float h0 = hT[(rc + 0) * M + i], h1 = hT[(rc + 1) * M + i];
+                    const float h2 = hT[(rc + 2) * M + i], h3 = hT[(rc + 3) * M + i];
+                    const float2* base = col + (P4 - 1 - rc - 3) * M;
+                    float2 w[19];
+#pragma unroll
+                    for (int q = 0; q < 19; q++)
+                        w[q] = base[q * M];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        acc[j] = __ffma2_rn(w[j + 3], make_float2(h0, h0), acc[j]);
+                        acc[j] = __ffma2_rn(w[j + 2], make_float2(h1, h1), acc[j]);
+                        acc[j] = __ffma2_rn(w[j + 1], make_float2(h2, h2), acc[j]);
+                        acc[j] = __ffma2_rn(w[j], make_float2(h3, h3), acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                U[i * US + tg * 16 + j] = acc[j];
+        }
+        __syncthreads(); // U complete; X fully consumed
+        {
+            const long long nxt = tile + gridDim.x;
+            if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
+                mbar_arrive_expect_tx(bar, tile_bytes);
+                bulk_copy_g2s(X, x + (nxt * TT - (P4 - 1)) * M, tile_bytes, bar);
+            }
+        }
+#pragma unroll 1
+        for (int fr = tid; fr < TT; fr += 256) {
+            float2 z[M];
+#pragma unroll
+            for (int i = 0; i < M; i++)
+                z[i] = U[i * US + fr];
+            if constexpr (M == 8)
+                idft8(z);
+            else
+                idft4(z[0], z[1], z[2], z[3]);
+            const long long f = f0 + fr;
+            if (f < n_frames) {
+                if (out16 && ch_begin == 0 && ch_count == M) {
+                    float4* y = reinterpret_cast<float4*>(out + f * M);
+#pragma unroll
+                    for (int c = 0; c < M; c += 2)
+                        __stcs(y + c / 2, make_float4(z[c].x, z[c].y, z[c + 1].x, z[c + 1].y));
+                } else {
+                    float2* y = out + f * ch_count - ch_begin;
+#pragma unroll
+                    for (int c = 0; c < M; c++)
+                        if (c >= ch_begin && c < ch_begin + ch_count)
+                            __stcs(y + c, z[c]);
+                }
+            }
+        }
+        __syncthreads(); // U free for the next tile's branch filters
+    }
+}
+
 // generic M (power of two, 4..256): straightforward shared-memory version
 __global__ void __launch_bounds__(256)
     pfb_generic_kernel(const float2* __restrict__ x, const float2* __restrict__ halo,
@@ -607,7 +748,7 @@ struct b200_pfb {
     size_t smem = 0;
     int TT = 0;
     int grid = 296;
-    int fusedM = 0; // M = 16 / 32 / 128 / 256 on the single-pass kernel (pfbm_kernel)
+    int fusedM = 0; // 1: M = 16 / 32 / 128 / 256 on pfbm_kernel; 2: M = 4 / 8 on pfbs_kernel (single pass both)
     // generic M >= 16: branch filters -> scratch -> the library's own reverse FFT of length M
     b200_fft* ifft = nullptr;
     float2* d_u = nullptr;    // [chunk_frames][M] branch outputs
@@ -637,6 +778,30 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         default: PFB64_GO(0); break;
         }
 #undef PFB64_GO
+    } else if (h->fusedM == 2) {
+        const int TT = 4096 / h->M;
+        long long tiles = (n_frames + TT - 1) / TT;
+        long long g = tiles < h->grid ? tiles : h->grid;
+#define PFBS_GO(MM, PT)                                                                               \
+    B200_LAUNCH((pfbs_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
+                (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
+                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), (int)((uintptr_t)d_out % 16 == 0))
+        if (h->M == 8) {
+            switch (h->P4) {
+            case 4: PFBS_GO(8, 4); break;
+            case 8: PFBS_GO(8, 8); break;
+            case 16: PFBS_GO(8, 16); break;
+            default: PFBS_GO(8, 0); break;
+            }
+        } else {
+            switch (h->P4) {
+            case 4: PFBS_GO(4, 4); break;
+            case 8: PFBS_GO(4, 8); break;
+            case 16: PFBS_GO(4, 16); break;
+            default: PFBS_GO(4, 0); break;
+            }
+        }
+#undef PFBS_GO
     } else if (h->fusedM) {
         const int TT = 4096 / h->M;
         long long tiles = (n_frames + TT - 1) / TT;
@@ -759,6 +924,24 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        h->grid = 2 * sm_count();
+    } else if ((M == 4 || M == 8) && !getenv("B200_PFB_TWOPASS") &&
+               sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)M * (4096 / M + 1)) +
+                       sizeof(float) * ((size_t)h->P4 * M + 1) + 16 <= 110 * 1024) {
+        h->fusedM = 2;
+        h->smem = sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)M * (4096 / M + 1)) +
+                  sizeof(float) * ((size_t)h->P4 * M + 1) + 16;
+#define PFBS_ATTR(MM)                                                                                          \
+    PFB_CUDA(cudaFuncSetAttribute(pfbs_kernel<MM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
+    PFB_CUDA(cudaFuncSetAttribute(pfbs_kernel<MM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
+    PFB_CUDA(cudaFuncSetAttribute(pfbs_kernel<MM, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
+    PFB_CUDA(cudaFuncSetAttribute(pfbs_kernel<MM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem))
+        if (M == 8) {
+            PFBS_ATTR(8);
+        } else {
+            PFBS_ATTR(4);
+        }
+#undef PFBS_ATTR
         h->grid = 2 * sm_count();
     } else if ((M == 16 || M == 32 || M == 128 || M == 256) && !getenv("B200_PFB_TWOPASS") &&
                sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)(4096 / M) * 17 * (M / 16)) +

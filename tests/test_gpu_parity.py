@@ -814,7 +814,7 @@ def test_pfb_golden(cuda, golden, name):
 
 
 @pytest.mark.parametrize("M,P", [(64, 16), (64, 3), (64, 32), (16, 8), (256, 4), (4, 7), (16, 16), (16, 5),
-                                 (32, 16), (32, 4), (128, 8), (128, 13), (256, 16), (8, 12)])
+                                 (32, 16), (32, 4), (128, 8), (128, 13), (256, 16), (8, 12), (8, 16), (8, 4), (4, 16), (4, 3)])
 def test_pfb_matches_oracle_and_streams(cuda, M, P):
     import scipy.signal as sig
     import newsched_b200 as nb
@@ -843,7 +843,7 @@ def test_pfb_matches_oracle_and_streams(cuda, M, P):
 def test_pfb_tone(cuda):
     import scipy.signal as sig
     import newsched_b200 as nb
-    for M, P, c0 in ((64, 16, 5), (16, 8, 3), (32, 8, 21), (128, 8, 77), (256, 4, 200)):
+    for M, P, c0 in ((64, 16, 5), (16, 8, 3), (32, 8, 21), (128, 8, 77), (256, 4, 200), (8, 16, 6), (4, 16, 1)):
         taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
         x = np.exp(2j * np.pi * c0 / M * np.arange(M * 600)).astype(np.complex64)
         y = host(nb.PfbChannelizer(taps, M).work(dev(cuda, x))[0])
@@ -875,7 +875,7 @@ def test_small_and_ragged_sizes_for_the_tiled_kernels(cuda):
             assert y.numel() == n * L and nc == n
             assert o.rel_rms(host(y), o.resample(x, taps, L, 1)) < TOL_RMS
     # single-pass channelizers: tiles of 4096 samples
-    for M, P in ((16, 8), (32, 4), (128, 8), (256, 4), (64, 16)):
+    for M, P in ((16, 8), (32, 4), (128, 8), (256, 4), (64, 16), (8, 8), (4, 16)):
         taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
         TT = 4096 // M
         for nf in (1, TT - 1, TT, TT + 1, 3 * TT + 2):
