@@ -161,6 +161,72 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // DECIM = false: D == 1 instantiation (TMA for interior tiles, register-staged loads for the few
 // edge tiles).  DECIM = true: decimating filters -- phase de-interleave with cp.async.  (Keeping
 // the cp.async path out of the D == 1 kernel is worth ~10 % on short filters: measured A/B.)
+// ---- decimation by ANY small D folded into the full-rate kernel (DG) --------------------------------
+// A thread owns D consecutive 16-sample rows of the input tile = exactly 16 outputs (one output row).
+// Row c of the thread starts at input 16 (D t + c), so its outputs sit at the compile-time positions
+// p0(c), p0(c) + D, ... with p0(c) = (-16 c) mod D, and they are the thread's outputs
+// off(c) .. off(c) + n(c) - 1 with off(c) = ceil(16 c / D): D passes of the register-window loop, each
+// over its own row window, accumulate disjoint slices of the SAME 16 accumulators, and the epilogue
+// (row per thread, one TMA store) is the full-rate one.  Same products as the phase-plane kernel, no
+// de-interleaving copies; the window loads per input sample equal those of the full-rate filter.
+template <int DG, int C>
+struct fir_dg {
+    static constexpr int P0 = (DG - (16 * C) % DG) % DG;
+    static constexpr int OFF_OUT = (16 * C + DG - 1) / DG;
+    static constexpr int N = (16 - P0 + DG - 1) / DG;
+};
+
+template <int CH, int OFF, int DG, int C>
+__device__ __forceinline__ void fir_step_dg(float (&acc)[FIR_ACC], const float (&W)[FIR_RING],
+                                            const float* __restrict__ hs)
+{
+    using G = fir_dg<DG, C>;
+#pragma unroll
+    for (int q4 = 0; q4 < CH; q4 += 4) {
+        float4 h4 = *reinterpret_cast<const float4*>(hs + q4);
+        const float hv[4] = { h4.x, h4.y, h4.z, h4.w };
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float2 h2 = make_float2(hv[u], hv[u]);
+#pragma unroll
+            for (int j = 0; j < G::N; j++) {
+                const int i = (OFF + (q4 + u + 1) * 2 + (G::P0 + j * DG) * 2) % FIR_RING;
+                const int l = (G::OFF_OUT + j) * 2;
+                float2 a = __ffma2_rn(make_float2(W[i], W[i + 1]), h2, make_float2(acc[l], acc[l + 1]));
+                acc[l] = a.x;
+                acc[l + 1] = a.y;
+            }
+        }
+    }
+}
+
+template <int HALF>
+__device__ __forceinline__ void fir_load_half(float (&W)[FIR_RING], const float* __restrict__ plane, int row);
+
+template <int DG, int C = 0>
+__device__ __forceinline__ void fir_passes_dg(float (&acc)[FIR_ACC], float (&W)[FIR_RING],
+                                              const float* __restrict__ plane, const float* __restrict__ hp,
+                                              int nsteps, int tid)
+{
+    if constexpr (C < DG) {
+        constexpr int CH = FIR_ACC / 2;
+        const int r0 = tid * DG + C;
+        fir_load_half<0>(W, plane, r0);
+        int b = 0;
+        for (; b + 1 < nsteps; b += 2) {
+            fir_load_half<1>(W, plane, r0 + b + 1);
+            fir_step_dg<CH, 0, DG, C>(acc, W, hp + b * CH);
+            fir_load_half<0>(W, plane, r0 + b + 2);
+            fir_step_dg<CH, 32, DG, C>(acc, W, hp + (b + 1) * CH);
+        }
+        if (b < nsteps) {
+            fir_load_half<1>(W, plane, r0 + b + 1);
+            fir_step_dg<CH, 0, DG, C>(acc, W, hp + b * CH);
+        }
+        fir_passes_dg<DG, C + 1>(acc, W, plane, hp, nsteps, tid);
+    }
+}
+
 // DD > 1 (with DECIM = false): decimation by a divisor of the 16 (32) window positions of a thread.
 // The tile is the SAME 2048-sample (4096 for fff) input tile as for D = 1, staged by the same single
 // TMA tensor load with the taps in natural order; a thread simply keeps accumulators only for the
@@ -178,7 +244,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // even / odd taps: two passes of the FFMA2 loop, i.e. half the issue slots of the scalar fff loop.
 // P0 is staged by the same TMA tensor load as a complex stream; P1 is derived from it in shared memory
 // (each thread shifts its own row by one float).
-template <int VEC, bool DECIM, int DD = 1, int LL = 1, bool RP = false>
+template <int VEC, bool DECIM, int DD = 1, int LL = 1, bool RP = false, int DG = 1>
 __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
@@ -187,8 +253,9 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
 {
     constexpr int R = FIR_ACC / VEC;  // window positions per thread (= outputs per thread for DD == 1)
     constexpr int CH = FIR_ACC / VEC; // taps per step
-    constexpr int MT = FIR_NT * R;    // input-rate positions per tile
-    constexpr int MTO = MT / DD;      // outputs per tile
+    constexpr int MT = FIR_NT * R * DG; // input-rate positions per tile
+    constexpr int MTO = MT / DD / DG;   // outputs per tile
+    static_assert(DG == 1 || (VEC == 2 && !DECIM && DD == 1 && LL == 1 && !RP), "DG: complex streams, own mode");
     static_assert(!DECIM || DD == 1, "DD applies to the TMA-staged full-rate kernel only");
     static_assert(R % DD == 0, "decimation must divide the positions per thread");
     static_assert(LL == 1 || (!DECIM && DD == 1), "LL applies to the TMA-staged full-rate kernel only");
@@ -389,6 +456,9 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         }
         return;
     }
+    if constexpr (DG > 1) {
+        fir_passes_dg<DG>(acc, W, planes, hs, nsteps, tid);
+    } else
     for (int p = 0; p < (RP ? 2 : D); p++) {
         const float* plane = planes + p * plane_f;
         const float* hp = hs + p * TQ;
@@ -538,6 +608,7 @@ struct b200_fir {
     int use_tma = 1;
     int rp = 0;      // real stream through the packed complex x real loop (fir_direct_kernel<..., RP>)
     int interp = 0;  // > 1: interpolation folded into the full-rate kernel (created by fir_interp_create)
+    int dg = 0;      // > 1: decimation by a non-divisor of 16 folded into the full-rate kernel (D rows per thread)
     int dd = 0;      // > 1: decimation folded into the TMA-staged full-rate kernel (geometry as for D = 1)
     ols_plan* ols = nullptr; // algorithm 3
     ffa_plan* ffa = nullptr; // algorithm 5
@@ -619,7 +690,7 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
             return set_err(B200_ERR_ARG, "fir: too many items for one call");
         fir_geom gm{};
         gm.Tm1 = h->T - 1;
-        gm.D = h->dd ? 1 : h->D;
+        gm.D = (h->dd || h->dg) ? 1 : h->D;
         gm.TQ = h->TQ;
         gm.plane_rows = h->plane_rows;
         gm.box_rows = h->box_rows;
@@ -630,7 +701,7 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         gm.tma_ok = 0;
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
-        if (h->use_tma && (h->D == 1 || h->dd) && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0) {
+        if (h->use_tma && (h->D == 1 || h->dd || h->dg) && gm.full_rows >= h->plane_rows && (uintptr_t)d_in % 16 == 0) {
             int rc = fir_make_tmap(&tmap, d_in, gm.full_rows, h->box_rows);
             if (rc != B200_OK)
                 return rc;
@@ -648,7 +719,18 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
             gm.tma_out_ok = 1;
         }
         const bool decim = h->D > 1;
-        if (h->dd) {
+        if (h->dg) {
+#define FIR_DG(DGV)                                                                                          \
+    B200_LAUNCH((fir_direct_kernel<2, false, 1, 1, false, DGV>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, \
+                y, h->d_taps_pp, tmap, tmap_out, gm, h->ep)
+            switch (h->dg) {
+            case 3: FIR_DG(3); break;
+            case 5: FIR_DG(5); break;
+            case 6: FIR_DG(6); break;
+            default: FIR_DG(7); break;
+            }
+#undef FIR_DG
+        } else if (h->dd) {
 #define FIR_DD(V, DDV)                                                                                     \
     B200_LAUNCH((fir_direct_kernel<V, false, DDV>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, y,     \
                 h->d_taps_pp, tmap, tmap_out, gm, h->ep)
@@ -853,12 +935,15 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     // decimations that divide the 16 (32) window positions of a thread run in the full-rate kernel
     if (h->D > 1 && (FIR_ACC / h->vec) % h->D == 0 && !getenv("B200_FIR_PLANES"))
         h->dd = h->D;
-    const int Dg = h->rp ? 2 : h->dd ? 1 : h->D; // phases the plane / tap geometry is built for
+    // ... and the other small decimations (3, 5, 6, 7) of complex streams with D rows per thread
+    if (!h->dd && h->vec == 2 && h->D > 1 && h->D <= 7 && !getenv("B200_FIR_PLANES"))
+        h->dg = h->D;
+    const int Dg = h->rp ? 2 : (h->dd || h->dg) ? 1 : h->D; // phases the plane / tap geometry is built for
     int tq = (h->T + Dg - 1) / Dg;
     h->TQ = (tq + CH - 1) / CH * CH; // whole 16- (32-) tap steps
     (void)MT;
     {
-        int need = FIR_NT + h->TQ / CH; // rows per plane: one per thread + one per tap step
+        int need = FIR_NT * (h->dg ? h->dg : 1) + h->TQ / CH; // rows per plane: per thread + one per tap step
         h->n_boxes = (need + 255) / 256;
         h->box_rows = (need + h->n_boxes - 1) / h->n_boxes;
         h->plane_rows = h->box_rows * h->n_boxes;
@@ -884,7 +969,12 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         const int cross = poly == 1 ? 40 : poly == 2 ? 64 : h->D == 1 ? 65 : 96;
         if (p->algorithm == 0 && can && h->T / h->D >= cross)
             want = true;
-        if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
+        if (p->algorithm == 0 && h->dg && can) {
+            // D = 3, 5, 6, 7 folded into the full-rate kernel with D rows per thread (tools/decim_ab.py,
+            // DS=3,5,6,7): 420-600 GS/s for short filters; overlap-save beyond 160 / 224 / 64 / 224 taps
+            const int tx = h->dg == 3 ? 160 : h->dg == 5 ? 224 : h->dg == 6 ? 64 : 224;
+            want = h->T > tx;
+        } else if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
             // decimations that cannot fold (tools/decim_ab.py with DS=3,5,6,7,10,12): the phase-plane kernel
             // stages with per-sample copies and sits at 150-290 GS/s; the polyphase overlap-save is flat at
             // 130-280.  Even D = 6, 10, 12, 14 (TMA-staged polyphase form): from 64 taps; D = 3, 5, 7: beyond 96 taps;
@@ -977,6 +1067,16 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     for (int i = 0; i < 2; i++) {
         FIR_CUDA(cudaMalloc(&h->d_hist[i], hb));
         FIR_CUDA(cudaMemset(h->d_hist[i], 0, hb));
+    }
+    if (h->algorithm == 1 && h->dg) {
+        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 3>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 5>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 6>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 7>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     if (h->algorithm == 1 && h->dd) {
 #define FIR_DD_ATTR(V, DDV) \

@@ -462,7 +462,9 @@ def test_fir_two_parallel_form(cuda, T, cplxin):
 
 @pytest.mark.parametrize("T,D,cplxin", [(16, 2, True), (64, 2, True), (96, 4, True), (160, 4, True), (33, 8, True),
                                         (192, 8, True), (64, 16, True), (384, 16, True), (64, 2, False),
-                                        (256, 4, False), (100, 8, False), (500, 16, False), (64, 32, False)])
+                                        (256, 4, False), (100, 8, False), (500, 16, False), (64, 32, False),
+                                        (64, 3, True), (17, 3, True), (200, 5, True), (96, 6, True), (48, 7, True),
+                                        (300, 7, True)])
 def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     """Decimations that divide a thread's window (2/4/8/16, 32 for fff) run in the TMA-staged
     full-rate kernel, which keeps accumulators only for every D-th position: bit-identical to the
@@ -471,7 +473,7 @@ def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     import os
     import newsched_b200 as nb
     rng = np.random.default_rng(T * 7 + D + cplxin)
-    n = 2048 * 37 + 1234
+    n = 2048 * 37 * (D if D in (3, 5, 6, 7) else 1) + 1234     # several tiles (2048 D inputs each for D = 3, 5, 6, 7)
     x = cplx(rng, n) if cplxin else rng.uniform(-1, 1, n).astype(np.float32)
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     dx = dev(cuda, x)
@@ -580,9 +582,11 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(np.ones(256, np.float32), 4).algorithm == 3    # polyphase overlap-save beyond 160 taps at D = 4
     assert nb.FirFilter(np.ones(128, np.float32), 4).algorithm == 1    # decimation folded into the full-rate kernel
     assert nb.FirFilter(np.ones(256, np.float32), 16).algorithm == 1
-    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # odd D: phase-plane kernel up to 96 taps
+    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # D = 3: folded kernel up to 160 taps
     assert nb.FirFilter(np.ones(64, np.float32), 3).algorithm == 1
-    assert nb.FirFilter(np.ones(64, np.float32), 6).algorithm == 3     # even D that cannot fold: polyphase overlap-save
+    assert nb.FirFilter(np.ones(64, np.float32), 6).algorithm == 1     # D = 3, 5, 6, 7 fold too (D rows per thread)
+    assert nb.FirFilter(np.ones(96, np.float32), 6).algorithm == 3
+    assert nb.FirFilter(np.ones(64, np.float32), 10).algorithm == 3    # even D that cannot fold: polyphase overlap-save
 
 
 def test_fir_empty_and_short(cuda):
