@@ -169,18 +169,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // over its own row window, accumulate disjoint slices of the SAME 16 accumulators, and the epilogue
 // (row per thread, one TMA store) is the full-rate one.  Same products as the phase-plane kernel, no
 // de-interleaving copies; the window loads per input sample equal those of the full-rate filter.
-template <int DG, int C>
+// threads per tile: D rows of 128 B per thread, so these kernels run 64-thread tiles (24-56 KB, 4-8 CTAs per
+// SM; with 128 threads D = 7 fits one CTA per SM: 64 taps 338 -> 492 GS/s, D = 5 471 -> 558, D = 3 476 -> 494)
+#ifndef B200_FIR_DG_SMALL
+#define B200_FIR_DG_SMALL 3
+#endif
+__host__ __device__ constexpr int fir_dg_nt(int dg) { return dg >= B200_FIR_DG_SMALL ? FIR_NT / 2 : FIR_NT; }
+
+template <int DG, int C, int R = 16> // R = samples per row: 16 complex, 32 real
 struct fir_dg {
-    static constexpr int P0 = (DG - (16 * C) % DG) % DG;
-    static constexpr int OFF_OUT = (16 * C + DG - 1) / DG;
-    static constexpr int N = (16 - P0 + DG - 1) / DG;
+    static constexpr int P0 = (DG - (R * C) % DG) % DG;
+    static constexpr int OFF_OUT = (R * C + DG - 1) / DG;
+    static constexpr int N = (R - P0 + DG - 1) / DG;
 };
 
-template <int CH, int OFF, int DG, int C>
+template <int VEC, int OFF, int DG, int C>
 __device__ __forceinline__ void fir_step_dg(float (&acc)[FIR_ACC], const float (&W)[FIR_RING],
                                             const float* __restrict__ hs)
 {
-    using G = fir_dg<DG, C>;
+    constexpr int CH = FIR_ACC / VEC;
+    using G = fir_dg<DG, C, CH>;
 #pragma unroll
     for (int q4 = 0; q4 < CH; q4 += 4) {
         float4 h4 = *reinterpret_cast<const float4*>(hs + q4);
@@ -190,11 +198,14 @@ __device__ __forceinline__ void fir_step_dg(float (&acc)[FIR_ACC], const float (
             const float2 h2 = make_float2(hv[u], hv[u]);
 #pragma unroll
             for (int j = 0; j < G::N; j++) {
-                const int i = (OFF + (q4 + u + 1) * 2 + (G::P0 + j * DG) * 2) % FIR_RING;
-                const int l = (G::OFF_OUT + j) * 2;
-                float2 a = __ffma2_rn(make_float2(W[i], W[i + 1]), h2, make_float2(acc[l], acc[l + 1]));
-                acc[l] = a.x;
-                acc[l + 1] = a.y;
+                const int i = (OFF + (q4 + u + 1 + G::P0 + j * DG) * VEC) % FIR_RING;
+                const int l = (G::OFF_OUT + j) * VEC;
+                if (VEC == 2) {
+                    float2 a = __ffma2_rn(make_float2(W[i], W[i + 1]), h2, make_float2(acc[l], acc[l + 1]));
+                    acc[l] = a.x;
+                    acc[l + 1] = a.y;
+                } else
+                    acc[l] = fmaf(hv[u], W[i], acc[l]);
             }
         }
     }
@@ -203,27 +214,27 @@ __device__ __forceinline__ void fir_step_dg(float (&acc)[FIR_ACC], const float (
 template <int HALF>
 __device__ __forceinline__ void fir_load_half(float (&W)[FIR_RING], const float* __restrict__ plane, int row);
 
-template <int DG, int C = 0>
+template <int VEC, int DG, int C = 0>
 __device__ __forceinline__ void fir_passes_dg(float (&acc)[FIR_ACC], float (&W)[FIR_RING],
                                               const float* __restrict__ plane, const float* __restrict__ hp,
                                               int nsteps, int tid)
 {
     if constexpr (C < DG) {
-        constexpr int CH = FIR_ACC / 2;
+        constexpr int CH = FIR_ACC / VEC;
         const int r0 = tid * DG + C;
         fir_load_half<0>(W, plane, r0);
         int b = 0;
         for (; b + 1 < nsteps; b += 2) {
             fir_load_half<1>(W, plane, r0 + b + 1);
-            fir_step_dg<CH, 0, DG, C>(acc, W, hp + b * CH);
+            fir_step_dg<VEC, 0, DG, C>(acc, W, hp + b * CH);
             fir_load_half<0>(W, plane, r0 + b + 2);
-            fir_step_dg<CH, 32, DG, C>(acc, W, hp + (b + 1) * CH);
+            fir_step_dg<VEC, 32, DG, C>(acc, W, hp + (b + 1) * CH);
         }
         if (b < nsteps) {
             fir_load_half<1>(W, plane, r0 + b + 1);
-            fir_step_dg<CH, 0, DG, C>(acc, W, hp + b * CH);
+            fir_step_dg<VEC, 0, DG, C>(acc, W, hp + b * CH);
         }
-        fir_passes_dg<DG, C + 1>(acc, W, plane, hp, nsteps, tid);
+        fir_passes_dg<VEC, DG, C + 1>(acc, W, plane, hp, nsteps, tid);
     }
 }
 
@@ -251,11 +262,12 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
                       const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
                       fir_geom gm, fir_epilogue ep)
 {
+    constexpr int NT = fir_dg_nt(DG);  // threads (= output rows) per tile
     constexpr int R = FIR_ACC / VEC;  // window positions per thread (= outputs per thread for DD == 1)
     constexpr int CH = FIR_ACC / VEC; // taps per step
-    constexpr int MT = FIR_NT * R * DG; // input-rate positions per tile
+    constexpr int MT = NT * R * DG; // input-rate positions per tile
     constexpr int MTO = MT / DD / DG;   // outputs per tile
-    static_assert(DG == 1 || (VEC == 2 && !DECIM && DD == 1 && LL == 1 && !RP), "DG: complex streams, own mode");
+    static_assert(DG == 1 || (!DECIM && DD == 1 && LL == 1 && !RP), "DG is a mode of its own");
     static_assert(!DECIM || DD == 1, "DD applies to the TMA-staged full-rate kernel only");
     static_assert(R % DD == 0, "decimation must divide the positions per thread");
     static_assert(LL == 1 || (!DECIM && DD == 1), "LL applies to the TMA-staged full-rate kernel only");
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
             tma_load_2d(planes + (size_t)bx * gm.box_rows * 32, &tmap, 0, (int)(row0 + (long long)bx * gm.box_rows),
                         bar);
     }
-    for (int i = tid; i < NTAPROWS * TQ; i += FIR_NT)
+    for (int i = tid; i < NTAPROWS * TQ; i += NT)
         hs[i] = __ldg(taps_pp + i);
     if (DECIM) {
         // decimating filters: every sample inside the input goes global -> shared with cp.async
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         // the history buffer
         const long long g_lo = B0 * D - (D - 1);
         const int total = PLs * D;
-        for (int i = tid; i < total; i += FIR_NT) {
+        for (int i = tid; i < total; i += NT) {
             const int e = i / D;
             const int p = D - 1 - (i - e * D);
             float* dst = planes + p * plane_f + swz(e * VEC);
@@ -329,11 +341,11 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         // D == 1 edge tiles / unaligned input: coalesced loads, 8 independent loads in flight
         const long long g_lo = B0;
         const int total = PLs;
-        for (int i0 = tid; i0 < total; i0 += FIR_NT * 8) {
+        for (int i0 = tid; i0 < total; i0 += NT * 8) {
             float v[8][2];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const int i = i0 + u * FIR_NT;
+                const int i = i0 + u * NT;
                 if (i < total) {
                     if (RP) { // pair g = floats 2g, 2g+1 of the real stream, each with its own bounds
                         float t0[2], t1_[2];
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const int i = i0 + u * FIR_NT;
+                const int i = i0 + u * NT;
                 if (i < total) {
                     float* dst = planes + swz(i * VEC);
                     if (VEC == 2)
@@ -366,7 +378,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         float first[2];
         fir_fetch<1>(x, hist, gm.Tm1, 2 * B0 - 1, gm.n_in_f, first); // the float in front of the tile
         float* P1 = planes + plane_f;
-        for (int r = tid; r < gm.plane_rows; r += FIR_NT) {
+        for (int r = tid; r < gm.plane_rows; r += NT) {
             const float* rb = planes + (r << 5);
             const int sw = (r & 7) << 2;
             float a[32];
@@ -394,7 +406,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     float W[FIR_RING];
     const int nsteps = TQ / CH; // any count >= 1: an odd tail step runs alone
     if (LL > 1) {
-        // output tile: LL * FIR_NT rows behind the input plane (1024-byte aligned for the TMA stores)
+        // output tile: LL * NT rows behind the input plane (1024-byte aligned for the TMA stores)
         float* otile = planes + (((gm.plane_rows << 5) + 255) & ~255);
 #pragma unroll 1
         for (int r = 0; r < LL; r++) {
@@ -424,8 +436,8 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
                     otile[swz(f)] = acc[pz];
             }
         }
-        const long long orow0 = tile * (FIR_NT * LL);
-        if (gm.tma_out_ok && orow0 + FIR_NT * LL <= gm.full_out_rows) {
+        const long long orow0 = tile * (NT * LL);
+        if (gm.tma_out_ok && orow0 + NT * LL <= gm.full_out_rows) {
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
@@ -433,8 +445,8 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
                 for (int r = 0; r < LL; r++)
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
                                      &tmap_out),
-                                 "r"(0), "r"((int)(orow0 + (long long)r * FIR_NT)),
-                                 "r"(smem_u32(otile + (size_t)r * FIR_NT * 32))
+                                 "r"(0), "r"((int)(orow0 + (long long)r * NT)),
+                                 "r"(smem_u32(otile + (size_t)r * NT * 32))
                                  : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -444,7 +456,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         __syncthreads();
         const long long OL = tile * (long long)(MT * LL);
 #pragma unroll 4
-        for (int i = tid; i < MT * LL; i += FIR_NT) {
+        for (int i = tid; i < MT * LL; i += NT) {
             const long long m = OL + i;
             if (m >= gm.n_out)
                 break;
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         return;
     }
     if constexpr (DG > 1) {
-        fir_passes_dg<DG>(acc, W, planes, hs, nsteps, tid);
+        fir_passes_dg<VEC, DG>(acc, W, planes, hs, nsteps, tid);
     } else
     for (int p = 0; p < (RP ? 2 : D); p++) {
         const float* plane = planes + p * plane_f;
@@ -521,8 +533,8 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
                 planes[swz(f0 + j)] = o[j];
         }
     }
-    const long long orow0 = tile * (FIR_NT / DD); // output rows per tile
-    if (FIR_NT / DD >= 8 && gm.tma_out_ok && orow0 + FIR_NT / DD <= gm.full_out_rows) {
+    const long long orow0 = tile * (NT / DD); // output rows per tile
+    if (NT / DD >= 8 && gm.tma_out_ok && orow0 + NT / DD <= gm.full_out_rows) {
         // whole tile inside the output: one TMA tensor store from the swizzled rows
         fence_proxy_async();
         __syncthreads();
@@ -538,7 +550,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     }
     __syncthreads();
 #pragma unroll 4
-    for (int i = tid; i < MTO; i += FIR_NT) {
+    for (int i = tid; i < MTO; i += NT) {
         const long long m = O0 + i;
         if (m >= gm.n_out)
             break;
@@ -684,7 +696,8 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         return B200_OK;
     }
     if (h->algorithm == 1) {
-        const int MT = FIR_NT * (FIR_ACC / h->vec) / (h->dd ? h->dd : 1); // outputs per tile
+        const int NTt = h->dg ? fir_dg_nt(h->dg) : FIR_NT;             // threads per tile
+        const int MT = NTt * (FIR_ACC / h->vec) / (h->dd ? h->dd : 1); // outputs per tile
         long long tiles = (n_out + MT - 1) / MT;
         if (tiles > 0x7fffffffLL)
             return set_err(B200_ERR_ARG, "fir: too many items for one call");
@@ -711,7 +724,7 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         memset(&tmap_out, 0, sizeof(tmap_out));
         gm.full_out_rows = n_out * h->vec / 32;
         gm.tma_out_ok = 0;
-        const int out_rows = FIR_NT / (h->dd ? h->dd : 1); // rows of the output tile
+        const int out_rows = NTt / (h->dd ? h->dd : 1); // rows of the output tile
         if (h->use_tma && out_rows >= 8 && gm.full_out_rows >= out_rows && (uintptr_t)d_out % 16 == 0) {
             int rc = fir_make_tmap(&tmap_out, d_out, gm.full_out_rows, out_rows);
             if (rc != B200_OK)
@@ -720,14 +733,23 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
         }
         const bool decim = h->D > 1;
         if (h->dg) {
-#define FIR_DG(DGV)                                                                                          \
-    B200_LAUNCH((fir_direct_kernel<2, false, 1, 1, false, DGV>), (unsigned)tiles, FIR_NT, h->smem, s, x, d_hist, \
+#define FIR_DG(V, DGV)                                                                                       \
+    B200_LAUNCH((fir_direct_kernel<V, false, 1, 1, false, DGV>), (unsigned)tiles, NTt, h->smem, s, x, d_hist, \
                 y, h->d_taps_pp, tmap, tmap_out, gm, h->ep)
-            switch (h->dg) {
-            case 3: FIR_DG(3); break;
-            case 5: FIR_DG(5); break;
-            case 6: FIR_DG(6); break;
-            default: FIR_DG(7); break;
+            if (h->vec == 2) {
+                switch (h->dg) {
+                case 3: FIR_DG(2, 3); break;
+                case 5: FIR_DG(2, 5); break;
+                case 6: FIR_DG(2, 6); break;
+                default: FIR_DG(2, 7); break;
+                }
+            } else {
+                switch (h->dg) {
+                case 3: FIR_DG(1, 3); break;
+                case 5: FIR_DG(1, 5); break;
+                case 6: FIR_DG(1, 6); break;
+                default: FIR_DG(1, 7); break;
+                }
             }
 #undef FIR_DG
         } else if (h->dd) {
@@ -935,15 +957,15 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     // decimations that divide the 16 (32) window positions of a thread run in the full-rate kernel
     if (h->D > 1 && (FIR_ACC / h->vec) % h->D == 0 && !getenv("B200_FIR_PLANES"))
         h->dd = h->D;
-    // ... and the other small decimations (3, 5, 6, 7) of complex streams with D rows per thread
-    if (!h->dd && h->vec == 2 && h->D > 1 && h->D <= 7 && !getenv("B200_FIR_PLANES"))
+    // ... and the other small decimations (3, 5, 6, 7) with D rows per thread
+    if (!h->dd && h->D > 1 && h->D <= 7 && !getenv("B200_FIR_PLANES"))
         h->dg = h->D;
     const int Dg = h->rp ? 2 : (h->dd || h->dg) ? 1 : h->D; // phases the plane / tap geometry is built for
     int tq = (h->T + Dg - 1) / Dg;
     h->TQ = (tq + CH - 1) / CH * CH; // whole 16- (32-) tap steps
     (void)MT;
     {
-        int need = FIR_NT * (h->dg ? h->dg : 1) + h->TQ / CH; // rows per plane: per thread + one per tap step
+        int need = (h->dg ? fir_dg_nt(h->dg) * h->dg : FIR_NT) + h->TQ / CH; // rows per plane: per thread + one per tap step
         h->n_boxes = (need + 255) / 256;
         h->box_rows = (need + h->n_boxes - 1) / h->n_boxes;
         h->plane_rows = h->box_rows * h->n_boxes;
@@ -971,8 +993,10 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
             want = true;
         if (p->algorithm == 0 && h->dg && can) {
             // D = 3, 5, 6, 7 folded into the full-rate kernel with D rows per thread (tools/decim_ab.py,
-            // DS=3,5,6,7): 420-600 GS/s for short filters; overlap-save beyond 160 / 224 / 64 / 224 taps
-            const int tx = h->dg == 3 ? 160 : h->dg == 5 ? 224 : h->dg == 6 ? 64 : 224;
+            // DS=3,5,6,7; tools/dg_ab.py): complex 510-670 GS/s at 32 taps, overlap-save beyond 160 / 256 /
+            // 64 / 256 taps; real 1.07-1.24 TS/s at 32 taps, overlap-save (~200 GS/s) beyond 256 / 512 / 480 / 576
+            const int tx = h->vec == 2 ? (h->dg == 3 ? 160 : h->dg == 5 ? 256 : h->dg == 6 ? 64 : 256)
+                                       : (h->dg == 3 ? 256 : h->dg == 5 ? 512 : h->dg == 6 ? 480 : 576);
             want = h->T > tx;
         } else if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
             // decimations that cannot fold (tools/decim_ab.py with DS=3,5,6,7,10,12): the phase-plane kernel
@@ -1069,14 +1093,18 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         FIR_CUDA(cudaMemset(h->d_hist[i], 0, hb));
     }
     if (h->algorithm == 1 && h->dg) {
-        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 3>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 5>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 6>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<2, false, 1, 1, false, 7>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define FIR_DG_ATTR(V, DGV)                                                                                   \
+    FIR_CUDA(cudaFuncSetAttribute(fir_direct_kernel<V, false, 1, 1, false, DGV>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+        FIR_DG_ATTR(2, 3);
+        FIR_DG_ATTR(2, 5);
+        FIR_DG_ATTR(2, 6);
+        FIR_DG_ATTR(2, 7);
+        FIR_DG_ATTR(1, 3);
+        FIR_DG_ATTR(1, 5);
+        FIR_DG_ATTR(1, 6);
+        FIR_DG_ATTR(1, 7);
+#undef FIR_DG_ATTR
     }
     if (h->algorithm == 1 && h->dd) {
 #define FIR_DD_ATTR(V, DDV) \

@@ -464,7 +464,8 @@ def test_fir_two_parallel_form(cuda, T, cplxin):
                                         (192, 8, True), (64, 16, True), (384, 16, True), (64, 2, False),
                                         (256, 4, False), (100, 8, False), (500, 16, False), (64, 32, False),
                                         (64, 3, True), (17, 3, True), (200, 5, True), (96, 6, True), (48, 7, True),
-                                        (300, 7, True)])
+                                        (300, 7, True), (64, 3, False), (33, 5, False), (200, 6, False),
+                                        (130, 7, False)])
 def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     """Decimations that divide a thread's window (2/4/8/16, 32 for fff) run in the TMA-staged
     full-rate kernel, which keeps accumulators only for every D-th position: bit-identical to the
