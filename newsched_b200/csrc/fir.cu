@@ -38,7 +38,10 @@ namespace b200 {
 #ifndef FIR_MINB
 #define FIR_MINB 6
 #endif
-constexpr int FIR_NT = 128;  // threads per CTA
+#ifndef B200_FIR_NT
+#define B200_FIR_NT 128
+#endif
+constexpr int FIR_NT = B200_FIR_NT; // threads per CTA
 constexpr int FIR_ACC = 32;  // fp32 accumulators per thread
 constexpr int FIR_RING = 64; // register window (floats)
 
@@ -175,6 +178,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 #define B200_FIR_DG_SMALL 3
 #endif
 __host__ __device__ constexpr int fir_dg_nt(int dg) { return dg >= B200_FIR_DG_SMALL ? FIR_NT / 2 : FIR_NT; }
+// Even D: the rows D t + k of the 8 lanes that share a shared-memory wavefront take only 8 / gcd(D, 8)
+// different values of (row & 7), i.e. of the 128-byte swizzle: a 2-way (D = 6) bank conflict on every
+// window load.  One unused row after every P = 8 / gcd(D, 8) threads' rows (P D rows, one TMA box each)
+// makes lanes t and t + P differ by 1 (mod 8): fir_dg_group = rows per group, 0 = no padding.
+#ifndef B200_FIR_DG_PAD
+#define B200_FIR_DG_PAD 1
+#endif
+// (Complex streams only: the scalar loop of a real stream is FMA-bound, and the padding costs it a
+// resident CTA per SM at 512+ taps -- measured 194 -> 168 GS/s.)
+__host__ __device__ constexpr int fir_dg_group(int dg, int vec)
+{
+    return (!B200_FIR_DG_PAD || vec != 2 || dg < 2 || dg % 2) ? 0 : (dg % 8 == 0 ? 1 : dg % 4 == 0 ? 2 : 4) * dg;
+}
+template <int GR>
+__device__ __forceinline__ int fir_prow(int r) { return GR ? r + r / GR : r; }
 
 template <int DG, int C, int R = 16> // R = samples per row: 16 complex, 32 real
 struct fir_dg {
@@ -221,17 +239,18 @@ __device__ __forceinline__ void fir_passes_dg(float (&acc)[FIR_ACC], float (&W)[
 {
     if constexpr (C < DG) {
         constexpr int CH = FIR_ACC / VEC;
+        constexpr int GR = fir_dg_group(DG, VEC);
         const int r0 = tid * DG + C;
-        fir_load_half<0>(W, plane, r0);
+        fir_load_half<0>(W, plane, fir_prow<GR>(r0));
         int b = 0;
         for (; b + 1 < nsteps; b += 2) {
-            fir_load_half<1>(W, plane, r0 + b + 1);
+            fir_load_half<1>(W, plane, fir_prow<GR>(r0 + b + 1));
             fir_step_dg<VEC, 0, DG, C>(acc, W, hp + b * CH);
-            fir_load_half<0>(W, plane, r0 + b + 2);
+            fir_load_half<0>(W, plane, fir_prow<GR>(r0 + b + 2));
             fir_step_dg<VEC, 32, DG, C>(acc, W, hp + (b + 1) * CH);
         }
         if (b < nsteps) {
-            fir_load_half<1>(W, plane, r0 + b + 1);
+            fir_load_half<1>(W, plane, fir_prow<GR>(r0 + b + 1));
             fir_step_dg<VEC, 0, DG, C>(acc, W, hp + b * CH);
         }
         fir_passes_dg<VEC, DG, C + 1>(acc, W, plane, hp, nsteps, tid);
@@ -290,7 +309,8 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
     const long long tile = blockIdx.x;
     const long long B0 = tile * MT - TQ; // x_p index of plane element 0
     const long long O0 = tile * MTO;     // first output of this tile
-    const int PLs = (gm.plane_rows << 5) / VEC;            // samples per plane
+    constexpr int GR = fir_dg_group(DG, VEC);              // DG, even D: one pad row per GR rows
+    const int PLs = ((gm.box_rows * gm.n_boxes) << 5) / VEC; // samples per plane
 
     // interior tile of a D == 1 filter: one TMA tensor copy stages the whole window
     const long long row0 = B0 * VEC / 32;
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         fence_mbar_init();
         mbar_arrive_expect_tx(bar, (uint32_t)(gm.box_rows * gm.n_boxes) * 128u);
         for (int bx = 0; bx < gm.n_boxes; bx++)
-            tma_load_2d(planes + (size_t)bx * gm.box_rows * 32, &tmap, 0, (int)(row0 + (long long)bx * gm.box_rows),
+            tma_load_2d(planes + (size_t)bx * (gm.box_rows + (GR ? 1 : 0)) * 32, &tmap, 0, (int)(row0 + (long long)bx * gm.box_rows),
                         bar);
     }
     for (int i = tid; i < NTAPROWS * TQ; i += NT)
@@ -361,7 +381,8 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
             for (int u = 0; u < 8; u++) {
                 const int i = i0 + u * NT;
                 if (i < total) {
-                    float* dst = planes + swz(i * VEC);
+                    const int fl = i * VEC;
+                    float* dst = planes + swz(GR ? (fir_prow<GR>(fl >> 5) << 5) | (fl & 31) : fl);
                     if (VEC == 2)
                         *reinterpret_cast<float2*>(dst) = make_float2(v[u][0], v[u][1]);
                     else
@@ -969,6 +990,11 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         h->n_boxes = (need + 255) / 256;
         h->box_rows = (need + h->n_boxes - 1) / h->n_boxes;
         h->plane_rows = h->box_rows * h->n_boxes;
+        if (const int gr = fir_dg_group(h->dg, h->vec)) { // padded layout: one TMA box per group, one spare row behind each
+            h->n_boxes = (need + gr - 1) / gr;
+            h->box_rows = gr;
+            h->plane_rows = h->n_boxes * (gr + 1);
+        }
     }
     h->smem = 16 + sizeof(float) * ((size_t)Dg * h->TQ + (size_t)Dg * (h->plane_rows * 32 + 8)) + 1024;
     if (const char* e = getenv("B200_FIR_TMA"))
@@ -994,8 +1020,8 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         if (p->algorithm == 0 && h->dg && can) {
             // D = 3, 5, 6, 7 folded into the full-rate kernel with D rows per thread (tools/decim_ab.py,
             // DS=3,5,6,7; tools/dg_ab.py): complex 510-670 GS/s at 32 taps, overlap-save beyond 160 / 256 /
-            // 64 / 256 taps; real 1.07-1.24 TS/s at 32 taps, overlap-save (~200 GS/s) beyond 256 / 512 / 480 / 576
-            const int tx = h->vec == 2 ? (h->dg == 3 ? 160 : h->dg == 5 ? 256 : h->dg == 6 ? 64 : 256)
+            // 96 / 256 taps; real 1.07-1.24 TS/s at 32 taps, overlap-save (~200 GS/s) beyond 256 / 512 / 480 / 576
+            const int tx = h->vec == 2 ? (h->dg == 3 ? 160 : h->dg == 5 ? 256 : h->dg == 6 ? 96 : 256)
                                        : (h->dg == 3 ? 256 : h->dg == 5 ? 512 : h->dg == 6 ? 480 : 576);
             want = h->T > tx;
         } else if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
