@@ -172,12 +172,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // over its own row window, accumulate disjoint slices of the SAME 16 accumulators, and the epilogue
 // (row per thread, one TMA store) is the full-rate one.  Same products as the phase-plane kernel, no
 // de-interleaving copies; the window loads per input sample equal those of the full-rate filter.
-// threads per tile: D rows of 128 B per thread, so these kernels run 64-thread tiles (24-56 KB, 4-8 CTAs per
-// SM; with 128 threads D = 7 fits one CTA per SM: 64 taps 338 -> 492 GS/s, D = 5 471 -> 558, D = 3 476 -> 494)
+// threads per tile: D rows of 128 B per thread, so these kernels run 64-thread tiles (32 threads from D = 9;
+// 24-60 KB, 3-8 CTAs per SM; with 128 threads D = 7 fits one CTA per SM: 64 taps 338 -> 492 GS/s, D = 5 471 -> 558, D = 3 476 -> 494)
 #ifndef B200_FIR_DG_SMALL
 #define B200_FIR_DG_SMALL 3
 #endif
-__host__ __device__ constexpr int fir_dg_nt(int dg) { return dg >= B200_FIR_DG_SMALL ? FIR_NT / 2 : FIR_NT; }
+__host__ __device__ constexpr int fir_dg_nt(int dg) { return dg >= 9 ? FIR_NT / 4 : dg >= B200_FIR_DG_SMALL ? FIR_NT / 2 : FIR_NT; }
 // Even D: the rows D t + k of the 8 lanes that share a shared-memory wavefront take only 8 / gcd(D, 8)
 // different values of (row & 7), i.e. of the 128-byte swizzle: a 2-way (D = 6) bank conflict on every
 // window load.  One unused row after every P = 8 / gcd(D, 8) threads' rows (P D rows, one TMA box each)
@@ -185,11 +185,17 @@ __host__ __device__ constexpr int fir_dg_nt(int dg) { return dg >= B200_FIR_DG_S
 #ifndef B200_FIR_DG_PAD
 #define B200_FIR_DG_PAD 1
 #endif
-// (Complex streams only: the scalar loop of a real stream is FMA-bound, and the padding costs it a
-// resident CTA per SM at 512+ taps -- measured 194 -> 168 GS/s.)
+#ifndef B200_FIR_DG_PAD_REAL
+#define B200_FIR_DG_PAD_REAL 9 // real streams: pad multiples of 4 from this D on (i.e. D = 12)
+#endif
+// (Real streams: only D = 12, where the conflict is 4-way -- 32 taps 671 -> 835 GS/s; the 2-way cases are
+// FMA-bound in the scalar loop and the padding costs them a resident CTA per SM: D = 6 at 512 taps
+// 194 -> 168, D = 10 at 32 taps 1017 -> 870.)
 __host__ __device__ constexpr int fir_dg_group(int dg, int vec)
 {
-    return (!B200_FIR_DG_PAD || vec != 2 || dg < 2 || dg % 2) ? 0 : (dg % 8 == 0 ? 1 : dg % 4 == 0 ? 2 : 4) * dg;
+    return (!B200_FIR_DG_PAD || (vec != 2 && (dg < B200_FIR_DG_PAD_REAL || dg % 4)) || dg < 2 || dg % 2)
+               ? 0
+               : (dg % 8 == 0 ? 1 : dg % 4 == 0 ? 2 : 4) * dg;
 }
 template <int GR>
 __device__ __forceinline__ int fir_prow(int r) { return GR ? r + r / GR : r; }
@@ -757,21 +763,26 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
 #define FIR_DG(V, DGV)                                                                                       \
     B200_LAUNCH((fir_direct_kernel<V, false, 1, 1, false, DGV>), (unsigned)tiles, NTt, h->smem, s, x, d_hist, \
                 y, h->d_taps_pp, tmap, tmap_out, gm, h->ep)
+#define FIR_DG_ALL(V)                                                                                        \
+    switch (h->dg) {                                                                                         \
+    case 3: FIR_DG(V, 3); break;                                                                             \
+    case 5: FIR_DG(V, 5); break;                                                                             \
+    case 6: FIR_DG(V, 6); break;                                                                             \
+    case 7: FIR_DG(V, 7); break;                                                                             \
+    case 9: FIR_DG(V, 9); break;                                                                             \
+    case 10: FIR_DG(V, 10); break;                                                                           \
+    case 11: FIR_DG(V, 11); break;                                                                           \
+    case 12: FIR_DG(V, 12); break;                                                                           \
+    case 13: FIR_DG(V, 13); break;                                                                           \
+    case 14: FIR_DG(V, 14); break;                                                                           \
+    default: FIR_DG(V, 15); break;                                                                           \
+    }
             if (h->vec == 2) {
-                switch (h->dg) {
-                case 3: FIR_DG(2, 3); break;
-                case 5: FIR_DG(2, 5); break;
-                case 6: FIR_DG(2, 6); break;
-                default: FIR_DG(2, 7); break;
-                }
+                FIR_DG_ALL(2);
             } else {
-                switch (h->dg) {
-                case 3: FIR_DG(1, 3); break;
-                case 5: FIR_DG(1, 5); break;
-                case 6: FIR_DG(1, 6); break;
-                default: FIR_DG(1, 7); break;
-                }
+                FIR_DG_ALL(1);
             }
+#undef FIR_DG_ALL
 #undef FIR_DG
         } else if (h->dd) {
 #define FIR_DD(V, DDV)                                                                                     \
@@ -978,8 +989,8 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     // decimations that divide the 16 (32) window positions of a thread run in the full-rate kernel
     if (h->D > 1 && (FIR_ACC / h->vec) % h->D == 0 && !getenv("B200_FIR_PLANES"))
         h->dd = h->D;
-    // ... and the other small decimations (3, 5, 6, 7) with D rows per thread
-    if (!h->dd && h->D > 1 && h->D <= 7 && !getenv("B200_FIR_PLANES"))
+    // ... and the other decimations up to 15 (3, 5, 6, 7, 9 ... 15) with D rows per thread
+    if (!h->dd && h->D > 1 && h->D <= (getenv("B200_FIR_DG_MAX") ? atoi(getenv("B200_FIR_DG_MAX")) : 15) && !getenv("B200_FIR_PLANES"))
         h->dg = h->D;
     const int Dg = h->rp ? 2 : (h->dd || h->dg) ? 1 : h->D; // phases the plane / tap geometry is built for
     int tq = (h->T + Dg - 1) / Dg;
@@ -1018,14 +1029,15 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         if (p->algorithm == 0 && can && h->T / h->D >= cross)
             want = true;
         if (p->algorithm == 0 && h->dg && can) {
-            // D = 3, 5, 6, 7 folded into the full-rate kernel with D rows per thread (tools/decim_ab.py,
-            // DS=3,5,6,7; tools/dg_ab.py): complex 510-670 GS/s at 32 taps, overlap-save beyond 160 / 256 /
-            // 96 / 256 taps; real 1.07-1.24 TS/s at 32 taps, overlap-save (~200 GS/s) beyond 256 / 512 / 480 / 576
-            const int tx = h->vec == 2 ? (h->dg == 3 ? 160 : h->dg == 5 ? 256 : h->dg == 6 ? 96 : 256)
-                                       : (h->dg == 3 ? 256 : h->dg == 5 ? 512 : h->dg == 6 ? 480 : 576);
+            // D = 3, 5, 6, 7, 9 ... 15 folded into the full-rate kernel with D rows per thread (tools/decim_ab.py
+            // with DS=..., tools/dg_ab.py): complex 400-670 GS/s at 32 taps against 93-280 for overlap-save, real
+            // 0.67-1.24 TS/s against ~200; its cost grows with T, overlap-save is flat: measured crossovers (taps)
+            static const short tx_c[16] = { 0, 0, 0, 160, 0, 256, 96, 256, 0, 320, 128, 384, 160, 384, 160, 448 };
+            static const short tx_r[16] = { 0, 0, 0, 256, 0, 512, 480, 576, 0, 640, 448, 640, 448, 512, 416, 576 };
+            const int tx = (h->vec == 2 ? tx_c : tx_r)[h->dg];
             want = h->T > tx;
         } else if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {
-            // decimations that cannot fold (tools/decim_ab.py with DS=3,5,6,7,10,12): the phase-plane kernel
+            // decimations that do not fold (beyond 15, or B200_FIR_PLANES / B200_FIR_DG_MAX set): the phase-plane kernel
             // stages with per-sample copies and sits at 150-290 GS/s; the polyphase overlap-save is flat at
             // 130-280.  Even D = 6, 10, 12, 14 (TMA-staged polyphase form): from 64 taps; D = 3, 5, 7: beyond 96 taps;
             // larger D: from 192 taps, and whenever the phase planes would not fit shared memory
@@ -1126,10 +1138,24 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         FIR_DG_ATTR(2, 5);
         FIR_DG_ATTR(2, 6);
         FIR_DG_ATTR(2, 7);
+        FIR_DG_ATTR(2, 9);
+        FIR_DG_ATTR(2, 10);
+        FIR_DG_ATTR(2, 11);
+        FIR_DG_ATTR(2, 12);
+        FIR_DG_ATTR(2, 13);
+        FIR_DG_ATTR(2, 14);
+        FIR_DG_ATTR(2, 15);
         FIR_DG_ATTR(1, 3);
         FIR_DG_ATTR(1, 5);
         FIR_DG_ATTR(1, 6);
         FIR_DG_ATTR(1, 7);
+        FIR_DG_ATTR(1, 9);
+        FIR_DG_ATTR(1, 10);
+        FIR_DG_ATTR(1, 11);
+        FIR_DG_ATTR(1, 12);
+        FIR_DG_ATTR(1, 13);
+        FIR_DG_ATTR(1, 14);
+        FIR_DG_ATTR(1, 15);
 #undef FIR_DG_ATTR
     }
     if (h->algorithm == 1 && h->dd) {

@@ -465,7 +465,8 @@ def test_fir_two_parallel_form(cuda, T, cplxin):
                                         (256, 4, False), (100, 8, False), (500, 16, False), (64, 32, False),
                                         (64, 3, True), (17, 3, True), (200, 5, True), (96, 6, True), (48, 7, True),
                                         (300, 7, True), (64, 3, False), (33, 5, False), (200, 6, False),
-                                        (130, 7, False)])
+                                        (130, 7, False), (40, 9, True), (64, 12, True), (100, 15, True),
+                                        (33, 10, True), (64, 10, False), (90, 13, False), (48, 14, True)])
 def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     """Decimations that divide a thread's window (2/4/8/16, 32 for fff) run in the TMA-staged
     full-rate kernel, which keeps accumulators only for every D-th position: bit-identical to the
@@ -474,7 +475,7 @@ def test_fir_decimation_folded_into_full_rate_kernel(cuda, T, D, cplxin):
     import os
     import newsched_b200 as nb
     rng = np.random.default_rng(T * 7 + D + cplxin)
-    n = 2048 * 37 * (D if D in (3, 5, 6, 7) else 1) + 1234     # several tiles (2048 D inputs each for D = 3, 5, 6, 7)
+    n = 1024 * 37 * (D if 32 % D else 1) + 1234     # several tiles (1024 D or 512 D inputs each for non-divisors of 16 / 32)
     x = cplx(rng, n) if cplxin else rng.uniform(-1, 1, n).astype(np.float32)
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     dx = dev(cuda, x)
@@ -586,8 +587,11 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # D = 3: folded kernel up to 160 taps
     assert nb.FirFilter(np.ones(64, np.float32), 3).algorithm == 1
     assert nb.FirFilter(np.ones(64, np.float32), 6).algorithm == 1     # D = 3, 5, 6, 7 fold too (D rows per thread)
-    assert nb.FirFilter(np.ones(96, np.float32), 6).algorithm == 3
-    assert nb.FirFilter(np.ones(64, np.float32), 10).algorithm == 3    # even D that cannot fold: polyphase overlap-save
+    assert nb.FirFilter(np.ones(128, np.float32), 6).algorithm == 3
+    assert nb.FirFilter(np.ones(64, np.float32), 10).algorithm == 1    # ... and 9 ... 15
+    assert nb.FirFilter(np.ones(192, np.float32), 10).algorithm == 3
+    assert nb.FirFilter(np.ones(512, np.float32), 11, is_complex=False).algorithm == 1   # real streams fold further out
+    assert nb.FirFilter(np.ones(1024, np.float32), 11, is_complex=False).algorithm == 3
 
 
 def test_fir_empty_and_short(cuda):
