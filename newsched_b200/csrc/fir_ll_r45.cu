@@ -1,0 +1,4 @@
+#define FIR_TU_VEC 1
+#define FIR_TU_NAME(f) f##_r45
+#define FIR_LL_EACH(X) X(4, 1) X(4, 3) X(4, 5) X(5, 3)
+#include "fir_ll.inc"

@@ -243,7 +243,7 @@ struct b200_resampler {
     float* d_taps_pp = nullptr;
     float* d_hist[2] = { nullptr, nullptr };
     int cur = 0;
-    b200_fir* fold = nullptr; // D == 1, L <= 4: interpolation folded into the TMA-staged direct FIR kernel
+    b200_fir* fold = nullptr; // L <= 4 (D == 1) or coprime L, D <= 5: folded into the TMA-staged direct FIR kernel
     int rb_R = 0;   // > 0: register-blocked kernel with R outputs per thread
     int rb_tpt = 0; // its active threads per CTA (multiple of L)
     size_t rb_smem = 0;
@@ -388,8 +388,8 @@ int b200_resampler_create(const b200_resampler_params* p, b200_resampler** out)
     RS_ATTR(1, 3, 6);
     RS_ATTR(1, 4, 3);
 #undef RS_ATTR
-    if (h->D == 1 && fir_interp_supported(h->T, h->L, h->vec == 2)) {
-        int rc = fir_interp_create(p->taps, h->T, h->L, h->vec == 2, &h->fold);
+    if (fir_interp_supported(h->T, h->L, h->D, h->vec == 2)) {
+        int rc = fir_interp_create(p->taps, h->T, h->L, h->D, h->vec == 2, &h->fold);
         if (rc != B200_OK) {
             b200_resampler_destroy(h);
             return rc;

@@ -350,7 +350,11 @@ def test_fir_overlap_save_real_stream(cuda, T, D):
                                           (7, 1, 3, True), (33, 5, 5, False), (3, 7, 2, True),
                                           (1024, 16, 1, True), (2048, 4, 3, True), (256, 2, 9, False),
                                           (96, 3, 64, True), (64, 2, 1, True), (100, 3, 1, False),
-                                          (33, 4, 1, False), (2000, 4, 1, True), (5, 3, 1, True)])
+                                          (33, 4, 1, False), (2000, 4, 1, True), (5, 3, 1, True),
+                                          (96, 3, 2, True), (70, 2, 3, True), (320, 5, 4, True), (97, 4, 5, True),
+                                          (64, 5, 3, True), (150, 3, 5, True), (40, 4, 3, True), (200, 3, 4, True),
+                                          (31, 5, 2, True), (77, 2, 5, True), (96, 3, 2, False), (130, 2, 3, False),
+                                          (400, 5, 4, False), (65, 4, 5, False), (90, 3, 4, False)])
 def test_resampler_matches_oracle(cuda, T, L, D, cplxin):
     """interp_fir_filter (D = 1) / rational_resampler against the fp64 oracle; streaming in ragged
     chunks (history on the device) and time segments with a halo are bit-identical to one shot."""
