@@ -247,20 +247,26 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
 namespace b200 {
 
 // (L, M) pairs the rational fold is instantiated for, and from how many taps per phase it beats the
-// register-blocked resampler kernel (tools/resampler_sweep.py with RATIOS=1, out rate fold vs kernel at 16 / 64
-// taps per phase): the decimating ratios always (2/5: 97 vs 54, 54 vs 25 GS/s; 3/5: 104 vs 67, 55 vs 26;
-// 4/5: 95 vs 76, 42 vs 27; 3/4: 121 vs 117, 57 vs 43), 4/3 and 5/3 once the phases are long (4/3: 146 vs 169,
-// 75 vs 62; 5/3: 159 vs 171, 77 vs 62).  3/2, 2/3, 5/2 and 5/4 measured 3-40 % slower than the kernel (their
-// L x 64-row output tile leaves 3-4 two-warp CTAs per SM) and are not built.
+// register-blocked resampler kernel (tools/resampler_sweep.py with RATIOS=1 and B200_RATIONAL_MINTQ=1 against
+// B200_RATIONAL_RB=1; TFLOP/s fold vs kernel at 16 / 32 / 64 taps per phase): 3/2 17.7 / 28.7 / 41.6 vs 15.4 /
+// 24.7 / 32.9, 2/3 15.5 / 25.4 / 37.2 vs 11.4 / 18.3 / 24.4, 4/3 12.5 / 20.4 / 28.4 vs 10.8 / 14.3 / 15.8,
+// 3/4 10.5 / 17.1 / 24.7 vs 7.4 / 10.0 / 11.0, 4/5 6.6 / 11.5 / 17.6 vs 4.9 / 6.4 / 6.9, 5/3 14.8 / 23.4 / 30.4
+// vs 10.9 / 14.2 / 15.8, 3/5 9.1 / 15.9 / 23.9 vs 4.3 / 6.1 / 6.7, 2/5 7.9 / 13.7 / 21.8 vs 3.5 / 5.4 / 6.4;
+// 5/4 only from long phases (8.8 / 14.3 / 20.9 vs 10.7 / 15.1 / 18.4); 5/2 never (16.3 / 25.6 / 30.5 vs
+// 16.6 / 25.8 / 33.5: its 5 x 64-row output tile leaves 3 two-warp CTAs per SM).
 static int fir_ratio_min_tq(int L, int M)
 {
     switch (L * 8 + M) {
+    case 2 * 8 + 3:
     case 2 * 8 + 5:
+    case 3 * 8 + 2:
     case 3 * 8 + 4:
     case 3 * 8 + 5:
-    case 4 * 8 + 5: return 1;
     case 4 * 8 + 3:
-    case 5 * 8 + 3: return 40;
+    case 4 * 8 + 5:
+    case 5 * 8 + 3: return 1;
+    case 5 * 8 + 4: return 48;
+    case 5 * 8 + 2: return 1 << 20; // (built, selectable with B200_RATIONAL_MINTQ)
     }
     return 0; // not built
 }
@@ -272,7 +278,9 @@ bool fir_interp_supported(int T, int L, int M, int is_complex)
     const int vec = is_complex ? 2 : 1, CH = FIR_ACC / vec;
     const int TQ = ((T + L - 1) / L + CH - 1) / CH * CH;
     if (M > 1) {
-        const int mq = fir_ratio_min_tq(L, M);
+        int mq = fir_ratio_min_tq(L, M);
+        if (const char* e = getenv("B200_RATIONAL_MINTQ")) // (measurement: fold from this many taps per phase)
+            mq = mq > 0 ? atoi(e) : 0;
         return mq > 0 && (T + L - 1) / L >= mq && TQ / CH <= 64 && !getenv("B200_RATIONAL_RB");
     }
     if (L < 2 || L > 4)
@@ -458,10 +466,10 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
             want = true;
         if (p->algorithm == 0 && h->dg && can) {
             // D = 3, 5, 6, 7, 9 ... 15 folded into the full-rate kernel with D rows per thread (tools/decim_ab.py
-            // with DS=..., tools/dg_ab.py): complex 400-670 GS/s at 32 taps against 93-280 for overlap-save, real
-            // 0.67-1.24 TS/s against ~200; its cost grows with T, overlap-save is flat: measured crossovers (taps)
-            static const short tx_c[16] = { 0, 0, 0, 160, 0, 256, 96, 256, 0, 320, 128, 384, 160, 384, 160, 448 };
-            static const short tx_r[16] = { 0, 0, 0, 256, 0, 512, 480, 576, 0, 640, 448, 640, 448, 512, 416, 576 };
+            // with DS=..., tools/dg_ab.py): complex 400-660 GS/s at 32 taps against 93-280 for overlap-save, real
+            // 0.83-1.25 TS/s against ~200; its cost grows with T, overlap-save is flat: measured crossovers (taps)
+            static const short tx_c[16] = { 0, 0, 0, 208, 0, 304, 176, 368, 0, 448, 208, 544, 288, 448, 224, 512 };
+            static const short tx_r[16] = { 0, 0, 0, 352, 0, 608, 608, 640, 0, 640, 576, 640, 480, 448, 448, 512 };
             const int tx = (h->vec == 2 ? tx_c : tx_r)[h->dg];
             want = h->T > tx;
         } else if (p->algorithm == 0 && !h->dd && h->vec == 2 && h->D > 1 && can) {

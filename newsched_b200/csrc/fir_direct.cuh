@@ -249,6 +249,60 @@ __device__ __forceinline__ void fir_passes_dg(float (&acc)[FIR_ACC], float (&W)[
     }
 }
 
+// Row-major order of the same work: the D passes of a thread re-read each other's rows (pass c, step b needs
+// rows c + b and c + b + 1: D (nsteps + 1) row loads for D + nsteps distinct rows).  Walking the rows once
+// and running, for row rho, the step b = rho - c of every pass c that has one, loads each row exactly once
+// (D = 5, 64 taps: 25 -> 9 row loads per thread; these kernels are LSU-bound, profiles/r01_firdec64d5).  Every
+// accumulator still sees its taps in the same order, so the results are bit-identical.
+#ifndef B200_FIR_DG_ROWS
+#define B200_FIR_DG_ROWS 1
+#endif
+template <int VEC, int OFF, int DG, int S, int C = 0>
+__device__ __forceinline__ void fir_row_steps(float (&acc)[FIR_ACC], const float (&W)[FIR_RING],
+                                              const float* __restrict__ hp, int rho, int nsteps)
+{
+    if constexpr (C < DG) {
+        constexpr int CH = FIR_ACC / VEC;
+        const int b = rho - C;
+        if (b >= 0 && b < nsteps)
+            fir_step_dg<VEC, OFF, DG, C, S>(acc, W, hp + b * CH);
+        fir_row_steps<VEC, OFF, DG, S, C + 1>(acc, W, hp, rho, nsteps);
+    }
+}
+
+template <int VEC, int DG, int S = 0>
+__device__ __forceinline__ void fir_rows_dg(float (&acc)[FIR_ACC], float (&W)[FIR_RING],
+                                            const float* __restrict__ plane, const float* __restrict__ hp,
+                                            int nsteps, int tid)
+{
+#if B200_FIR_DG_ROWS
+    // the row walk tests DG guards per row: with few steps and many passes that costs more than the repeated
+    // loads (complex D = 15, 32 taps: 465 -> 393 GS/s; real D = 12, 32 taps: 835 -> 737), so short filters at
+    // large D keep the pass-major order
+    if (DG > 6 && 2 * nsteps < DG - 4) {
+        fir_passes_dg<VEC, DG, 0, S>(acc, W, plane, hp, nsteps, tid);
+        return;
+    }
+    constexpr int GR = fir_dg_group(DG, VEC);
+    const int r0 = tid * DG;
+    const int nrows = DG - 1 + nsteps;
+    fir_load_half<0>(W, plane, fir_prow<GR>(r0));
+    int rho = 0;
+    for (; rho + 1 < nrows; rho += 2) {
+        fir_load_half<1>(W, plane, fir_prow<GR>(r0 + rho + 1));
+        fir_row_steps<VEC, 0, DG, S>(acc, W, hp, rho, nsteps);
+        fir_load_half<0>(W, plane, fir_prow<GR>(r0 + rho + 2));
+        fir_row_steps<VEC, 32, DG, S>(acc, W, hp, rho + 1, nsteps);
+    }
+    if (rho < nrows) {
+        fir_load_half<1>(W, plane, fir_prow<GR>(r0 + rho + 1));
+        fir_row_steps<VEC, 0, DG, S>(acc, W, hp, rho, nsteps);
+    }
+#else
+    fir_passes_dg<VEC, DG, 0, S>(acc, W, plane, hp, nsteps, tid);
+#endif
+}
+
 // Rational resampling by LL / DG (LL and DG coprime) = both folds at once.  Output m = LL n + r is
 //   y[LL n + r] = sum_q h[q LL + (r DG) mod LL] x[DG n + floor(r DG / LL) - q],
 // a decimate-by-DG filter with the taps of phase (r DG) mod LL whose input is shifted by S_r = floor(r DG / LL):
@@ -264,7 +318,7 @@ __device__ __forceinline__ void fir_passes_ll_dg(float (&acc)[FIR_ACC], float (&
 #pragma unroll
         for (int l = 0; l < FIR_ACC; l++)
             acc[l] = 0.f;
-        fir_passes_dg<VEC, DG, 0, (RR * DG) / LL>(acc, W, plane, hs + RR * TQ, nsteps, tid);
+        fir_rows_dg<VEC, DG, (RR * DG) / LL>(acc, W, plane, hs + RR * TQ, nsteps, tid);
 #pragma unroll
         for (int pz = 0; pz < R; pz++) {
             const int f = ((tid * R + pz) * LL + RR) * VEC;
@@ -295,7 +349,7 @@ __device__ __forceinline__ void fir_passes_ll_dg(float (&acc)[FIR_ACC], float (&
 // P0 is staged by the same TMA tensor load as a complex stream; P1 is derived from it in shared memory
 // (each thread shifts its own row by one float).
 template <int VEC, bool DECIM, int DD = 1, int LL = 1, bool RP = false, int DG = 1>
-__global__ void __launch_bounds__(FIR_NT, FIR_MINB)
+__global__ void __launch_bounds__(fir_tile_nt(LL, DG), (LL > 1 && DG > 1) ? 4 : DG > 1 ? 8 : FIR_MINB) // (DG: 1-2 warp CTAs)
     fir_direct_kernel(const float* __restrict__ x, const float* __restrict__ hist,
                       float* __restrict__ y, const float* __restrict__ taps_pp,
                       const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
@@ -513,7 +567,7 @@ __global__ void __launch_bounds__(FIR_NT, FIR_MINB)
         return;
     }
     if constexpr (DG > 1) {
-        fir_passes_dg<VEC, DG>(acc, W, planes, hs, nsteps, tid);
+        fir_rows_dg<VEC, DG>(acc, W, planes, hs, nsteps, tid);
     } else
     for (int p = 0; p < (RP ? 2 : D); p++) {
         const float* plane = planes + p * plane_f;

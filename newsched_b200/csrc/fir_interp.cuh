@@ -5,8 +5,8 @@
 
 struct b200_fir;
 namespace b200 {
-// decimation == 1: interpolators (L = 2, 3, 4); decimation > 1: the rational ratios 2/5, 3/4, 3/5, 4/5 and,
-// for long phases, 4/3 and 5/3
+// decimation == 1: interpolators (L = 2, 3, 4); decimation > 1: the rational ratios with coprime L, M <= 5
+// (5/4 for long phases only, 5/2 never: see fir_ratio_min_tq)
 // (L passes x M rows per thread, see fir_passes_ll_dg in fir.cu)
 bool fir_interp_supported(int n_taps, int interpolation, int decimation, int is_complex);
 // handle without history buffers: the caller passes the ceil(T/L)-1 samples of history per launch

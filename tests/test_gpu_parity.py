@@ -588,12 +588,12 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(np.ones(256, np.float32), 4).algorithm == 3    # polyphase overlap-save beyond 160 taps at D = 4
     assert nb.FirFilter(np.ones(128, np.float32), 4).algorithm == 1    # decimation folded into the full-rate kernel
     assert nb.FirFilter(np.ones(256, np.float32), 16).algorithm == 1
-    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # D = 3: folded kernel up to 160 taps
+    assert nb.FirFilter(np.ones(300, np.float32), 3).algorithm == 3    # D = 3: folded kernel up to 208 taps
     assert nb.FirFilter(np.ones(64, np.float32), 3).algorithm == 1
     assert nb.FirFilter(np.ones(64, np.float32), 6).algorithm == 1     # D = 3, 5, 6, 7 fold too (D rows per thread)
-    assert nb.FirFilter(np.ones(128, np.float32), 6).algorithm == 3
+    assert nb.FirFilter(np.ones(256, np.float32), 6).algorithm == 3
     assert nb.FirFilter(np.ones(64, np.float32), 10).algorithm == 1    # ... and 9 ... 15
-    assert nb.FirFilter(np.ones(192, np.float32), 10).algorithm == 3
+    assert nb.FirFilter(np.ones(256, np.float32), 10).algorithm == 3
     assert nb.FirFilter(np.ones(512, np.float32), 11, is_complex=False).algorithm == 1   # real streams fold further out
     assert nb.FirFilter(np.ones(1024, np.float32), 11, is_complex=False).algorithm == 3
 
