@@ -254,8 +254,27 @@ namespace b200 {
 // vs 10.9 / 14.2 / 15.8, 3/5 9.1 / 15.9 / 23.9 vs 4.3 / 6.1 / 6.7, 2/5 7.9 / 13.7 / 21.8 vs 3.5 / 5.4 / 6.4;
 // 5/4 only from long phases (8.8 / 14.3 / 20.9 vs 10.7 / 15.1 / 18.4); 5/2 never (16.3 / 25.6 / 30.5 vs
 // 16.6 / 25.8 / 33.5: its 5 x 64-row output tile leaves 3 two-warp CTAs per SM).
-static int fir_ratio_min_tq(int L, int M)
+// Real streams (32 samples per row, scalar FMAs): the register-blocked kernel is the faster one except for
+// the strongly decimating ratios (out GS/s fold vs kernel at 16 / 32 / 64 taps per phase: 2/5 137 / 136 / 113 vs
+// 111 / 75 / 43, 3/5 121 / 122 / 97 vs 124 / 80 / 44, 4/5 74 / 74 / 58 vs 135 / 83 / 45, 2/3 218 / 220 / 162 vs
+// 257 / 212 / 147; 5/3 136 vs 311, 4/3 141 vs 284 at 16).
+static int fir_ratio_min_tq(int L, int M, int is_complex)
 {
+    if (!is_complex) {
+        switch (L * 8 + M) {
+        case 2 * 8 + 5: return 1;
+        case 3 * 8 + 5:
+        case 2 * 8 + 3: return 32;
+        case 4 * 8 + 5: return 64;
+        case 3 * 8 + 2:
+        case 3 * 8 + 4:
+        case 4 * 8 + 3:
+        case 5 * 8 + 2:
+        case 5 * 8 + 3:
+        case 5 * 8 + 4: return 1 << 20;
+        }
+        return 0;
+    }
     switch (L * 8 + M) {
     case 2 * 8 + 3:
     case 2 * 8 + 5:
@@ -278,7 +297,7 @@ bool fir_interp_supported(int T, int L, int M, int is_complex)
     const int vec = is_complex ? 2 : 1, CH = FIR_ACC / vec;
     const int TQ = ((T + L - 1) / L + CH - 1) / CH * CH;
     if (M > 1) {
-        int mq = fir_ratio_min_tq(L, M);
+        int mq = fir_ratio_min_tq(L, M, is_complex);
         if (const char* e = getenv("B200_RATIONAL_MINTQ")) // (measurement: fold from this many taps per phase)
             mq = mq > 0 ? atoi(e) : 0;
         return mq > 0 && (T + L - 1) / L >= mq && TQ / CH <= 64 && !getenv("B200_RATIONAL_RB");

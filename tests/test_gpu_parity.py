@@ -354,7 +354,8 @@ def test_fir_overlap_save_real_stream(cuda, T, D):
                                           (96, 3, 2, True), (70, 2, 3, True), (320, 5, 4, True), (97, 4, 5, True),
                                           (64, 5, 3, True), (150, 3, 5, True), (40, 4, 3, True), (200, 3, 4, True),
                                           (31, 5, 2, True), (77, 2, 5, True), (96, 3, 2, False), (130, 2, 3, False),
-                                          (400, 5, 4, False), (65, 4, 5, False), (90, 3, 4, False)])
+                                          (400, 5, 4, False), (65, 4, 5, False), (90, 3, 4, False), (77, 2, 5, False),
+                                          (200, 3, 5, False), (300, 4, 5, False)])
 def test_resampler_matches_oracle(cuda, T, L, D, cplxin):
     """interp_fir_filter (D = 1) / rational_resampler against the fp64 oracle; streaming in ragged
     chunks (history on the device) and time segments with a halo are bit-identical to one shot."""
@@ -387,6 +388,32 @@ def test_resampler_matches_oracle(cuda, T, L, D, cplxin):
         halo = None if (g == 0 or nh == 0) else dx[lo - nh:lo]
         parts.append(host(r.work_segment(dx[lo:hi], halo)))
     assert np.array_equal(np.concatenate(parts), one), "time segments + halo != one stream"
+
+
+@pytest.mark.parametrize("cplxin", [True, False])
+def test_rational_fold_every_built_ratio(cuda, cplxin, monkeypatch):
+    """Every (L, M) the folded rational kernel is instantiated for, forced on (the automatic choice leaves
+    some ratios on the register-blocked kernel): against the fp64 oracle, and ragged chunks == one shot."""
+    import newsched_b200 as nb
+    monkeypatch.setenv("B200_RATIONAL_MINTQ", "1")
+    rng = np.random.default_rng(77 + cplxin)
+    n = 64 * 16 * 5 * 7 + 321
+    x = cplx(rng, n) if cplxin else rng.uniform(-1, 1, n).astype(np.float32)
+    dx = dev(cuda, x)
+    for L, D in ((3, 2), (2, 3), (4, 3), (3, 4), (5, 4), (4, 5), (5, 3), (3, 5), (5, 2), (2, 5)):
+        for T in (L * 7 + 1, L * 40):
+            taps = (rng.uniform(-1, 1, T) * (L / T)).astype(np.float32)
+            r = nb.RationalResampler(taps, L, D, is_complex=cplxin)
+            y, nc = r.work(dx)
+            assert y.numel() == (n // D) * L and nc == (n // D) * D
+            assert o.rel_rms(host(y), o.resample(x, taps, L, D)) < TOL_RMS, (L, D, T)
+            r2 = nb.RationalResampler(taps, L, D, is_complex=cplxin)
+            outs, pos = [], 0
+            for chunk in (4099, D, 10 ** 9):
+                yy, c = r2.work(dx[pos:min(pos + max(chunk, D), n)])
+                outs.append(host(yy))
+                pos += c
+            assert np.array_equal(np.concatenate(outs), host(y)), (L, D, T)
 
 
 def test_interp_fir_impulse_exact_and_empty(cuda):
