@@ -307,7 +307,7 @@ bool fir_interp_supported(int T, int L, int M, int is_complex)
     // measured against the register-blocked resampler kernel (tools/resampler_sweep.py): +22..47 % for
     // L = 2, 3 at any length; at L = 4 the 64 KiB output tile leaves 2 CTAs per SM and short phases lose
     // (128 taps: 230 vs 259 GS/s out), so L = 4 folds only once the phases are FMA-bound
-    if (L == 4 && T < 192)
+    if (L == 4 && T < (getenv("B200_INTERP_L4_MIN") ? atoi(getenv("B200_INTERP_L4_MIN")) : 192))
         return false;
     return TQ / CH <= 64;
 }

@@ -184,7 +184,14 @@ template <int GR>
 __device__ __forceinline__ int fir_prow(int r) { return GR ? r + r / GR : r; }
 
 // S (rational resampling, 0 <= S < DG): the thread's output j reads the input DG j + S instead of DG j.
-__host__ __device__ constexpr int fir_tile_nt(int ll, int dg) { return ll > 1 && dg > 1 ? FIR_NT / 2 : fir_dg_nt(dg); }
+#ifndef B200_FIR_LL4_NT
+#define B200_FIR_LL4_NT (FIR_NT / 2) // threads per tile of the interpolate-by-4 fold (64: 41 KB, 5 CTAs per SM;
+                                     // 192 taps 190 -> 213 GS/s out against 128-thread tiles, same from 256)
+#endif
+__host__ __device__ constexpr int fir_tile_nt(int ll, int dg)
+{
+    return ll > 1 && dg > 1 ? FIR_NT / 2 : ll >= 4 ? B200_FIR_LL4_NT : fir_dg_nt(dg);
+}
 
 template <int DG, int C, int R = 16, int S = 0> // R = samples per row: 16 complex, 32 real
 struct fir_dg {

@@ -1,5 +1,5 @@
 """Runs one hot-path kernel a few times on synthetic data (for ncu captures / launch lists).
-usage: python tools/prof_one.py fftmag|fft|fftnN|fir64|firdec64d4|firdec64d5|fir1024d4|fir4096|ffa64|pfb|pfb16|copy [reps]"""
+usage: python tools/prof_one.py fftmag|fft|fftnN|fir64|firdec64d4|firdec64d5|rs32|fir1024d4|fir4096|ffa64|pfb|pfb16|copy [reps]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -33,6 +33,8 @@ elif what == "firdec64d4":
 elif what == "firdec64d5":
     n = N * 32768 // 5 * 5; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
     op = nb.FirFilter((rng.uniform(-1, 1, 64) / 64).astype(np.float32), 5); out = torch.empty(n // 5, dtype=torch.complex64, device="cuda"); fn = lambda: op.work_segment(x, None, out)
+elif what == "rs32":
+    op = nb.RationalResampler((rng.uniform(-1, 1, 192) / 64).astype(np.float32), 3, 2); out = torch.empty(n // 2 * 3, dtype=torch.complex64, device="cuda"); fn = lambda: op.work_segment(x, None, out)
 elif what == "pfb16":
     import scipy.signal as sig
     n = N * 32768; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)

@@ -9,7 +9,7 @@ CPLX = os.environ.get("REAL", "0") != "1"
 xc = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1) if CPLX else torch.rand(n, device="cuda", generator=g) * 2 - 1
 rng = np.random.default_rng(1)
 fp32, _ = nb.measure_fp32_tflops(8192)
-for T, L, D in [(32, 2, 1), (64, 2, 1), (128, 2, 1), (256, 2, 1), (48, 3, 1), (96, 3, 1), (192, 3, 1), (128, 4, 1), (256, 8, 1), (96, 3, 2), (320, 5, 4), (1024, 16, 1), (128, 2, 3)] if 'RATIOS' not in os.environ else [(T * L, L, D) for (L, D) in ((3, 2), (2, 3), (4, 3), (3, 4), (5, 4), (4, 5), (5, 3), (3, 5), (5, 2), (2, 5)) for T in (16, 32, 64)]:
+for T, L, D in [(32, 2, 1), (64, 2, 1), (128, 2, 1), (256, 2, 1), (48, 3, 1), (96, 3, 1), (192, 3, 1), (128, 4, 1), (256, 8, 1), (96, 3, 2), (320, 5, 4), (1024, 16, 1), (128, 2, 3)] if 'RATIOS' not in os.environ and 'L4' not in os.environ else [(T, 4, 1) for T in (32, 64, 128, 192, 256, 512)] if 'L4' in os.environ else [(T * L, L, D) for (L, D) in ((3, 2), (2, 3), (4, 3), (3, 4), (5, 4), (4, 5), (5, 3), (3, 5), (5, 2), (2, 5)) for T in (16, 32, 64)]:
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     r = nb.RationalResampler(taps, L, D, is_complex=CPLX)
     out = torch.empty((n // D) * L, dtype=xc.dtype, device="cuda")
