@@ -6,7 +6,7 @@
  * plain pointers and sizes (device pointers unless the name says `_host`), returns an int
  * status (0 = ok, < 0 = error, text via b200_last_error()), never allocates or
  * synchronises inside a `_run` call, and launches on the caller's stream.  The host-side
- * C++17 block wrappers (include/gnuradio/blocklib/b200/ *.hpp) and the Python mirror
+ * C++17 block wrappers (include/gnuradio/blocklib/cuda/ *.hpp) and the Python mirror
  * (newsched_b200/) are thin shims over exactly these symbols.
  *
  * Each op lists the reference interface it stands behind:
@@ -84,6 +84,27 @@ B200_API int b200_event_synchronize(b200_event_t e);
 B200_API int b200_event_query(b200_event_t e);             /* 0 = complete, 1 = not yet, <0 error */
 B200_API int b200_event_elapsed_ms(b200_event_t start, b200_event_t stop, float* ms);
 
+/* ---- peer memory (time-segment sharding needs the (ntaps-1)-sample halo that precedes
+ * a GPU's segment, which lives at the end of the left neighbour's segment).  Instead of exchanging it,
+ * the neighbour's buffer is mapped into this GPU's address space and the FIR / channelizer kernels read
+ * the halo straight over NVLink (`d_halo` of the *_run_segment calls may be such a pointer).
+ * One process, several devices: b200_enable_peer_access(peer) on the current device.
+ * One process per device: export a handle for any pointer inside a cudaMalloc allocation, ship the
+ * 88 bytes to the other process (any host channel), import it there.  The reference has no multi-device
+ * concept; its edges are created per flowgraph in one process,
+ * schedulers/mt/lib/buffer_management.cpp:78-82. */
+typedef struct {
+    unsigned char bytes[64]; /* cudaIpcMemHandle_t of the allocation */
+    uint64_t offset;         /* of the exported pointer inside the allocation */
+    uint64_t size;           /* of the allocation */
+    int32_t device;          /* exporting device ordinal (as that process numbers it) */
+    int32_t reserved;
+} b200_ipc_handle;
+B200_API int b200_enable_peer_access(int peer_device);
+B200_API int b200_ipc_export(const void* dptr, b200_ipc_handle* out);
+B200_API int b200_ipc_import(const b200_ipc_handle* h, void** dptr);
+B200_API int b200_ipc_close(const b200_ipc_handle* h, void* dptr);
+
 /* ---- device-resident doubly mapped ring (replaces gr::cuda_buffer, cudabuffer.cu:17-183)
  * One physical allocation of `size` bytes mapped twice back to back with the CUDA VMM API,
  * so base[i] and base[i + size] alias: any window of <= size bytes starting anywhere in
@@ -132,7 +153,7 @@ typedef struct {
     int32_t is_complex;   /* 1 = ccf, 0 = fff */
     int32_t fuse_multiply_const; /* 0/1 */
     float k_re, k_im;     /* epilogue constant (k_im ignored for fff) */
-    int32_t algorithm;    /* 0 = auto, 1 = direct SIMT, 2 = reserved (tensor-core), 3 = overlap-save FFT,
+    int32_t algorithm;    /* 0 = auto, 1 = direct SIMT, 2 = block-Toeplitz GEMM on the tensor cores (tcgen05; ccf, D <= 8), 3 = overlap-save FFT,
                              4 = one thread per output (fallback), 5 = 2-parallel fast FIR (decimation 1) */
 } b200_fir_params;
 B200_API int b200_fir_create(const b200_fir_params* p, b200_fir** h);

@@ -15,7 +15,8 @@ import subprocess
 
 __all__ = [
     "lib", "build", "B200Error", "copy", "multiply_const", "multiply", "add", "complex_to_mag", "FirFilter", "FFT",
-    "PfbChannelizer", "Chain", "DeviceRing", "launch_count", "LIB_PATH",
+    "PfbChannelizer", "Chain", "DeviceRing", "launch_count", "LIB_PATH", "IpcHandle", "ipc_export", "ipc_import",
+    "ipc_close",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -62,6 +63,12 @@ class _PfbParams(C.Structure):
                 ("channel_count", C.c_int32)]
 
 
+class IpcHandle(C.Structure):
+    """b200_ipc_handle: 88 plain bytes, shipped between processes over any host channel."""
+    _fields_ = [("bytes", C.c_ubyte * 64), ("offset", C.c_uint64), ("size", C.c_uint64),
+                ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
 class _ChainOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("handle", C.c_void_p), ("k_re", C.c_float), ("k_im", C.c_float)]
 
@@ -101,6 +108,10 @@ SIGNATURES = {
     "b200_event_synchronize": (_I, [_V]),
     "b200_event_query": (_I, [_V]),
     "b200_event_elapsed_ms": (_I, [_V, _V, C.POINTER(_F)]),
+    "b200_enable_peer_access": (_I, [_I]),
+    "b200_ipc_export": (_I, [_V, C.POINTER(IpcHandle)]),
+    "b200_ipc_import": (_I, [C.POINTER(IpcHandle), C.POINTER(_V)]),
+    "b200_ipc_close": (_I, [C.POINTER(IpcHandle), _V]),
     "b200_ring_create": (_I, [_SZ, C.POINTER(_V)]),
     "b200_ring_destroy": (_I, [_V]),
     "b200_ring_base": (_V, [_V]),
@@ -206,6 +217,51 @@ def _need_cuda(x):
         raise B200Error("tensor must be contiguous")
 
 
+def _need_out(out, like, numel, dtype=None, what="out"):
+    """A caller-supplied output (or halo) goes straight to the kernels as a raw pointer: refuse anything
+    that is not a contiguous CUDA tensor of the right dtype / device / size."""
+    if not out.is_cuda or out.device != like.device:
+        raise B200Error(f"{what} must be a CUDA tensor on {like.device}")
+    if not out.is_contiguous():
+        raise B200Error(f"{what} must be contiguous")
+    if out.dtype != (dtype if dtype is not None else like.dtype):
+        raise B200Error(f"{what} has dtype {out.dtype}, expected {dtype if dtype is not None else like.dtype}")
+    if out.numel() < numel:
+        raise B200Error(f"{what} has {out.numel()} items, needs {numel}")
+
+
+def _halo_ptr(halo, like, numel):
+    """halo: None (zeros), a CUDA tensor, or a raw device pointer (int) -- e.g. a peer-mapped address."""
+    if halo is None:
+        return None
+    if isinstance(halo, int):
+        return halo
+    _need_out(halo, like, numel, what="halo")
+    return halo.data_ptr()
+
+
+def ipc_export(t) -> bytes:
+    """Handle (88 bytes) for the memory of CUDA tensor `t`, importable by another process on the same node."""
+    _need_cuda(t)
+    h = IpcHandle()
+    _check(lib().b200_ipc_export(t.data_ptr(), C.byref(h)))
+    return bytes(h)
+
+
+def ipc_import(raw: bytes) -> int:
+    """Maps an exported allocation into this process; returns the device pointer (an int) that aliases the
+    exporter's tensor.  Kernels of this GPU read it over NVLink."""
+    h = IpcHandle.from_buffer_copy(raw)
+    p = C.c_void_p()
+    _check(lib().b200_ipc_import(C.byref(h), C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(raw: bytes, ptr: int) -> None:
+    h = IpcHandle.from_buffer_copy(raw)
+    _check(lib().b200_ipc_close(C.byref(h), C.c_void_p(ptr)))
+
+
 def _floats(a):
     import numpy as np
     arr = np.ascontiguousarray(a, dtype=np.float32)
@@ -295,6 +351,7 @@ class FirFilter:
         _check(lib().b200_fir_create(C.byref(p), C.byref(h)))
         self._h = h
         self.n_taps, self.decimation, self.is_complex = arr.size, int(decimation), bool(is_complex)
+        self.device = _torch().cuda.current_device()     # the handle's buffers live on the device current at create
 
     @property
     def handle(self):
@@ -316,6 +373,8 @@ class FirFilter:
         n_out = x.numel() // self.decimation
         if out is None:
             out = torch.empty(n_out, dtype=x.dtype, device=x.device)
+        else:
+            _need_out(out, x, n_out)
         nc, npd = C.c_int64(), C.c_int64()
         _check(lib().b200_fir_run(self._h, x.data_ptr(), out.data_ptr(), x.numel(), C.byref(nc),
                                   C.byref(npd), _stream(stream)))
@@ -324,11 +383,14 @@ class FirFilter:
     def work_segment(self, x, halo=None, out=None, stream=None):
         torch = _torch()
         _need_cuda(x)
+        assert x.dtype == self._dtype()
         n_out = x.numel() // self.decimation
         if out is None:
             out = torch.empty(n_out, dtype=x.dtype, device=x.device)
+        else:
+            _need_out(out, x, n_out)
         npd = C.c_int64()
-        _check(lib().b200_fir_run_segment(self._h, halo.data_ptr() if halo is not None else None,
+        _check(lib().b200_fir_run_segment(self._h, _halo_ptr(halo, x, self.n_taps - 1),
                                           x.data_ptr(), out.data_ptr(), x.numel(), C.byref(npd),
                                           _stream(stream)))
         return out[: npd.value]
@@ -342,7 +404,7 @@ class FirFilter:
 
     def get_history(self, stream=None):
         torch = _torch()
-        out = torch.empty(max(self.n_taps - 1, 0), dtype=self._dtype(), device="cuda")
+        out = torch.empty(max(self.n_taps - 1, 0), dtype=self._dtype(), device=torch.device("cuda", self.device))
         if self.n_taps > 1:
             _check(lib().b200_fir_get_history(self._h, out.data_ptr(), _stream(stream)))
         return out
@@ -386,6 +448,8 @@ class FFT:
         if out is None:
             dt = torch.complex64 if self.output == OUT_COMPLEX else torch.float32
             out = torch.empty(n_vec * self.n, dtype=dt, device=x.device)
+        else:
+            _need_out(out, x, n_vec * self.n, torch.complex64 if self.output == OUT_COMPLEX else torch.float32)
         _check(lib().b200_fft_run(self._h, x.data_ptr(), out.data_ptr(), n_vec, _stream(stream)))
         return out
 
@@ -426,6 +490,8 @@ class RationalResampler:
         assert x.dtype == (torch.complex64 if self.is_complex else torch.float32)
         if out is None:
             out = torch.empty(self._n_out(x.numel()), dtype=x.dtype, device=x.device)
+        else:
+            _need_out(out, x, self._n_out(x.numel()))
         nc, npd = C.c_int64(), C.c_int64()
         _check(lib().b200_resampler_run(self._h, x.data_ptr(), out.data_ptr(), x.numel(), C.byref(nc),
                                         C.byref(npd), _stream(stream)))
@@ -434,10 +500,14 @@ class RationalResampler:
     def work_segment(self, x, halo=None, out=None, stream=None):
         torch = _torch()
         _need_cuda(x)
+        assert x.dtype == (torch.complex64 if self.is_complex else torch.float32)
         if out is None:
             out = torch.empty(self._n_out(x.numel()), dtype=x.dtype, device=x.device)
+        else:
+            _need_out(out, x, self._n_out(x.numel()))
         npd = C.c_int64()
-        _check(lib().b200_resampler_run_segment(self._h, halo.data_ptr() if halo is not None else None,
+        _check(lib().b200_resampler_run_segment(self._h,
+                                                _halo_ptr(halo, x, -(-self.n_taps // self.interpolation) - 1),
                                                 x.data_ptr(), out.data_ptr(), x.numel(), C.byref(npd),
                                                 _stream(stream)))
         return out[: npd.value]
@@ -475,9 +545,12 @@ class PfbChannelizer:
     def work(self, x, out=None, stream=None):
         torch = _torch()
         _need_cuda(x)
+        assert x.dtype == torch.complex64
         n_t = x.numel() // self.m
         if out is None:
             out = torch.empty((n_t, self.channels), dtype=torch.complex64, device=x.device)
+        else:
+            _need_out(out, x, n_t * self.channels)
         nc, nv = C.c_int64(), C.c_int64()
         _check(lib().b200_pfb_run(self._h, x.data_ptr(), out.data_ptr(), x.numel(), C.byref(nc),
                                   C.byref(nv), _stream(stream)))
@@ -485,11 +558,15 @@ class PfbChannelizer:
 
     def work_segment(self, x, halo=None, out=None, stream=None):
         torch = _torch()
+        _need_cuda(x)
+        assert x.dtype == torch.complex64
         n_t = x.numel() // self.m
         if out is None:
             out = torch.empty((n_t, self.channels), dtype=torch.complex64, device=x.device)
+        else:
+            _need_out(out, x, n_t * self.channels)
         nv = C.c_int64()
-        _check(lib().b200_pfb_run_segment(self._h, halo.data_ptr() if halo is not None else None,
+        _check(lib().b200_pfb_run_segment(self._h, _halo_ptr(halo, x, (self.p - 1) * self.m),
                                           x.data_ptr(), out.data_ptr(), x.numel(), C.byref(nv),
                                           _stream(stream)))
         return out[: nv.value]
@@ -545,7 +622,10 @@ class Chain:
     def run(self, x, out, stream=None) -> int:
         """Device-resident pass; `out` is a uint8/any CUDA tensor big enough.  Returns bytes written."""
         _need_cuda(x)
+        _need_cuda(out)
         n_items = x.numel() * x.element_size() // self.in_item_bytes
+        if out.device != x.device or out.numel() * out.element_size() < self.out_bytes(n_items):
+            raise B200Error(f"Chain.run: out must be on {x.device} with >= {self.out_bytes(n_items)} bytes")
         nb = C.c_int64()
         _check(lib().b200_chain_run(self._h, x.data_ptr(), out.data_ptr(), n_items, C.byref(nb),
                                     _stream(stream)))
@@ -556,6 +636,9 @@ class Chain:
         if x_host.is_cuda or out_host.is_cuda:
             raise B200Error("run_host takes host (pinned) tensors")
         n_items = x_host.numel() * x_host.element_size() // self.in_item_bytes
+        if not (x_host.is_contiguous() and out_host.is_contiguous()) or \
+                out_host.numel() * out_host.element_size() < self.out_bytes(n_items):
+            raise B200Error(f"Chain.run_host: contiguous host tensors, out >= {self.out_bytes(n_items)} bytes")
         nb = C.c_int64()
         _check(lib().b200_chain_run_host(self._h, x_host.data_ptr(), out_host.data_ptr(), n_items,
                                          C.byref(nb)))

@@ -81,6 +81,7 @@ struct b200_fir {
     int dg = 0;      // > 1: decimation by a non-divisor of 16 folded into the full-rate kernel (D rows per thread)
     int dd = 0;      // > 1: decimation folded into the TMA-staged full-rate kernel (geometry as for D = 1)
     ols_plan* ols = nullptr; // algorithm 3
+    tc_plan* tc = nullptr;   // algorithm 2
     ffa_plan* ffa = nullptr; // algorithm 5
     int algorithm = 1;
     fir_epilogue ep{ 0, 1.f, 0.f };
@@ -118,6 +119,8 @@ static int fir_launch(b200_fir* h, const float* d_hist, const void* d_in, void* 
     float* y = (float*)d_out;
     if (h->algorithm == 3)
         return ols_launch(h->ols, d_hist, d_in, d_out, n_in, n_out, s);
+    if (h->algorithm == 2)
+        return tc_launch(h->tc, d_hist, d_in, d_out, n_in, n_out, s);
     if (h->algorithm == 5)
         return ffa_launch(h->ffa, d_hist, d_in, d_out, n_in, n_out, s);
     if (h->algorithm == 1 && h->rp) {
@@ -415,6 +418,7 @@ int b200_fir_destroy(b200_fir* h)
     cudaFree(h->d_hist[0]);
     cudaFree(h->d_hist[1]);
     ols_destroy(h->ols);
+    tc_destroy(h->tc);
     ffa_destroy(h->ffa);
     delete h;
     return B200_OK;
@@ -427,8 +431,9 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     *out = nullptr;
     if (!p->taps || p->n_taps < 1 || p->decimation < 1)
         return set_err(B200_ERR_ARG, "fir_create: need n_taps >= 1, decimation >= 1, taps != NULL");
-    if (p->algorithm == 2)
-        return set_err(B200_ERR_UNSUPPORTED, "fir_create: tensor-core algorithm not built yet");
+    if (p->algorithm == 2 && !tc_supported(p->n_taps, p->decimation, !p->is_complex))
+        return set_err(B200_ERR_UNSUPPORTED,
+                       "fir_create: the tensor-core form needs a complex stream, decimation 1..8, <= 2048 taps per branch");
     b200_fir* h = new b200_fir();
     h->T = p->n_taps;
     h->D = p->decimation;
@@ -529,6 +534,24 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
                 return rc;
             }
             h->algorithm = 3;
+        }
+    }
+
+    // block-Toeplitz GEMM on the tensor cores (algorithm 2, fir_tc.cu): explicit, or B200_FIR_ALGO=2
+    {
+        bool want2 = p->algorithm == 2;
+        if (const char* e = getenv("B200_FIR_ALGO"))
+            if (p->algorithm == 0 && atoi(e) == 2 && tc_supported(h->T, h->D, h->vec == 1))
+                want2 = true;
+        if (want2) {
+            ols_destroy(h->ols);
+            h->ols = nullptr;
+            int rc = tc_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
+            if (rc != B200_OK) {
+                b200_fir_destroy(h);
+                return rc;
+            }
+            h->algorithm = 2;
         }
     }
 

@@ -13,6 +13,7 @@
 #include "fir_ffa.cuh"
 #include "fir_interp.cuh"
 #include "fir_ols.cuh"
+#include "fir_tc.cuh"
 
 namespace b200 {
 

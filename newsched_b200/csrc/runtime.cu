@@ -283,6 +283,82 @@ int b200_event_elapsed_ms(b200_event_t start, b200_event_t stop, float* ms)
     return B200_OK;
 }
 
+// ---- peer memory: another GPU's buffer addressed directly by this GPU's kernels (NVLink loads),
+// the multi-GPU halo path: no exchange step, no copy, nothing on the critical path.
+int b200_enable_peer_access(int peer_device)
+{
+    int dev = 0, can = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev)
+        return B200_OK;
+    B200_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can)
+        return set_err(B200_ERR_UNSUPPORTED, "device %d cannot access device %d", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return B200_OK;
+    }
+    B200_CUDA(e);
+    return B200_OK;
+}
+
+int b200_ipc_export(const void* dptr, b200_ipc_handle* out)
+{
+    if (!dptr || !out)
+        return set_err(B200_ERR_ARG, "ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    memset(out, 0, sizeof(*out));
+    void* base = nullptr;
+    size_t size = 0;
+    {
+        static CUresult (*get_range)(CUdeviceptr*, size_t*, CUdeviceptr) = [] {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess)
+                fn = nullptr;
+            return (CUresult(*)(CUdeviceptr*, size_t*, CUdeviceptr))fn;
+        }();
+        if (!get_range)
+            return set_err(B200_ERR_CUDA, "ipc_export: cuMemGetAddressRange unavailable");
+        CUdeviceptr b = 0;
+        CUresult r = get_range(&b, &size, (CUdeviceptr)dptr);
+        if (r != CUDA_SUCCESS)
+            return set_err(B200_ERR_CUDA, "ipc_export: cuMemGetAddressRange -> %s", drv_err(r));
+        base = (void*)b;
+    }
+    cudaIpcMemHandle_t h;
+    B200_CUDA(cudaIpcGetMemHandle(&h, base));
+    memcpy(out->bytes, &h, 64);
+    out->offset = (uint64_t)((const char*)dptr - (const char*)base);
+    out->size = size;
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    out->device = dev;
+    return B200_OK;
+}
+
+int b200_ipc_import(const b200_ipc_handle* h, void** dptr)
+{
+    if (!h || !dptr)
+        return set_err(B200_ERR_ARG, "ipc_import: null argument");
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, h->bytes, 64);
+    void* base = nullptr;
+    B200_CUDA(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = (char*)base + h->offset;
+    return B200_OK;
+}
+
+int b200_ipc_close(const b200_ipc_handle* h, void* dptr)
+{
+    if (!h || !dptr)
+        return set_err(B200_ERR_ARG, "ipc_close: null argument");
+    B200_CUDA(cudaIpcCloseMemHandle((char*)dptr - h->offset));
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------- ring
 static int ring_prop(CUmemAllocationProp* prop, int* dev_out)
 {
