@@ -461,68 +461,108 @@ def run_b200(args):
         except Exception as e:  # pragma: no cover
             extras["flowgraph_error"] = repr(e)
 
-    # ---- multi-GPU only: BASELINE config 5 (time-segmented FIR, 4096 taps, halo + NCCL gather)
+    # ---- multi-GPU only: BASELINE config 5 (time-segmented FIR, 4096 taps, (ntaps-1) halo, NCCL gather) and
+    # config 4 (64-channel channelizer, both partitions of SURVEY.md 8e).  Every rank owns one 2^27-sample
+    # time segment.  The halo that precedes it is read IN PLACE from the left neighbour's buffer (PeerHalo:
+    # CUDA IPC mapping + peer access, NVLink loads by the first blocks of the kernel), so a step is one
+    # kernel launch; the NCCL point-to-point exchange it replaces is timed beside it.  Windows at the
+    # start (where the halo matters) and the end of every rank's output are checked against the CPU oracle
+    # on the same data; the trusted halo for that check comes from an all_gather, not from the path under test.
     if dist is not None:
+        from newsched_b200 import multigpu as mg
+        import oracle as o
+
+        def gather_tails(n_tail):
+            tails = [torch.empty(n_tail, dtype=torch.complex64, device=dev) for _ in range(world)]
+            dist.all_gather([torch.view_as_real(t) for t in tails], torch.view_as_real(x[-n_tail:].contiguous()))
+            return tails
+
+        def all_max(v):
+            return max_over_ranks(float(v))
+
         try:
-            from newsched_b200 import multigpu as mg
             rng5 = np.random.default_rng(5)
-            taps5 = (rng5.uniform(-1, 1, 4096) / 4096).astype(np.float32)
-            seg = x                                         # this rank's 2^27-sample time segment
+            T5, W = 4096, 1024
+            taps5 = (rng5.uniform(-1, 1, T5) / T5).astype(np.float32)
             fir5 = nb.FirFilter(taps5, 1)
-            sf = mg.SegmentedFir(fir5, rank, world)
             y5 = torch.empty(SAMPLES, dtype=torch.complex64, device=dev)
-            t = timed(torch, lambda: sf.run(seg, y5), 3, 2, barrier) / 3
-            t = max_over_ranks(t)
-            extras["config5_segmented_fir_4096taps"] = {
-                "Msamples_s_outputs_sharded": world * SAMPLES / (t * 1e-3) / 1e6, "ms": t,
-                "halo_bytes_per_rank": 4095 * 8, "algorithm": fir5.algorithm}
+            sf_peer = mg.SegmentedFir(fir5, rank, world, peer=True)
+            sf_p2p = mg.SegmentedFir(fir5, rank, world, peer=False)
+            sf_peer.run(x, y5)                                   # collective set-up of the mapping
+            t = max_over_ranks(timed(torch, lambda: sf_peer.run(x, y5), 5, 2, barrier) / 5)
+            tails = gather_tails(T5 - 1)
+            hist = tails[rank - 1].cpu().numpy() if rank > 0 else None
+            e0 = o.rel_rms(y5[:W].cpu().numpy(), o.fir(x[:W].cpu().numpy(), taps5, 1, hist=hist))
+            e1 = o.rel_rms(y5[-W:].cpu().numpy(), o.fir(x[-(W + T5 - 1):].cpu().numpy(), taps5, 1)[T5 - 1:])
+            err5 = all_max(max(e0, e1))
+            t_p2p = max_over_ranks(timed(torch, lambda: sf_p2p.run(x, y5), 5, 2, barrier) / 5)
+            c5 = {"Msamples_s_outputs_sharded": world * SAMPLES / (t * 1e-3) / 1e6, "ms": t,
+                  "halo": "read in place from the left neighbour over NVLink (peer-mapped pointer)",
+                  "halo_bytes_per_rank": (T5 - 1) * 8, "algorithm": fir5.algorithm,
+                  "ms_with_nccl_p2p_halo_exchange": t_p2p,
+                  "parity_ok": bool(err5 < 1e-5), "rel_rms_vs_oracle": err5,
+                  "parity_windows": f"first and last {W} outputs of every rank's segment vs oracle.fir (fp64), max over ranks"}
             full = mg.gather_concat(y5, rank, world, sizes=[SAMPLES] * world)   # warm-up (NCCL p2p setup)
             del full
             torch.cuda.synchronize()
             barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0_.record()
             full = mg.gather_concat(y5, rank, world, sizes=[SAMPLES] * world)
-            e1.record()
+            e1_.record()
             torch.cuda.synchronize()
-            tg = max_over_ranks(e0.elapsed_time(e1))
-            extras["config5_segmented_fir_4096taps"]["nccl_gather_ms"] = tg
-            extras["config5_segmented_fir_4096taps"]["Msamples_s_incl_gather"] = (
-                world * SAMPLES / ((t + tg) * 1e-3) / 1e6)
+            tg = max_over_ranks(e0_.elapsed_time(e1_))
+            c5["nccl_gather_ms"] = tg
+            c5["Msamples_s_incl_gather"] = world * SAMPLES / ((t + tg) * 1e-3) / 1e6
+            extras["config5_segmented_fir_4096taps"] = c5
             del full, y5
         except Exception as e:  # pragma: no cover
             extras["config5_error"] = repr(e)
 
-    # ---- multi-GPU only: BASELINE config 4 (64-channel channelizer over the GPUs), both partitions
-    # of SURVEY.md 8(e): channel slices of ONE stream (every GPU reads the whole input, writes
-    # 64/world channels: does not scale for an HBM-bound kernel) and time segments with a
-    # (P-1)*M-sample halo (every GPU filters its own 2^27-sample segment, all 64 channels)
-    if dist is not None and 64 % world == 0:
-        try:
-            from newsched_b200 import multigpu as mg
-            import scipy.signal as sig
-            pt = sig.firwin(1024, 1 / 64).astype(np.float32)
-            cb, cc = mg.channel_slice(64, rank, world)
-            pfb_c = nb.PfbChannelizer(pt, 64, cb, cc)
-            yc = torch.empty((SAMPLES // 64, cc), dtype=torch.complex64, device=dev)
-            t = max_over_ranks(timed(torch, lambda: pfb_c.work_segment(x, None, yc), 5, 2, barrier) / 5)
-            c4 = {"channel_sharded_one_stream_Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "channel_sharded_ms": t,
-                  "channels_per_gpu": cc}
-            del yc
-            pfb_t = nb.PfbChannelizer(pt, 64)
-            yt = torch.empty((SAMPLES // 64, 64), dtype=torch.complex64, device=dev)
-
-            def seg_run():
-                halo = mg.exchange_halo(x, 15 * 64, rank, world)
-                pfb_t.work_segment(x, halo, yt)
-            t = max_over_ranks(timed(torch, seg_run, 5, 2, barrier) / 5)
-            c4["time_segmented_Msamples_s"] = world * SAMPLES / (t * 1e-3) / 1e6
-            c4["time_segmented_ms"] = t
-            c4["halo_bytes_per_rank"] = 15 * 64 * 8
-            extras["config4_channelizer_64ch"] = c4
-            del yt
-        except Exception as e:  # pragma: no cover
-            extras["config4_error"] = repr(e)
+        if 64 % world == 0:
+            try:
+                import scipy.signal as sig
+                M, P, WF = 64, 16, 32
+                pt = sig.firwin(M * P, 1 / M).astype(np.float32)
+                cb, cc = mg.channel_slice(M, rank, world)
+                pfb_c = nb.PfbChannelizer(pt, M, cb, cc)
+                yc = torch.empty((SAMPLES // M, cc), dtype=torch.complex64, device=dev)
+                t = max_over_ranks(timed(torch, lambda: pfb_c.work_segment(x, None, yc), 5, 2, barrier) / 5)
+                # channel-sharded: zeros in front of the stream (no halo); first / last WF frames vs the oracle's columns
+                ref0 = o.pfb_channelizer(x[:WF * M].cpu().numpy(), pt, M)[:, cb:cb + cc]
+                ref1 = o.pfb_channelizer(x[-(WF + P - 1) * M:].cpu().numpy(), pt, M)[P - 1:, cb:cb + cc]
+                errc = all_max(max(o.rel_rms(yc[:WF].cpu().numpy().reshape(-1), ref0.reshape(-1)),
+                                   o.rel_rms(yc[-WF:].cpu().numpy().reshape(-1), ref1.reshape(-1))))
+                c4 = {"channel_sharded_one_stream_Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "channel_sharded_ms": t,
+                      "channels_per_gpu": cc, "channel_sharded_parity_ok": bool(errc < 1e-5),
+                      "channel_sharded_rel_rms_vs_oracle": errc}
+                del yc
+                pfb_t = nb.PfbChannelizer(pt, M)
+                yt = torch.empty((SAMPLES // M, M), dtype=torch.complex64, device=dev)
+                halo_len = (P - 1) * M
+                st_peer = mg.SegmentedFir(pfb_t, rank, world, peer=True, halo_len=halo_len)
+                st_p2p = mg.SegmentedFir(pfb_t, rank, world, peer=False, halo_len=halo_len)
+                st_peer.run(x, yt)
+                t = max_over_ranks(timed(torch, lambda: st_peer.run(x, yt), 5, 2, barrier) / 5)
+                tails = gather_tails(halo_len)
+                hist = tails[rank - 1].cpu().numpy() if rank > 0 else None
+                ref0 = o.pfb_channelizer(x[:WF * M].cpu().numpy(), pt, M, hist=hist)
+                ref1 = o.pfb_channelizer(x[-(WF + P - 1) * M:].cpu().numpy(), pt, M)[P - 1:]
+                errt = all_max(max(o.rel_rms(yt[:WF].cpu().numpy().reshape(-1), ref0.reshape(-1)),
+                                   o.rel_rms(yt[-WF:].cpu().numpy().reshape(-1), ref1.reshape(-1))))
+                t_p2p = max_over_ranks(timed(torch, lambda: st_p2p.run(x, yt), 5, 2, barrier) / 5)
+                c4["time_segmented_Msamples_s"] = world * SAMPLES / (t * 1e-3) / 1e6
+                c4["time_segmented_ms"] = t
+                c4["time_segmented_ms_with_nccl_p2p_halo_exchange"] = t_p2p
+                c4["halo"] = "read in place from the left neighbour over NVLink (peer-mapped pointer)"
+                c4["halo_bytes_per_rank"] = halo_len * 8
+                c4["parity_ok"] = bool(errt < 1e-5)
+                c4["rel_rms_vs_oracle"] = errt
+                c4["parity_windows"] = f"first and last {WF} frames of every rank's segment vs oracle.pfb_channelizer (fp64), max over ranks"
+                extras["config4_channelizer_64ch"] = c4
+                del yt
+            except Exception as e:  # pragma: no cover
+                extras["config4_error"] = repr(e)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

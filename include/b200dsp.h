@@ -76,6 +76,7 @@ B200_API int b200_memset(void* dst, int value, size_t bytes, b200_stream_t s);
 B200_API int b200_stream_create(b200_stream_t* s);
 B200_API int b200_stream_destroy(b200_stream_t s);
 B200_API int b200_stream_synchronize(b200_stream_t s);
+B200_API int b200_stream_activate(b200_stream_t s);        /* current device := the stream's device */
 B200_API int b200_stream_wait_event(b200_stream_t s, b200_event_t e);
 B200_API int b200_event_create(b200_event_t* e, int timing);
 B200_API int b200_event_destroy(b200_event_t e);
@@ -114,6 +115,7 @@ B200_API int b200_ipc_close(const b200_ipc_handle* h, void* dptr);
 typedef struct b200_ring b200_ring;
 B200_API int b200_ring_create(size_t min_bytes, b200_ring** ring);
 B200_API int b200_ring_destroy(b200_ring* ring);
+B200_API int b200_ring_enable_peer(b200_ring* ring, int peer_device); /* grant another GPU access to the ring */
 B200_API void* b200_ring_base(const b200_ring* ring);
 B200_API size_t b200_ring_size(const b200_ring* ring);
 B200_API size_t b200_ring_granularity(void);

@@ -45,6 +45,15 @@ public:
         return work(work_input, work_output);
     }
     void set_scheduler(std::shared_ptr<scheduler> sched) { p_scheduler = std::move(sched); }
+
+    // Called once by the scheduler when the edge buffers exist (flowgraph::validate(), i.e. before start()
+    // and outside the timed start()->wait() region): inputs[i] is the buffer of input port i, outputs[o] the
+    // buffers of output port o (several when it fans out).  Not in the reference -- there a block first
+    // sees its buffers inside work().  Default: nothing.
+    virtual void buffers_attached(const std::vector<std::shared_ptr<buffer>>& /*inputs*/,
+                                  const std::vector<std::vector<std::shared_ptr<buffer>>>& /*outputs*/)
+    {
+    }
 };
 typedef block::sptr block_sptr;
 typedef std::vector<block_sptr> block_vector_t;

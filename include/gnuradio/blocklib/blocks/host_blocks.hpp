@@ -47,6 +47,7 @@ class vector_source : public sync_block
     std::vector<tag_t> d_tags;
     size_t d_vlen, d_cursor = 0; // cursor counts scalars
     bool d_repeat;
+    std::vector<host_direct_io*> d_direct; // every buffer of the output port takes page-locked memory directly
 
     void emit_tags(buffer& out, size_t first_scalar, size_t n_scalars)
     {
@@ -72,11 +73,43 @@ public:
             throw std::invalid_argument("data length must be a multiple of vlen");
     }
 
+    // Host-to-device edges (device_buffer H2D): page-lock the vector once, before start(), and let every
+    // work() call hand its window over in place -- the DMA engine reads the std::vector itself, the
+    // intermediate memcpy into the edge's staging ring (128 MiB for configs[0]) disappears.
+    void buffers_attached(const std::vector<buffer_sptr>&, const std::vector<std::vector<buffer_sptr>>& outs) override
+    {
+        d_direct.clear();
+        if (outs.empty() || outs[0].empty() || d_data.empty())
+            return;
+        std::vector<host_direct_io*> ios;
+        for (auto& b : outs[0]) {
+            auto* io = host_direct_io::from(b);
+            if (!io || !io->write_from_host(nullptr, 0)) // probe: only host -> device edges accept
+                return;
+            ios.push_back(io);
+        }
+        if (ios[0]->pin_host(d_data.data(), d_data.size() * sizeof(T)))
+            d_direct = ios;
+    }
+
     work_return_code_t work(std::vector<block_work_input>&, std::vector<block_work_output>& wo) override
     {
         auto& o = wo[0];
-        T* dst = static_cast<T*>(o.buffer->write_ptr());
         const size_t room = (size_t)o.n_items * d_vlen;
+        if (!d_direct.empty() && !d_data.empty() && d_cursor < d_data.size() &&
+            (d_repeat ? d_data.size() - d_cursor >= room : true)) {
+            // in place: the window [d_cursor, d_cursor + run) of the page-locked vector is this call's output
+            const size_t run = std::min(room, d_data.size() - d_cursor);
+            if (!d_repeat)
+                emit_tags(*o.buffer, d_cursor, run);
+            d_direct[0]->write_from_host(&d_data[d_cursor], (int)(run / d_vlen)); // fan-out branches follow in copy_items
+            d_cursor += run;
+            if (d_repeat)
+                d_cursor %= d_data.size();
+            o.n_produced = (int)(run / d_vlen);
+            return (!d_repeat && d_cursor >= d_data.size()) ? work_return_code_t::WORK_DONE : work_return_code_t::WORK_OK;
+        }
+        T* dst = static_cast<T*>(o.buffer->write_ptr());
         if (d_data.empty() || (!d_repeat && d_cursor >= d_data.size())) {
             o.n_produced = 0;
             return work_return_code_t::WORK_DONE;
@@ -112,6 +145,11 @@ class vector_sink : public sync_block
     std::vector<T> d_store;
     std::vector<tag_t> d_seen;
     size_t d_vlen;
+    // device -> host edges (device_buffer D2H): the reserved storage is page-locked before start() and the
+    // edge delivers the stream straight into it; work() then only advances d_count (no append pass)
+    bool d_in_place = false;
+    size_t d_count = 0;        // scalars delivered in place
+    std::vector<T> d_overflow; // whatever arrives beyond the reservation (through the staging ring)
 
 public:
     typedef std::shared_ptr<vector_sink> sptr;
@@ -127,17 +165,49 @@ public:
         d_store.resize(d_vlen * reserve_items);
         d_store.clear();
     }
+    void buffers_attached(const std::vector<buffer_sptr>& ins, const std::vector<std::vector<buffer_sptr>>&) override
+    {
+        d_in_place = false;
+        auto* io = ins.empty() ? nullptr : host_direct_io::from(ins[0]);
+        const size_t cap = d_store.capacity();
+        if (!io || cap < d_vlen)
+            return;
+        d_store.resize(cap / d_vlen * d_vlen);
+        if (io->pin_host(d_store.data(), d_store.size() * sizeof(T)) &&
+            io->deliver_into_host(d_store.data(), d_store.size() / d_vlen)) {
+            d_in_place = true;
+            d_count = 0;
+        } else {
+            d_store.clear();
+        }
+    }
+
     work_return_code_t work(std::vector<block_work_input>& wi, std::vector<block_work_output>&) override
     {
         auto& in = wi[0];
         const T* src = static_cast<const T*>(in.buffer->read_ptr());
-        d_store.insert(d_store.end(), src, src + (size_t)in.n_items * d_vlen); // one append per call
+        const size_t n = (size_t)in.n_items * d_vlen;
+        if (d_in_place) {
+            if (src == d_store.data() + d_count)
+                d_count += n; // already where it belongs
+            else
+                d_overflow.insert(d_overflow.end(), src, src + n);
+        } else
+            d_store.insert(d_store.end(), src, src + n); // one append per call
         for (auto& t : in.buffer->get_tags((unsigned)in.n_items))
             d_seen.push_back(t);
         in.n_consumed = in.n_items;
         return work_return_code_t::WORK_OK;
     }
-    std::vector<T> data() { return d_store; }
+    std::vector<T> data()
+    {
+        if (!d_in_place)
+            return d_store;
+        std::vector<T> r(d_store.begin(), d_store.begin() + (std::ptrdiff_t)d_count);
+        r.insert(r.end(), d_overflow.begin(), d_overflow.end());
+        return r;
+    }
+    size_t size() const { return d_in_place ? d_count + d_overflow.size() : d_store.size(); }
     std::vector<tag_t> tags() { return d_seen; }
 };
 typedef vector_sink<std::uint8_t> vector_sink_b;

@@ -19,13 +19,22 @@ inline void check(int rc, const char* what)
         throw std::runtime_error(std::string(what) + ": " + b200_last_error());
 }
 
+// A GPU block lives on the device that is current when it is constructed: its stream, its C-ABI handles
+// (taps, history, twiddles) and -- through work_guard, which activates the stream's device -- every launch
+// of its work().  `b200_set_device(k)` before make() places a block on GPU k; the reference has no device
+// notion at all, its cuda::copy takes whatever device is current (copy.cpp:41-63).
 class stream_owner
 {
 protected:
     b200_stream_t d_stream = nullptr;
+    int d_device = 0;
 
 public:
-    stream_owner() { check(b200_stream_create(&d_stream), "stream_create"); }
+    stream_owner()
+    {
+        check(b200_get_device(&d_device), "get_device");
+        check(b200_stream_create(&d_stream), "stream_create");
+    }
     virtual ~stream_owner()
     {
         if (d_stream) {
@@ -33,6 +42,7 @@ public:
             b200_stream_destroy(d_stream);
         }
     }
+    int device() const { return d_device; }
     stream_owner(const stream_owner&) = delete;
     b200_stream_t stream() const { return d_stream; }
     void synchronize() { check(b200_stream_synchronize(d_stream), "stream_synchronize"); }

@@ -63,7 +63,18 @@ public:
             if (t.offset + num_items >= _total_written && t.offset < _total_written)
                 _tags.push_back(t);
     }
-    const std::vector<tag_t>& tags() const { return _tags; }
+    // snapshot under the lock (the reference hands out an unlocked reference, buffer.hpp:73, which races
+    // with add_tag / propagate_tags from the producer's thread)
+    std::vector<tag_t> tags()
+    {
+        std::scoped_lock g(_buf_mutex);
+        return _tags;
+    }
+    bool has_tags()
+    {
+        std::scoped_lock g(_buf_mutex);
+        return !_tags.empty();
+    }
     std::vector<tag_t> tags_in_window(uint64_t item_start, uint64_t item_end)
     {
         std::scoped_lock g(_buf_mutex);
@@ -132,6 +143,26 @@ public:
 };
 
 typedef std::shared_ptr<buffer> buffer_sptr;
+
+// Optional capability of an edge buffer whose far side is a device (gnuradio/devicebuffer.hpp): items can be
+// handed over from / delivered into page-locked host memory OWNED BY THE BLOCK, without passing through the
+// buffer's own staging ring.  Not in the reference (its cuda_buffer always stages, cudabuffer.cu:126-158);
+// host blocks probe for it with dynamic_cast and fall back to read_ptr()/write_ptr() when it is absent.
+class host_direct_io
+{
+public:
+    virtual ~host_direct_io() {}
+    // page-lock [p, p + bytes) for asynchronous copies; the buffer releases it when it is destroyed
+    virtual bool pin_host(void* p, size_t bytes) = 0;
+    // producer side (host -> device edge): this work() call's n_items output items are at `src`; the block
+    // then reports n_produced as usual and does not touch write_ptr()
+    virtual bool write_from_host(const void* src, int n_items) = 0;
+    // consumer side (device -> host edge): deliver the stream, in order, into dst[0 .. capacity_items) and
+    // offer it to the reader there (read_ptr() then points into dst); anything beyond the capacity goes
+    // through the staging ring again.  dst = nullptr switches it off
+    virtual bool deliver_into_host(void* dst, uint64_t capacity_items) = 0;
+    static host_direct_io* from(const buffer_sptr& b) { return dynamic_cast<host_direct_io*>(b.get()); }
+};
 
 class buffer_properties
 {

@@ -16,7 +16,11 @@
 //   * the ring is sized from the PROPERTIES (default 64 MiB), not from the scheduler's
 //     2*32768-byte default (buffer_management.cpp:117), so one work() covers millions of items;
 //   * _total_read/_total_written are maintained, so stream tags work on device edges
-//     (the reference's cuda_buffer never updates them).
+//     (the reference's cuda_buffer never updates them);
+//   * the staging flavours are asynchronous and multi-buffered: H2D keeps three copies in flight, D2H
+//     publishes a span to the CPU reader from its completion event and never blocks the producer; host
+//     blocks that own page-locked memory (vector_source / vector_sink) hand it over through
+//     gr::host_direct_io, so configs[0] moves every byte exactly once in each direction.
 // A GPU block brackets its launches with device_stream_guard (below): wait for the producer's
 // writes / the consumer's reads on ITS stream before launching, record both events after.
 #pragma once
@@ -25,7 +29,9 @@
 #include <b200dsp.h>
 
 #include <cstring>
+#include <deque>
 #include <stdexcept>
+#include <vector>
 
 namespace gr {
 
@@ -48,30 +54,80 @@ class device_buffer_properties : public buffer_properties
 {
     device_buffer_type _buffer_type;
     size_t _bytes;
+    int _device; // -1: the device current when the buffer is created (flowgraph::validate())
 
 public:
     static constexpr size_t default_bytes = 64u << 20;
-    device_buffer_properties(device_buffer_type t, size_t bytes = default_bytes) : _buffer_type(t), _bytes(bytes) {}
+    device_buffer_properties(device_buffer_type t, size_t bytes = default_bytes, int device = -1)
+        : _buffer_type(t), _bytes(bytes), _device(device)
+    {
+    }
     device_buffer_type buffer_type() { return _buffer_type; }
     size_t bytes() { return _bytes; }
-    static std::shared_ptr<buffer_properties> make(device_buffer_type t, size_t bytes = default_bytes)
+    int device() { return _device; }
+    static std::shared_ptr<buffer_properties> make(device_buffer_type t, size_t bytes = default_bytes, int device = -1)
     {
-        return std::make_shared<device_buffer_properties>(t, bytes);
+        return std::make_shared<device_buffer_properties>(t, bytes, device);
     }
 };
 
-class device_buffer : public buffer, public stream_ordered_buffer
+// the calling thread's current device for the lifetime of the object (buffers of a multi-GPU flowgraph are all
+// created by the thread that calls validate())
+class device_scope
+{
+    int _prev = -1;
+
+public:
+    explicit device_scope(int device)
+    {
+        if (device >= 0 && b200_get_device(&_prev) == B200_OK && _prev != device) {
+            if (b200_set_device(device) != B200_OK)
+                throw std::runtime_error(std::string("device_scope: ") + b200_last_error());
+        } else
+            _prev = -1;
+    }
+    ~device_scope()
+    {
+        if (_prev >= 0)
+            b200_set_device(_prev);
+    }
+};
+
+class device_buffer : public buffer, public stream_ordered_buffer, public host_direct_io
 {
     device_buffer_type _buffer_type;
     size_t _item_size, _num_items = 0, _buf_size = 0; // bytes of one mapping
-    size_t _read_index = 0, _write_index = 0;         // bytes
+    size_t _read_index = 0, _write_index = 0;         // bytes; _write_index = the PRODUCER's position
     b200_ring* _ring = nullptr;
     uint8_t* _dev = nullptr;
     uint8_t* _host = nullptr; // pinned staging (H2D: producer side, D2H: consumer side)
     b200_stream_t _stream = nullptr;
-    b200_event_t _ev_written = nullptr, _ev_read = nullptr, _ev_copy[2] = { nullptr, nullptr };
+    b200_event_t _ev_written = nullptr, _ev_read = nullptr;
+
+    // ---- H2D: up to H2D_SLOTS - 1 copies in flight; an offered window is at most capacity / H2D_SLOTS
+    // items, so the staging spans of the copies still in flight are never the ones being refilled
+    static constexpr int H2D_SLOTS = 4;
+    b200_event_t _ev_copy[H2D_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
+    bool _copy_pending[H2D_SLOTS] = { false, false, false, false };
     int _copy_slot = 0;
-    bool _copy_pending[2] = { false, false };
+    const uint8_t* _ext_src = nullptr; // H2D: this work() call's items sit in caller-owned pinned memory
+
+    // ---- D2H: copies are enqueued by the producer's post_write and PUBLISHED to the (CPU) reader when
+    // their completion event has fired -- the reader's thread waits for the oldest copy if it has
+    // nothing else to read, the producer's thread never waits (the reference, and round 1 of this file,
+    // synchronised the stream under the buffer mutex in every post_write: cudabuffer.cu:148-158)
+    struct span {
+        b200_event_t ev;
+        uint8_t* host;
+        uint64_t n_items;
+    };
+    std::deque<span> _pending; // copies in flight, oldest first          (both threads, under _buf_mutex)
+    std::deque<span> _ready;   // landed and published, not yet consumed  (both threads, under _buf_mutex)
+    std::vector<b200_event_t> _free_events;
+    uint8_t* _land = nullptr;  // optional landing zone of the consumer (deliver_into_host)
+    uint64_t _land_items = 0, _land_used = 0;
+    std::vector<void*> _pinned; // caller memory page-locked through pin_host(), released with the buffer
+    int _device = -1;
 
     static void ck(int rc, const char* what)
     {
@@ -88,13 +144,53 @@ class device_buffer : public buffer, public stream_ordered_buffer
         }
         return a / x * b;
     }
+    b200_event_t get_event()
+    {
+        if (!_free_events.empty()) {
+            b200_event_t e = _free_events.back();
+            _free_events.pop_back();
+            return e;
+        }
+        b200_event_t e = nullptr;
+        ck(b200_event_create(&e, 0), "event_create");
+        return e;
+    }
+    // move every landed copy from _pending to _ready (caller holds _buf_mutex)
+    void publish_landed()
+    {
+        while (!_pending.empty()) {
+            int q = b200_event_query(_pending.front().ev);
+            if (q < 0)
+                ck(q, "event_query");
+            if (q != 0)
+                break;
+            span sp = _pending.front();
+            _pending.pop_front();
+            _free_events.push_back(sp.ev);
+            sp.ev = nullptr;
+            if (!_ready.empty() && _ready.back().host + _ready.back().n_items * _item_size == sp.host)
+                _ready.back().n_items += sp.n_items; // contiguous in host memory: one window for the reader
+            else
+                _ready.push_back(sp);
+        }
+    }
+    void enqueue_d2h(uint8_t* host_dst, const uint8_t* dev_src, uint64_t n_items)
+    {
+        ck(b200_memcpy_d2h(host_dst, dev_src, n_items * _item_size, _stream), "memcpy_d2h");
+        span sp{ get_event(), host_dst, n_items };
+        ck(b200_event_record(sp.ev, _stream), "event_record");
+        _pending.push_back(sp);
+    }
 
 public:
     typedef std::shared_ptr<device_buffer> sptr;
     device_buffer(size_t /*num_items from the scheduler: ignored*/, size_t item_size,
-                  device_buffer_type type, size_t bytes)
+                  device_buffer_type type, size_t bytes, int device = -1)
         : _buffer_type(type), _item_size(item_size)
     {
+        device_scope on(device); // ring, stream, events and staging all belong to this device
+        if (b200_get_device(&_device) != B200_OK)
+            _device = -1;
         size_t want = std::max(bytes, 4 * item_size);
         if (type != device_buffer_type::D2D) {
             // the host side is not doubly mapped: keep the wrap point on an item boundary
@@ -111,8 +207,8 @@ public:
         ck(b200_stream_create(&_stream), "stream_create");
         ck(b200_event_create(&_ev_written, 0), "event_create");
         ck(b200_event_create(&_ev_read, 0), "event_create");
-        ck(b200_event_create(&_ev_copy[0], 0), "event_create");
-        ck(b200_event_create(&_ev_copy[1], 0), "event_create");
+        for (auto& e : _ev_copy)
+            ck(b200_event_create(&e, 0), "event_create");
         // make the events "complete" so the first waits fall through
         ck(b200_event_record(_ev_written, _stream), "event_record");
         ck(b200_event_record(_ev_read, _stream), "event_record");
@@ -122,11 +218,19 @@ public:
     }
     ~device_buffer() override
     {
+        device_scope on(_device);
         if (_stream)
             b200_stream_synchronize(_stream);
+        for (void* p : _pinned)
+            b200_host_unregister(p);
         if (_host)
             b200_host_free(_host);
-        for (auto e : { _ev_written, _ev_read, _ev_copy[0], _ev_copy[1] })
+        for (auto& sp : _pending)
+            if (sp.ev)
+                b200_event_destroy(sp.ev);
+        for (auto e : _free_events)
+            b200_event_destroy(e);
+        for (auto e : { _ev_written, _ev_read, _ev_copy[0], _ev_copy[1], _ev_copy[2], _ev_copy[3] })
             if (e)
                 b200_event_destroy(e);
         if (_stream)
@@ -139,25 +243,27 @@ public:
         auto p = std::dynamic_pointer_cast<device_buffer_properties>(props);
         if (!p)
             throw std::runtime_error("Failed to cast buffer properties to device_buffer_properties");
-        return buffer_sptr(new device_buffer(num_items, item_size, p->buffer_type(), p->bytes()));
+        return buffer_sptr(new device_buffer(num_items, item_size, p->buffer_type(), p->bytes(), p->device()));
     }
     static device_buffer* from(const buffer_sptr& b) { return dynamic_cast<device_buffer*>(b.get()); }
 
     device_buffer_type buffer_type() const { return _buffer_type; }
     size_t bytes() const { return _buf_size; }
-    int size()
-    {
-        size_t w = _write_index, r = _read_index;
-        if (w < r)
-            w += _buf_size;
-        return (int)((w - r) / _item_size);
-    }
+    int device() const { return _device; }
+    // lets another GPU of this process read / write the ring directly (peer loads over NVLink, peer copies)
+    void enable_peer(int peer_device) { ck(b200_ring_enable_peer(_ring, peer_device), "ring_enable_peer"); }
+    void* device_base() const { return _dev; }
+    // items between the reader's and the PRODUCER's position (what occupies the ring)
+    int size() { return (int)(_total_written - _total_read); }
     int capacity() { return (int)_num_items; }
 
     // device pointer except on the host-facing side of a staging buffer
     void* read_ptr() override
     {
-        return _buffer_type == device_buffer_type::D2H ? (void*)(_host + _read_index) : (void*)(_dev + _read_index);
+        if (_buffer_type != device_buffer_type::D2H)
+            return (void*)(_dev + _read_index);
+        std::scoped_lock g(_buf_mutex);
+        return _ready.empty() ? (void*)(_host + _read_index) : (void*)_ready.front().host;
     }
     void* write_ptr() override
     {
@@ -166,14 +272,31 @@ public:
 
     bool read_info(buffer_info_t& info) override
     {
-        std::scoped_lock g(_buf_mutex);
-        info.ptr = read_ptr();
-        int n = size();
-        if (_buffer_type == device_buffer_type::D2H) // host side is not doubly mapped: clip at the wrap
-            n = std::min<int>(n, (int)((_buf_size - _read_index) / _item_size));
-        info.n_items = n;
+        std::unique_lock<std::mutex> g(_buf_mutex);
         info.item_size = _item_size;
         info.total_items = (int)_total_read;
+        if (_buffer_type != device_buffer_type::D2H) {
+            info.ptr = (void*)(_dev + _read_index);
+            info.n_items = size();
+            return true;
+        }
+        publish_landed();
+        if (_ready.empty() && !_pending.empty()) {
+            // nothing to hand out yet, but a copy is on its way: wait for it HERE, on the reader's thread
+            // and outside the lock, so the producer keeps launching kernels and enqueuing copies meanwhile
+            b200_event_t ev = _pending.front().ev;
+            g.unlock();
+            ck(b200_event_synchronize(ev), "event_synchronize");
+            g.lock();
+            publish_landed();
+        }
+        if (_ready.empty()) {
+            info.ptr = (void*)(_host + _read_index);
+            info.n_items = 0;
+        } else {
+            info.ptr = (void*)_ready.front().host;
+            info.n_items = (int)std::min<uint64_t>(_ready.front().n_items, 0x7fffffff);
+        }
         return true;
     }
     bool write_info(buffer_info_t& info) override
@@ -194,7 +317,7 @@ public:
         }
         if (_buffer_type == device_buffer_type::H2D) {
             n = std::min<int>(n, (int)((_buf_size - _write_index) / _item_size));
-            n = std::min<int>(n, capacity() / 2); // keeps the in-flight H2D source span untouched
+            n = std::min<int>(n, capacity() / H2D_SLOTS); // keeps the in-flight H2D source spans untouched
         }
         info.n_items = std::max(0, n);
         info.item_size = _item_size;
@@ -204,6 +327,18 @@ public:
     void post_read(int n) override
     {
         std::scoped_lock g(_buf_mutex);
+        if (_buffer_type == device_buffer_type::D2H) {
+            uint64_t left = (uint64_t)n;
+            while (left && !_ready.empty()) {
+                span& f = _ready.front();
+                const uint64_t take = std::min(left, f.n_items);
+                f.host += take * _item_size;
+                f.n_items -= take;
+                left -= take;
+                if (f.n_items == 0)
+                    _ready.pop_front();
+            }
+        }
         _read_index = (_read_index + (size_t)n * _item_size) % _buf_size;
         _total_read += n;
     }
@@ -214,26 +349,45 @@ public:
         if (_buffer_type == device_buffer_type::H2D) {
             // device destination may still be read by an in-flight consumer kernel
             ck(b200_stream_wait_event(_stream, _ev_read), "wait_event");
-            ck(b200_memcpy_h2d(_dev + _write_index, _host + _write_index, nbytes, _stream), "memcpy_h2d");
-            ck(b200_event_record(_ev_written, _stream), "event_record");
-            // allow ONE copy in flight: wait for the previous one before the producer refills
-            ck(b200_event_record(_ev_copy[_copy_slot], _stream), "event_record");
-            _copy_pending[_copy_slot] = true;
-            _copy_slot ^= 1;
-            if (_copy_pending[_copy_slot]) {
-                ck(b200_event_synchronize(_ev_copy[_copy_slot]), "event_synchronize");
-                _copy_pending[_copy_slot] = false;
+            if (_ext_src) {
+                // the block handed over caller-owned page-locked memory (write_from_host): copy from there,
+                // nothing of ours is reused, so there is nothing to throttle
+                ck(b200_memcpy_h2d(_dev + _write_index, _ext_src, nbytes, _stream), "memcpy_h2d");
+                ck(b200_event_record(_ev_written, _stream), "event_record");
+                _ext_src = nullptr;
+            } else {
+                ck(b200_memcpy_h2d(_dev + _write_index, _host + _write_index, nbytes, _stream), "memcpy_h2d");
+                ck(b200_event_record(_ev_written, _stream), "event_record");
+                // H2D_SLOTS - 1 copies stay in flight: before the producer refills, wait for the copy that
+                // was enqueued H2D_SLOTS - 1 calls ago (its staging span is the next one to be reused)
+                ck(b200_event_record(_ev_copy[_copy_slot], _stream), "event_record");
+                _copy_pending[_copy_slot] = true;
+                _copy_slot = (_copy_slot + 1) % H2D_SLOTS;
+                if (_copy_pending[_copy_slot]) {
+                    ck(b200_event_synchronize(_ev_copy[_copy_slot]), "event_synchronize");
+                    _copy_pending[_copy_slot] = false;
+                }
             }
         } else if (_buffer_type == device_buffer_type::D2H) {
-            // the producer block recorded _ev_written after its launches; bring the span to the
-            // host and only then publish it to the (CPU) consumer
+            // the producer block recorded _ev_written after its launches: enqueue the copy behind it and
+            // return; the span becomes visible to the reader when its completion event has fired
             ck(b200_stream_wait_event(_stream, _ev_written), "wait_event");
-            size_t first = std::min(nbytes, _buf_size - _write_index);
-            ck(b200_memcpy_d2h(_host + _write_index, _dev + _write_index, first, _stream), "memcpy_d2h");
-            if (nbytes > first)
-                ck(b200_memcpy_d2h(_host, _dev, nbytes - first, _stream), "memcpy_d2h");
+            uint64_t left = (uint64_t)n;
+            size_t src = _write_index;
+            if (_land && _land_used < _land_items) { // straight into the consumer's own storage
+                const uint64_t take = std::min(left, _land_items - _land_used);
+                enqueue_d2h(_land + _land_used * _item_size, _dev + src, take); // device ring is doubly mapped
+                _land_used += take;
+                left -= take;
+                src = (src + take * _item_size) % _buf_size;
+            }
+            while (left) { // staging ring: split at the wrap of the (singly mapped) host side
+                const uint64_t take = std::min<uint64_t>(left, (_buf_size - src) / _item_size);
+                enqueue_d2h(_host + src, _dev + src, take);
+                left -= take;
+                src = (src + take * _item_size) % _buf_size;
+            }
             ck(b200_event_record(_ev_read, _stream), "event_record"); // device span free again
-            ck(b200_stream_synchronize(_stream), "stream_synchronize");
         }
         _write_index = (_write_index + nbytes) % _buf_size;
         _total_written += n;
@@ -250,6 +404,10 @@ public:
         if (_buffer_type == device_buffer_type::H2D) {
             if (src->_buffer_type != device_buffer_type::H2D)
                 throw std::runtime_error("device_buffer::copy_items: mixed H2D / device fan-out");
+            if (src->_ext_src) { // the producer's pinned memory feeds every branch directly
+                _ext_src = src->_ext_src;
+                return;
+            }
             memcpy(_host + _write_index, src->_host + src->_write_index, nbytes);
             return;
         }
@@ -257,6 +415,34 @@ public:
         ck(b200_stream_wait_event(_stream, _ev_read), "wait_event");
         ck(b200_memcpy_d2d(_dev + _write_index, src->_dev + src->_write_index, nbytes, _stream), "memcpy_d2d");
         ck(b200_event_record(_ev_written, _stream), "event_record");
+    }
+
+    // ---- host_direct_io (gnuradio/buffer.hpp): zero-copy hand-over with host blocks
+    bool pin_host(void* p, size_t bytes) override
+    {
+        if (!p || !bytes || b200_host_register(p, bytes) != B200_OK)
+            return false;
+        std::scoped_lock g(_buf_mutex);
+        _pinned.push_back(p);
+        return true;
+    }
+    bool write_from_host(const void* src, int /*n_items*/) override
+    {
+        if (_buffer_type != device_buffer_type::H2D)
+            return false;
+        std::scoped_lock g(_buf_mutex);
+        _ext_src = static_cast<const uint8_t*>(src);
+        return true;
+    }
+    bool deliver_into_host(void* dst, uint64_t capacity_items) override
+    {
+        if (_buffer_type != device_buffer_type::D2H)
+            return false;
+        std::scoped_lock g(_buf_mutex);
+        _land = static_cast<uint8_t*>(dst);
+        _land_items = dst ? capacity_items : 0;
+        _land_used = 0;
+        return true;
     }
 
     // ---- stream ordering used by GPU blocks (see device_stream_guard)
@@ -290,6 +476,10 @@ class device_stream_guard
 public:
     device_stream_guard(In& in, Out& out, b200_stream_t s) : _in(in), _out(out), _s(s)
     {
+        // the block's stream decides which GPU this thread talks to: one process can drive several devices
+        // (each block was built with its device current; its scheduler thread follows it here)
+        if (b200_stream_activate(_s) != B200_OK)
+            throw std::runtime_error(std::string("device_stream_guard: ") + b200_last_error());
         for (auto& w : _in)
             if (auto* d = stream_ordered_buffer::from(w.buffer))
                 d->wait_readable(_s);
@@ -314,3 +504,4 @@ public:
 #define DEVICE_BUFFER_ARGS_D2H gr::device_buffer::make, gr::device_buffer_properties::make(gr::device_buffer_type::D2H)
 #define DEVICE_BUFFER_ARGS_D2D gr::device_buffer::make, gr::device_buffer_properties::make(gr::device_buffer_type::D2D)
 #define DEVICE_BUFFER_ARGS_SIZED(type, bytes) gr::device_buffer::make, gr::device_buffer_properties::make(gr::device_buffer_type::type, (bytes))
+#define DEVICE_BUFFER_ARGS_ON(type, bytes, device) gr::device_buffer::make, gr::device_buffer_properties::make(gr::device_buffer_type::type, (bytes), (device))

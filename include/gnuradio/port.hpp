@@ -7,6 +7,7 @@
 #include <gnuradio/types.hpp>
 
 #include <algorithm>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -41,27 +42,40 @@ public:
     size_t itemsize() { return _itemsize; }
     std::vector<size_t> dims() { return _dims; }
 
+    // Non-owning links.  The reference keeps shared_ptrs here (port.hpp:92-133), which closes two ownership
+    // cycles -- port <-> connected port, and thread_wrapper -> block -> port -> thread_wrapper -- so a
+    // flowgraph is never freed; with 64 MiB device rings + pinned staging per edge that leak matters here.
+    // The scheduler owns the thread wrappers and the blocks own their ports for as long as a notification
+    // can be in flight, so weak references are enough.
     void set_parent_intf(neighbor_interface_sptr intf) { _parent_intf = intf; }
     void notify_connected_ports(scheduler_message_sptr msg)
     {
-        for (auto& p : _connected_ports)
-            p->push_message(msg);
+        for (auto& w : _connected_ports)
+            if (auto p = w.lock())
+                p->push_message(msg);
     }
     virtual void push_message(scheduler_message_sptr msg)
     {
-        if (!_parent_intf)
+        auto intf = _parent_intf.lock();
+        if (!intf)
             throw std::runtime_error("port has no parent interface");
-        _parent_intf->push_message(msg);
+        intf->push_message(msg);
     }
     void connect(sptr other)
     {
-        if (std::find(_connected_ports.begin(), _connected_ports.end(), other) == _connected_ports.end())
-            _connected_ports.push_back(other);
+        for (auto& w : _connected_ports)
+            if (w.lock() == other)
+                return;
+        _connected_ports.push_back(other);
     }
 
     void disconnect(sptr other)
     {
-        _connected_ports.erase(std::remove(_connected_ports.begin(), _connected_ports.end(), other),
+        _connected_ports.erase(std::remove_if(_connected_ports.begin(), _connected_ports.end(),
+                                              [&](const std::weak_ptr<port_base>& w) {
+                                                  auto p = w.lock();
+                                                  return !p || p == other;
+                                              }),
                                _connected_ports.end());
     }
 
@@ -72,8 +86,8 @@ protected:
     int _index = -1;
     std::vector<size_t> _dims;
     size_t _datasize, _itemsize;
-    std::vector<sptr> _connected_ports;
-    neighbor_interface_sptr _parent_intf = nullptr;
+    std::vector<std::weak_ptr<port_base>> _connected_ports;
+    std::weak_ptr<neighbor_interface> _parent_intf;
 };
 typedef port_base::sptr port_sptr;
 typedef std::vector<port_sptr> port_vector_t;

@@ -60,7 +60,13 @@ public:
         auto it = _in_buf.find(p.get());
         return it == _in_buf.end() ? nullptr : it->second;
     }
-    std::vector<buffer_sptr>& get_output_buffers(port_sptr p) { return _out_bufs[p.get()]; }
+    // read-only after initialize_buffers(): several scheduler threads call this concurrently, so no operator[]
+    const std::vector<buffer_sptr>& get_output_buffers(port_sptr p) const
+    {
+        static const std::vector<buffer_sptr> none;
+        auto it = _out_bufs.find(p.get());
+        return it == _out_bufs.end() ? none : it->second;
+    }
 };
 
 enum class executor_iteration_status { READY, BLKD_IN, BLKD_OUT, DONE };
@@ -164,7 +170,7 @@ class thread_wrapper : public neighbor_interface
         for (size_t i = 0; i < in_ports.size(); i++) {
             auto& w = work_input[i];
             int nc = std::max(0, w.n_consumed);
-            if (!w.buffer->tags().empty()) {
+            if (w.buffer->has_tags()) {
                 auto pol = b->tag_propagation_policy();
                 for (size_t o = 0; o < out_ports.size(); o++)
                     if (pol == tag_propagation_policy_t::TPP_ALL_TO_ALL ||
@@ -339,6 +345,15 @@ public:
         for (auto& b : blocks)
             if (std::find(grouped.begin(), grouped.end(), b) == grouped.end())
                 make_thread({ b });
+        for (auto& b : blocks) {
+            std::vector<buffer_sptr> ins;
+            std::vector<std::vector<buffer_sptr>> outs;
+            for (auto& p : b->input_stream_ports())
+                ins.push_back(_bufman->get_input_buffer(p));
+            for (auto& p : b->output_stream_ports())
+                outs.push_back(_bufman->get_output_buffers(p));
+            b->buffers_attached(ins, outs);
+        }
     }
     void start() override
     {
@@ -354,9 +369,23 @@ public:
     {
         for (auto& t : _threads)
             t->wait();
+        std::exception_ptr first = nullptr;
         for (auto& t : _threads)
-            if (t->error())
-                std::rethrow_exception(t->error()); // first failure, after every thread has stopped
+            if (t->error() && !first)
+                first = t->error();
+        // the run is over: drop the threads and the edge buffers now (device rings, pinned staging, streams,
+        // events) instead of when the last reference to the scheduler happens to go away
+        _threads.clear();
+        _bufman.reset();
+        if (first)
+            std::rethrow_exception(first); // first failure, after every thread has stopped
+    }
+    ~scheduler_mt() override
+    {
+        for (auto& t : _threads) {
+            t->stop();
+            t->wait();
+        }
     }
 };
 

@@ -101,6 +101,7 @@ SIGNATURES = {
     "b200_stream_create": (_I, [C.POINTER(_V)]),
     "b200_stream_destroy": (_I, [_V]),
     "b200_stream_synchronize": (_I, [_V]),
+    "b200_stream_activate": (_I, [_V]),
     "b200_stream_wait_event": (_I, [_V, _V]),
     "b200_event_create": (_I, [C.POINTER(_V), _I]),
     "b200_event_destroy": (_I, [_V]),
@@ -114,6 +115,7 @@ SIGNATURES = {
     "b200_ipc_close": (_I, [C.POINTER(IpcHandle), _V]),
     "b200_ring_create": (_I, [_SZ, C.POINTER(_V)]),
     "b200_ring_destroy": (_I, [_V]),
+    "b200_ring_enable_peer": (_I, [_V, _I]),
     "b200_ring_base": (_V, [_V]),
     "b200_ring_size": (_SZ, [_V]),
     "b200_ring_granularity": (_SZ, []),

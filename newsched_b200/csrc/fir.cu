@@ -473,6 +473,35 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     h->algorithm = 1;
     if (h->smem > 200 * 1024 || p->algorithm == 4)
         h->algorithm = 4; // naive global-memory fallback
+    // block-Toeplitz GEMM on the tensor cores (algorithm 2, fir_tc.cu).  Measured on B200 (tools/tc_check.py,
+    // 64 Mi samples, input rate in GS/s, tensor form vs the best SIMT form): full-rate complex filters of
+    // 48 / 64 / 96 / 128 / 192 / 256 / 384 taps run 354 / 347 / 323 / 312 / 280 / 245 / 193 against
+    // 294 / 229 / 193 / 194 / 190 / 188 / 183 (direct FFMA2 kernel up to 64 taps, overlap-save beyond), i.e.
+    // 0.86 .. 0.60 of the HBM roofline where the SIMT forms reach 0.56 .. 0.45; at 512 taps it loses
+    // (133 vs 177) and so do the decimating cases (T=1024/D=4: 163 vs 252), which stay on overlap-save.
+    // Its results carry the bf16 hi/lo split error, 3.1e-6 .. 3.6e-6 relative RMS against the fp64 oracle
+    // (bar: 1e-5); the SIMT forms (~1e-7 / 3e-7) remain selectable with algorithm = 1 / 3 for callers that
+    // want bit-reproducible chunking or an exact impulse response.
+    {
+        bool want2 = p->algorithm == 2;
+        if (p->algorithm == 0 && h->vec == 2 && h->D == 1 && h->T >= 33 && h->T <= 384 && tc_supported(h->T, h->D, 0))
+            want2 = true;
+        if (const char* e = getenv("B200_FIR_ALGO")) {
+            if (p->algorithm == 0 && atoi(e) == 2 && tc_supported(h->T, h->D, h->vec == 1))
+                want2 = true;
+            else if (p->algorithm == 0 && atoi(e) != 0)
+                want2 = false;
+        }
+        if (want2) {
+            int rc = tc_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
+            if (rc != B200_OK) {
+                b200_fir_destroy(h);
+                return rc;
+            }
+            h->algorithm = 2;
+        }
+    }
+
     // overlap-save fast convolution: complex streams, enough taps per output to pay for two
     // FFTs per block (crossover measured on B200: ~100 taps per output sample)
     {
@@ -523,6 +552,8 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         if (const char* e = getenv("B200_FIR_ALGO"))
             if (p->algorithm == 0)
                 want = atoi(e) == 3;
+        if (h->algorithm == 2)
+            want = false; // the tensor-core form was chosen above
         if (want && !can && p->algorithm == 3) {
             b200_fir_destroy(h);
             return set_err(B200_ERR_UNSUPPORTED, "fir_create: overlap-save needs 2..32768 taps");
@@ -534,24 +565,6 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
                 return rc;
             }
             h->algorithm = 3;
-        }
-    }
-
-    // block-Toeplitz GEMM on the tensor cores (algorithm 2, fir_tc.cu): explicit, or B200_FIR_ALGO=2
-    {
-        bool want2 = p->algorithm == 2;
-        if (const char* e = getenv("B200_FIR_ALGO"))
-            if (p->algorithm == 0 && atoi(e) == 2 && tc_supported(h->T, h->D, h->vec == 1))
-                want2 = true;
-        if (want2) {
-            ols_destroy(h->ols);
-            h->ols = nullptr;
-            int rc = tc_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
-            if (rc != B200_OK) {
-                b200_fir_destroy(h);
-                return rc;
-            }
-            h->algorithm = 2;
         }
     }
 

@@ -32,6 +32,7 @@
 // one CTA's conversion / epilogue overlaps the other's MMAs.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -64,6 +65,10 @@ struct tc_args {
     int fuse;
     float kre, kim;
     int desc_mode;   // 0: base_offset field 0 (swizzle on absolute address bits); 1: base_offset = (addr >> 7) & 7
+    const uint32_t* gAt; // TMEM-resident form: tap matrix [128 lanes][16*ksteps / 2] bf16 pairs, K contiguous
+    int ts_plane_elems, ts_plane_bytes, ts_stages, ts_stage_bytes;
+    int ts_swap;     // diagnostic: swap the bf16 halves of every 32-bit TMEM column of A
+    int dbg;         // bottleneck attribution (B200_TC_DBG): 1 = skip conversion, 2 = skip epilogue, 4 = skip MMAs, 8 = skip input copies
 };
 
 // ---- tcgen05 / TMEM PTX ------------------------------------------------------------------------
@@ -95,6 +100,63 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
                  "}\n" ::"r"(d_tmem),
                  "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// one lane of a converged warp (CUTLASS's elect_one_sync): the predicate comes from elect.sync, which the
+// compiler knows to be true for exactly one lane, so operands need no per-lane loop to reach the uniform registers
+__device__ __forceinline__ uint32_t tc_elect_one()
+{
+    uint32_t pred = 0, laneid = 0;
+    asm volatile("{\n"
+                 ".reg .b32 %%rx;\n"
+                 ".reg .pred %%px;\n"
+                 "elect.sync %%rx|%%px, %2;\n"
+                 "@%%px mov.s32 %1, 1;\n"
+                 "mov.s32 %0, %%rx;\n"
+                 "}\n"
+                 : "+r"(laneid), "+r"(pred)
+                 : "r"(0xFFFFFFFFu));
+    return pred;
+}
+// warp index as a warp-uniform value for the compiler (a shuffle result is uniform by construction): keeps the
+// role dispatch and everything computed under it in the uniform datapath
+__device__ __forceinline__ int tc_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// Whole-warp forms: every lane executes them with warp-uniform operands and ONE lane is elected inside
+// the asm.  Issuing under `if (lane == 0)` makes the operands thread-divergent for the compiler, which
+// then wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~75 ns per MMA measured);
+// with uniform operands the descriptors live in uniform registers and an MMA is a handful of instructions.
+__device__ __forceinline__ void tc_commit_w(uint32_t bar_saddr)
+{
+    asm volatile("{\n"
+                 ".reg .pred e;\n"
+                 "elect.sync _|e, 0xffffffff;\n"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                 "}\n" ::"r"(bar_saddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate)
+{
+    asm volatile("{\n"
+                 ".reg .pred p, e;\n"
+                 "setp.ne.b32 p, %4, 0;\n"
+                 "elect.sync _|e, 0xffffffff;\n"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+                 "}\n" ::"r"(d_tmem),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+    asm volatile("{\n"
+                 ".reg .pred p, e;\n"
+                 "setp.ne.b32 p, %4, 0;\n"
+                 "elect.sync _|e, 0xffffffff;\n"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+                 "}\n" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
 // 32 consecutive fp32 columns of this thread's TMEM lane
@@ -349,6 +411,542 @@ __global__ void __launch_bounds__(TC_THREADS, 2) fir_tc_kernel(const tc_args a)
     }
 }
 
+// =================================================================================================
+// Pipelined form: one persistent CTA per SM, warp-specialised.
+//   warp 0       MMA issuer (one elected lane), owns the TMEM allocation (2 accumulator stages x 256 columns)
+//   warp 1       tap-atom producer (1-D bulk copies into a ring)
+//   warps 2..5   epilogue: TMEM -> registers, hi-/lo-tap halves combined through a 16 KiB exchange
+//                buffer, coalesced 8-byte stores straight to global memory
+//   warps 6..13  converters: fp32 stream -> four swizzled bf16 planes, two plane stages
+// so the conversion of tile i+1, the MMAs of tile i and the epilogue of tile i-1 run concurrently;
+// all hand-offs are mbarriers (tcgen05.commit on the tensor-core side).
+constexpr int TCP_THREADS = 14 * 32;
+constexpr int TCP_CONVERTERS = 8 * 32;
+constexpr int TCP_XBUF = 32 * 64 * 8; // one exchange buffer: 32 columns x 64 phases x complex64
+constexpr int TCP_LOADS = 18;         // loads in flight per converter thread: 256 x 18 x 16 B = 72 KiB >= one tile
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int TCP_CONV, int TCP_LD>
+__device__ __forceinline__ void tc_convert(const tc_args& a, uint8_t* planes, int plane_elems, int plane_bytes,
+                                           long long m0, int p, int ctid)
+{
+    if (a.dbg & 1)
+        return;
+    const long long j0 = m0 - a.P;
+    if (a.D == 1 && j0 >= 0 && j0 + plane_elems <= a.n_in && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
+        // the whole tile (64-80 KB) is requested before the first conversion: TCP_LD independent 16-byte loads per thread
+        const float4* src = reinterpret_cast<const float4*>(a.x + j0);
+        const int npairs = plane_elems >> 1;
+#pragma unroll 1
+        for (int base = 0; base < npairs; base += TCP_CONV * TCP_LD) {
+            float4 v[TCP_LD];
+#pragma unroll
+            for (int u = 0; u < TCP_LD; u++) {
+                const int q = base + u * TCP_CONV + ctid;
+                v[u] = q < npairs ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < TCP_LD; u++) {
+                const int q = base + u * TCP_CONV + ctid;
+                if (q < npairs) {
+                    const __nv_bfloat162 rh = __floats2bfloat162_rn(v[u].x, v[u].z);
+                    const __nv_bfloat162 ih = __floats2bfloat162_rn(v[u].y, v[u].w);
+                    const float2 rhf = __bfloat1622float2(rh), ihf = __bfloat1622float2(ih);
+                    const __nv_bfloat162 rl = __floats2bfloat162_rn(v[u].x - rhf.x, v[u].z - rhf.y);
+                    const __nv_bfloat162 il = __floats2bfloat162_rn(v[u].y - ihf.x, v[u].w - ihf.y);
+                    const uint32_t off = tc_plane_off(2u * q);
+                    *reinterpret_cast<__nv_bfloat162*>(planes + off) = rh;
+                    *reinterpret_cast<__nv_bfloat162*>(planes + plane_bytes + off) = rl;
+                    *reinterpret_cast<__nv_bfloat162*>(planes + 2 * plane_bytes + off) = ih;
+                    *reinterpret_cast<__nv_bfloat162*>(planes + 3 * plane_bytes + off) = il;
+                }
+            }
+        }
+        return;
+    }
+    const bool interior = j0 * a.D - p >= 0 && (j0 + plane_elems - 1) * a.D - p < a.n_in;
+#pragma unroll 1
+    for (int base = 0; base < plane_elems; base += TCP_CONV * 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = base + u * TCP_CONV + ctid;
+            const long long n = (j0 + i) * a.D - p;
+            v[u] = make_float2(0.f, 0.f);
+            if (i < plane_elems) {
+                if (interior || (n >= 0 && n < a.n_in))
+                    v[u] = __ldg(a.x + n);
+                else if (n < 0 && a.hist != nullptr && n >= -(long long)a.Tm1)
+                    v[u] = __ldg(a.hist + (a.Tm1 + n));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = base + u * TCP_CONV + ctid;
+            if (i < plane_elems) {
+                __nv_bfloat16 rh, rl, ih, il;
+                tc_split(v[u].x, rh, rl);
+                tc_split(v[u].y, ih, il);
+                const uint32_t off = tc_plane_off((uint32_t)i);
+                *reinterpret_cast<__nv_bfloat16*>(planes + off) = rh;
+                *reinterpret_cast<__nv_bfloat16*>(planes + plane_bytes + off) = rl;
+                *reinterpret_cast<__nv_bfloat16*>(planes + 2 * plane_bytes + off) = ih;
+                *reinterpret_cast<__nv_bfloat16*>(planes + 3 * plane_bytes + off) = il;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TCP_THREADS, 1) fir_tc_pipe_kernel(const tc_args a)
+{
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* planes = smem;                                          // [2 stages][re_hi, re_lo, im_hi, im_lo]
+    uint8_t* ring = smem + 8 * (size_t)a.plane_bytes;                // tap atoms
+    uint8_t* xbuf = ring + (size_t)a.stages * TC_ATOM_BYTES;         // [2] exchange buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + 2 * TCP_XBUF);
+    uint64_t* taps_full = bars;                                      // [TC_MAX_STAGES]
+    uint64_t* taps_empty = bars + TC_MAX_STAGES;                     // [TC_MAX_STAGES]
+    uint64_t* planes_full = bars + 2 * TC_MAX_STAGES;                // [2]
+    uint64_t* planes_empty = planes_full + 2;                        // [2]
+    uint64_t* tmem_full = planes_empty + 2;                          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
+    const long long n_tiles = (a.n_out + TC_TILE - 1) / TC_TILE;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(&taps_full[s], 1);
+            mbar_init(&taps_empty[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&planes_full[b], TCP_CONVERTERS / 32);
+            mbar_init(&planes_empty[b], 1);
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc_alloc(tmem_slot, 2 * TC_TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // the CTA owns all 512 columns, so the allocation starts at column 0 / lane 0: using the literal keeps
+    // every MMA operand warp-uniform for the compiler (a value loaded from shared memory is not)
+    if (*tmem_slot != 0)
+        __trap();
+    constexpr uint32_t tmem = 0;
+    const int atoms_per_tile = a.D * a.KA;
+
+    if (warp == 0) {
+        // ================= MMA issuer =================
+        const uint32_t planes_s = smem_u32(planes), ring_s = smem_u32(ring);
+        int g = 0, u = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const int acc = it & 1;
+            mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_re = tmem + acc * TC_TMEM_COLS, d_im = d_re + TC_NROW;
+            for (int p = 0; p < a.D; p++, u++) {
+                const int ps = u & 1;
+                mbar_wait(&planes_full[ps], (u >> 1) & 1);
+                tc_fence_after();
+                const uint32_t pl = planes_s + ps * 4 * a.plane_bytes;
+                for (int at = 0; at < a.KA; at++, g++) {
+                    const int s = g % a.stages;
+                    mbar_wait(&taps_full[s], (g / a.stages) & 1);
+                    tc_fence_after();
+                    const int nst = (a.dbg & 4) ? 0 : min(4, a.ksteps - 4 * at);
+                    if (tc_elect_one()) {
+                        const uint64_t pstep = (uint64_t)(a.plane_bytes >> 4);
+                        uint64_t adesc = tc_desc(ring_s + s * TC_ATOM_BYTES, 0), b0 = tc_desc(pl + at * 128, 0);
+                        for (int t = 0; t < nst; t++, adesc += 2, b0 += 2) {
+                            const uint32_t accum = (p | at | t) != 0;
+                            tc_mma_bf16(d_re, adesc, b0, TC_IDESC, accum);
+                            tc_mma_bf16(d_re, adesc, b0 + pstep, TC_IDESC, 1);
+                            tc_mma_bf16(d_im, adesc, b0 + 2 * pstep, TC_IDESC, accum);
+                            tc_mma_bf16(d_im, adesc, b0 + 3 * pstep, TC_IDESC, 1);
+                        }
+                        tc_commit(&taps_empty[s]);
+                        if (at == a.KA - 1) {
+                            tc_commit(&planes_empty[ps]);
+                            if (p == a.D - 1)
+                                tc_commit(&tmem_full[acc]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= tap-atom producer =================
+        const int total = my_tiles * atoms_per_tile;
+        for (int g = 0; g < total; g++) {
+            const int s = g % a.stages;
+            mbar_wait(&taps_empty[s], ((g / a.stages) & 1) ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&taps_full[s], TC_ATOM_BYTES);
+                bulk_copy_g2s(ring + (size_t)s * TC_ATOM_BYTES, a.gA + (size_t)(g % atoms_per_tile) * TC_ATOM_BYTES,
+                              TC_ATOM_BYTES, &taps_full[s]);
+            }
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ================= epilogue =================
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
+        const int part = quarter >> 1;                // 0: hi-tap rows, 1: lo-tap rows
+        const int c = (quarter & 1) * 32 + lane;      // phase
+        const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+        int cq = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const int acc = it & 1;
+            const long long m0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TC_TILE;
+            const long long left = a.n_out - m0;
+            const int count = left < TC_TILE ? (int)left : TC_TILE;
+            float2* dst = a.y + m0;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            if (a.dbg & 2) {
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
+#pragma unroll 1
+            for (int q = 0; q < 4; q++, cq++) {
+                float re[32], im[32];
+                tc_ld32(tl + acc * TC_TMEM_COLS + q * 32, re);
+                tc_ld32(tl + acc * TC_TMEM_COLS + TC_NROW + q * 32, im);
+                tc_wait_ld();
+                if (q == 3) { // this warp has drained its lanes of the accumulator stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(&tmem_empty[acc]);
+                }
+                float2* xb = reinterpret_cast<float2*>(xbuf + (cq & 1) * TCP_XBUF);
+                const bool writer = part == ((cq & 1) ^ 1);
+                if (writer) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        xb[i * 64 + c] = make_float2(re[i], im[i]);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (!writer) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        float2 v = xb[i * 64 + c];
+                        v.x += re[i];
+                        v.y += im[i];
+                        if (a.fuse)
+                            v = cmul_nofma(v, a.kre, a.kim);
+                        const int o = (q * 32 + i) * 64 + c;
+                        if (o < count)
+                            __stcs(dst + o, v);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= converters =================
+        const int ctid = tid - 6 * 32;
+        int u = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const long long m0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TC_TILE;
+            for (int p = 0; p < a.D; p++, u++) {
+                const int ps = u & 1;
+                mbar_wait(&planes_empty[ps], ((u >> 1) & 1) ^ 1);
+                tc_convert<TCP_CONVERTERS, TCP_LOADS>(a, planes + (size_t)ps * 4 * a.plane_bytes, a.plane_elems,
+                                                      a.plane_bytes, m0, p, ctid);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&planes_full[ps]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tc_dealloc(tmem, 2 * TC_TMEM_COLS);
+    }
+}
+
+// =================================================================================================
+// Tap-stationary form (decimation 1, K <= 512, i.e. up to 448 taps): the tap operand never changes, so it
+// is written ONCE per CTA into tensor memory (A operand from TMEM, 128 lanes x K/2 columns) and the
+// MMAs read only the signal from shared memory -- half the shared-memory traffic of the ring form and
+// no tap streaming at all.  Tiles are 64 Hankel rows (4096 outputs, MMA 128x64x16), so an accumulator
+// stage is 128 TMEM columns (re 64 + im 64): 256 columns of taps + 2 accumulator stages = 512.
+// The tap rows are permuted so that the hi- and lo-tap partial sums of a phase sit 16 lanes apart in the
+// same warp: the epilogue adds them with one shuffle, no shared-memory exchange and no CTA barrier.
+//   warp 0        MMA issuer (one elected lane), TMEM allocation
+//   warp 1        input producer: one 1-D bulk copy (TMA) per tile, raw fp32, into a 3-deep staging ring --
+//                 two to three tiles (70-100 KB) are in flight per SM whatever the other warps are doing
+//   warps 4..11   epilogue: (warp & 3) = TMEM lane quarter, two warps per quarter split the 64 columns
+//                 (warps 4..7 also do the one-off tap upload into TMEM)
+//   warps 2, 3, 12..15  converters: staging (fp32) -> four swizzled bf16 planes, 3 plane stages
+// Measured on the way here (tools/tc_dbg.py, per 4096-sample tile and SM): with register-staged global
+// loads in the converters (two groups x 36 KB in flight) the conversion alone took 1.5 us and did not
+// overlap the epilogue's stores (both latency-bound on the same memory system): 266 GS/s at 64 taps.
+constexpr int TS_NROW = 64;
+constexpr int TS_TILE = TS_NROW * TC_PH;  // 4096 outputs
+constexpr int TS_THREADS = 16 * 32;
+constexpr int TS_EPI_WARPS = 8;
+constexpr int TS_EPI_WARP0 = 4;
+constexpr int TS_CONV_WARPS = 6;
+constexpr int TS_CONV = TS_CONV_WARPS * 32;
+constexpr int TS_MAX_STAGES = 4;          // plane stages
+constexpr int TS_IN_STAGES = 3;           // staging ring (raw input tiles)
+constexpr int TS_A_COLS = 256;
+constexpr uint32_t TS_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TS_NROW >> 3) << 17) | ((128u >> 4) << 24);
+
+// interior tile: its whole input span [j0, j0 + plane_elems) lies inside this call's stream and is 16-byte aligned,
+// so it can travel as ONE bulk copy; edge tiles (history in front, ragged end) are read element-wise
+__device__ __forceinline__ bool ts_fast_tile(const tc_args& a, long long j0)
+{
+    return j0 >= 0 && j0 + a.ts_plane_elems <= a.n_in && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+}
+
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+                 "}\n" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args a)
+{
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* planes = smem;                                          // [stages][re_hi, re_lo, im_hi, im_lo]
+    uint8_t* staging = planes + (size_t)a.ts_stages * 4 * a.ts_plane_bytes; // [TS_IN_STAGES] raw complex64 tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (size_t)TS_IN_STAGES * a.ts_stage_bytes);
+    uint64_t* planes_full = bars;                                    // [TS_MAX_STAGES]
+    uint64_t* planes_empty = bars + TS_MAX_STAGES;                   // [TS_MAX_STAGES]
+    uint64_t* tmem_full = bars + 2 * TS_MAX_STAGES;                  // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                            // [2]
+    uint64_t* in_full = tmem_empty + 2;                              // [TS_IN_STAGES]
+    uint64_t* in_empty = in_full + TS_IN_STAGES;                     // [TS_IN_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + TS_IN_STAGES);
+
+    const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
+    const long long n_tiles = (a.n_out + TS_TILE - 1) / TS_TILE;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int S = a.ts_stages;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&planes_full[s], TS_CONV_WARPS);
+            mbar_init(&planes_empty[s], 1);
+        }
+        for (int s = 0; s < TS_IN_STAGES; s++) {
+            mbar_init(&in_full[s], 1);
+            mbar_init(&in_empty[s], TS_CONV_WARPS);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], TS_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (*tmem_slot != 0) // all 512 columns are ours: the allocation starts at 0 (keeps MMA operands warp-uniform)
+        __trap();
+    constexpr uint32_t tmem = 0;
+    if (warp >= TS_EPI_WARP0 && warp < TS_EPI_WARP0 + 4) {
+        // one-off: this thread's tap row -> its TMEM lane, 8 columns (16 bf16) per K-step
+        const int quarter = warp & 3;
+        const uint32_t* row = a.gAt + (size_t)(quarter * 32 + lane) * (a.ksteps * 8);
+        const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+        for (int k = 0; k < a.ksteps; k++) {
+            const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(row + k * 8));
+            const uint4 hi4 = __ldg(reinterpret_cast<const uint4*>(row + k * 8 + 4));
+            uint32_t v[8] = { lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w };
+            if (a.ts_swap) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    v[i] = __byte_perm(v[i], 0, 0x1032);
+            }
+            tc_st8(tl + k * 8, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t d_base = tmem + TS_A_COLS;
+
+    if (warp == 0) {
+        // ================= MMA issuer =================
+        const uint32_t planes_s = smem_u32(planes);
+        for (int it = 0; it < my_tiles; it++) {
+            const int acc = it & 1, ps = it % S;
+            mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+            mbar_wait(&planes_full[ps], (it / S) & 1);
+            tc_fence_after();
+            const uint32_t d_re = d_base + acc * 2 * TS_NROW, d_im = d_re + TS_NROW;
+            // descriptors of the four planes at K-step 0; a K-step advances the start address by 32 bytes = 2 units
+            uint64_t b0 = tc_desc(planes_s + ps * 4 * a.ts_plane_bytes, 0);
+            const uint64_t pstep = (uint64_t)(a.ts_plane_bytes >> 4);
+            const int nk = (a.dbg & 4) ? 0 : a.ksteps;
+            if (tc_elect_one()) {
+#pragma unroll 2
+                for (int k = 0; k < nk; k++, b0 += 2) {
+                    const uint32_t at = tmem + k * 8, accum = k != 0;
+                    tc_mma_bf16_ts(d_re, at, b0, TS_IDESC, accum);
+                    tc_mma_bf16_ts(d_re, at, b0 + pstep, TS_IDESC, 1);
+                    tc_mma_bf16_ts(d_im, at, b0 + 2 * pstep, TS_IDESC, accum);
+                    tc_mma_bf16_ts(d_im, at, b0 + 3 * pstep, TS_IDESC, 1);
+                }
+                tc_commit(&planes_empty[ps]);
+                tc_commit(&tmem_full[acc]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================= input producer =================
+        int nf = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const long long j0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TS_TILE - a.P;
+            if (!ts_fast_tile(a, j0))
+                continue;                                            // edge tile: the converters read it themselves
+            const int slot = nf % TS_IN_STAGES;
+            mbar_wait(&in_empty[slot], ((nf / TS_IN_STAGES) & 1) ^ 1);
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)a.ts_plane_elems * 8u;
+                if (a.dbg & 8) {
+                    mbar_arrive(&in_full[slot]);
+                } else {
+                    mbar_arrive_expect_tx(&in_full[slot], bytes);
+                    bulk_copy_g2s(staging + (size_t)slot * a.ts_stage_bytes, a.x + j0, bytes, &in_full[slot]);
+                }
+            }
+            __syncwarp();
+            nf++;
+        }
+    } else if (warp >= TS_EPI_WARP0 && warp < TS_EPI_WARP0 + TS_EPI_WARPS) {
+        // ================= epilogue =================
+        const int quarter = warp & 3, ch = (warp - TS_EPI_WARP0) >> 2;   // this warp drains columns 32 ch .. 32 ch + 31
+        const int c = quarter * 16 + (lane & 15);     // phase; lanes l and l+16 hold its hi- / lo-tap sums
+        const bool lower = lane < 16;
+        const uint32_t tl = d_base + ((uint32_t)(quarter * 32) << 16);
+        for (int it = 0; it < my_tiles; it++) {
+            const int acc = it & 1;
+            const long long m0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TS_TILE;
+            const long long left = a.n_out - m0;
+            const int count = left < TS_TILE ? (int)left : TS_TILE;
+            float2* dst = a.y + m0;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            if (a.dbg & 2) {
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
+            {
+                float re[32], im[32];
+                tc_ld32(tl + acc * 2 * TS_NROW + ch * 32, re);
+                tc_ld32(tl + acc * 2 * TS_NROW + TS_NROW + ch * 32, im);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&tmem_empty[acc]);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    // lower half-warp finishes column 2j, upper half column 2j+1: each sends what the other needs
+                    const float sr = lower ? re[2 * j + 1] : re[2 * j], si = lower ? im[2 * j + 1] : im[2 * j];
+                    const float rr = __shfl_xor_sync(0xffffffffu, sr, 16), ri = __shfl_xor_sync(0xffffffffu, si, 16);
+                    float2 v = make_float2((lower ? re[2 * j] : re[2 * j + 1]) + rr, (lower ? im[2 * j] : im[2 * j + 1]) + ri);
+                    if (a.fuse)
+                        v = cmul_nofma(v, a.kre, a.kim);
+                    const int o = (ch * 32 + 2 * j + (lower ? 0 : 1)) * 64 + c;
+                    if (o < count)
+                        __stcs(dst + o, v);
+                }
+            }
+        }
+    } else {
+        // ================= converters (warps 2, 3, 12..15) =================
+        const int ctid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
+        int nf = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const long long m0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TS_TILE;
+            const int ps = it % S;
+            uint8_t* pl = planes + (size_t)ps * 4 * a.ts_plane_bytes;
+            mbar_wait(&planes_empty[ps], ((it / S) & 1) ^ 1);
+            if (ts_fast_tile(a, m0 - a.P)) {
+                const int slot = nf % TS_IN_STAGES;
+                mbar_wait(&in_full[slot], (nf / TS_IN_STAGES) & 1);
+                if (!(a.dbg & 1)) {
+                    const float4* src = reinterpret_cast<const float4*>(staging + (size_t)slot * a.ts_stage_bytes);
+                    const int npairs = a.ts_plane_elems >> 1;
+#pragma unroll 4
+                    for (int q = ctid; q < npairs; q += TS_CONV) {
+                        const float4 v = src[q];
+                        const __nv_bfloat162 rh = __floats2bfloat162_rn(v.x, v.z);
+                        const __nv_bfloat162 ih = __floats2bfloat162_rn(v.y, v.w);
+                        const float2 rhf = __bfloat1622float2(rh), ihf = __bfloat1622float2(ih);
+                        const __nv_bfloat162 rl = __floats2bfloat162_rn(v.x - rhf.x, v.z - rhf.y);
+                        const __nv_bfloat162 il = __floats2bfloat162_rn(v.y - ihf.x, v.w - ihf.y);
+                        const uint32_t off = tc_plane_off(2u * q);
+                        *reinterpret_cast<__nv_bfloat162*>(pl + off) = rh;
+                        *reinterpret_cast<__nv_bfloat162*>(pl + a.ts_plane_bytes + off) = rl;
+                        *reinterpret_cast<__nv_bfloat162*>(pl + 2 * a.ts_plane_bytes + off) = ih;
+                        *reinterpret_cast<__nv_bfloat162*>(pl + 3 * a.ts_plane_bytes + off) = il;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&in_empty[slot]);                    // this warp has read its share of the slot
+                nf++;
+            } else {
+                tc_convert<TS_CONV, 8>(a, pl, a.ts_plane_elems, a.ts_plane_bytes, m0, 0, ctid);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&planes_full[ps]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tc_dealloc(tmem, 512);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 struct tc_plan {
     int T = 0, D = 1;
@@ -357,6 +955,13 @@ struct tc_plan {
     float kre = 1.f, kim = 0.f;
     int desc_mode = 0;
     size_t smem = 0;
+    int ts = 0;            // 1: tap-stationary kernel (fir_tc_ts_kernel): D = 1, K <= 512
+    int ts_plane_elems = 0, ts_plane_bytes = 0, ts_stages = 0, ts_stage_bytes = 0, ts_swap = 0;
+    size_t ts_smem = 0;
+    uint32_t* d_at = nullptr;
+    int pipe = 0;          // 1: persistent warp-specialised kernel (fir_tc_pipe_kernel)
+    int pipe_stages = 2;
+    size_t pipe_smem = 0;
     uint8_t* d_atoms = nullptr;
 };
 
@@ -426,6 +1031,20 @@ int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre
         delete p;
         return set_err(B200_ERR_UNSUPPORTED, "fir(tensor core): planes do not fit shared memory");
     }
+    // pipelined form: two plane stages + the deepest tap ring that still fits
+    {
+        const size_t fixed = 1024 + 8 * (size_t)p->plane_bytes + 2 * TCP_XBUF + 256;
+        int st = TC_MAX_STAGES;
+        while (st > 1 && fixed + (size_t)st * TC_ATOM_BYTES > 227 * 1024)
+            st--;
+        if (st > total_atoms)
+            st = total_atoms;
+        p->pipe_stages = st;
+        p->pipe_smem = fixed + (size_t)st * TC_ATOM_BYTES;
+        p->pipe = p->pipe_smem <= 227 * 1024;
+        if (const char* e = getenv("B200_TC_PIPE"))
+            p->pipe = p->pipe && atoi(e) != 0;
+    }
 
     // tap atoms: [branch][atom][row 0..127][64 bf16], rows 0..63 = hi part of phase c, 64..127 = lo part,
     // element e of atom at <-> j = 64 at + e, tap index q = c + P - j of the branch; SWIZZLE_128B order
@@ -449,11 +1068,51 @@ int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre
                 }
             }
         }
+    // tap-stationary form: [128 TMEM lanes][K] bf16, K contiguous; lane 32 q + l carries phase 16 q + (l & 15),
+    // hi part for l < 16 and lo part for l >= 16
+    std::vector<uint16_t> at_rows;
+    if (p->D == 1 && p->ksteps * 16 <= 2 * TS_A_COLS) {
+        const int K = p->ksteps * 16;
+        at_rows.assign((size_t)128 * K, 0);
+        for (int m = 0; m < 128; m++) {
+            const int q4 = m >> 5, l = m & 31, c = 16 * q4 + (l & 15), lo = l >> 4;
+            for (int j = 0; j < K; j++) {
+                const long long k = (long long)c + p->P - j;
+                const float hv = (k >= 0 && k < n_taps) ? taps[k] : 0.f;
+                const uint16_t hi = tc_bf16_rn(hv);
+                at_rows[(size_t)m * K + j] = lo ? tc_bf16_rn(hv - tc_bf16_f(hi)) : hi;
+            }
+        }
+        p->ts_plane_elems = TC_PH * (TS_NROW - 1) + K;
+        p->ts_plane_bytes = ((p->ts_plane_elems + 63) / 64 * 128 + 1023) / 1024 * 1024;
+        p->ts_stage_bytes = (p->ts_plane_elems * 8 + 1023) / 1024 * 1024;
+        int st = TS_MAX_STAGES;
+        while (st > 2 && 1024 + (size_t)st * 4 * p->ts_plane_bytes + (size_t)TS_IN_STAGES * p->ts_stage_bytes + 256 > 227 * 1024)
+            st--;
+        if (const char* e = getenv("B200_TC_TS_STAGES"))
+            st = std::max(2, std::min(st, atoi(e)));
+        p->ts_stages = st;
+        p->ts_smem = 1024 + (size_t)st * 4 * p->ts_plane_bytes + (size_t)TS_IN_STAGES * p->ts_stage_bytes + 256;
+        p->ts = 1;
+        if (const char* e = getenv("B200_TC_TS"))
+            p->ts = atoi(e) != 0;
+        if (const char* e = getenv("B200_TC_TS_SWAP"))
+            p->ts_swap = atoi(e);
+    }
     cudaError_t e = cudaMalloc(&p->d_atoms, atoms.size() * 2);
     if (e == cudaSuccess)
         e = cudaMemcpy(p->d_atoms, atoms.data(), atoms.size() * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(fir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess && !at_rows.empty()) {
+        e = cudaMalloc(&p->d_at, at_rows.size() * 2);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->d_at, at_rows.data(), at_rows.size() * 2, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fir_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fir_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
         e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -470,6 +1129,7 @@ void tc_destroy(tc_plan* p)
     if (!p)
         return;
     cudaFree(p->d_atoms);
+    cudaFree(p->d_at);
     delete p;
 }
 
@@ -500,6 +1160,25 @@ int tc_launch(tc_plan* p, const float* d_hist, const void* d_in, void* d_out, lo
     a.kre = p->kre;
     a.kim = p->kim;
     a.desc_mode = p->desc_mode;
+    if (const char* e = getenv("B200_TC_DBG"))
+        a.dbg = atoi(e);
+    if (p->ts) {
+        a.gAt = p->d_at;
+        a.ts_plane_elems = p->ts_plane_elems;
+        a.ts_plane_bytes = p->ts_plane_bytes;
+        a.ts_stages = p->ts_stages;
+        a.ts_stage_bytes = p->ts_stage_bytes;
+        a.ts_swap = p->ts_swap;
+        const long long ts_tiles = (n_out + TS_TILE - 1) / TS_TILE, sms = sm_count();
+        B200_LAUNCH(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
+        return B200_OK;
+    }
+    if (p->pipe) {
+        a.stages = p->pipe_stages;
+        const long long sms = sm_count();
+        B200_LAUNCH(fir_tc_pipe_kernel, (unsigned)(tiles < sms ? tiles : sms), TCP_THREADS, p->pipe_smem, s, a);
+        return B200_OK;
+    }
     B200_LAUNCH(fir_tc_kernel, (unsigned)tiles, TC_THREADS, p->smem, s, a);
     return B200_OK;
 }

@@ -303,6 +303,19 @@ int b200_enable_peer_access(int peer_device)
     return B200_OK;
 }
 
+// makes the device a stream lives on the calling thread's current device (kernel launches need it; copies and
+// event operations do not).  Host blocks call it at the top of work(): one flowgraph process can then drive
+// several GPUs, one scheduler thread per block as in the reference (thread_wrapper.cpp:21).
+int b200_stream_activate(b200_stream_t s)
+{
+    int dev = -1, cur = -1;
+    B200_CUDA(cudaStreamGetDevice(cs(s), &dev));
+    B200_CUDA(cudaGetDevice(&cur));
+    if (dev != cur)
+        B200_CUDA(cudaSetDevice(dev));
+    return B200_OK;
+}
+
 int b200_ipc_export(const void* dptr, b200_ipc_handle* out)
 {
     if (!dptr || !out)
@@ -450,6 +463,25 @@ int b200_ring_create(size_t min_bytes, b200_ring** ring)
     RING_DRV(d.MemSetAccess(r->base, 2 * size, &acc, 1));
 #undef RING_DRV
     *ring = r;
+    return B200_OK;
+}
+
+// lets kernels and copy engines of `peer_device` address this ring (VMM allocations are private to the
+// device they were granted to until cuMemSetAccess says otherwise)
+int b200_ring_enable_peer(b200_ring* r, int peer_device)
+{
+    if (!r)
+        return set_err(B200_ERR_ARG, "ring_enable_peer: null ring");
+    if (peer_device == r->device)
+        return B200_OK;
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = peer_device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CUresult c = drv().MemSetAccess(r->base, 2 * r->size, &acc, 1);
+    if (c != CUDA_SUCCESS)
+        return set_err(B200_ERR_CUDA, "ring_enable_peer: cuMemSetAccess -> %s", drv_err(c));
     return B200_OK;
 }
 

@@ -350,6 +350,48 @@ QA_TEST(SchedulerMTTest, BlockExceptionSurfacesInWait)
     EXPECT_TRUE(caught);
 }
 
+// thread_wrapper -> block -> port -> thread_wrapper and port <-> port were shared_ptr
+// cycles (as in the reference), so a flowgraph -- and every edge buffer: 64 MiB device rings plus pinned
+// staging here -- was never freed.  A counting buffer type shows the edges are destroyed when the run
+// is over, and the blocks when the last outside reference goes away.
+static std::atomic<int> g_live_buffers{ 0 };
+class counted_buffer : public vmcirc_buffer
+{
+public:
+    counted_buffer(size_t n, size_t isz) : vmcirc_buffer(n, isz) { g_live_buffers++; }
+    ~counted_buffer() override { g_live_buffers--; }
+    static buffer_sptr make(size_t n, size_t isz, std::shared_ptr<buffer_properties>)
+    {
+        return buffer_sptr(new counted_buffer(n, isz));
+    }
+};
+QA_TEST(SchedulerMTTest, TeardownFreesBuffersAndBlocks)
+{
+    std::weak_ptr<blocks::vector_sink_f> weak_sink;
+    std::weak_ptr<flowgraph> weak_fg;
+    for (int round = 0; round < 3; round++) {
+        std::vector<float> input_data(50000, 1.0f);
+        auto src = blocks::vector_source_f::make(input_data, false);
+        auto hd = blocks::head::make(sizeof(float), 40000);
+        auto snk = blocks::vector_sink_f::make();
+        auto fg = flowgraph::make();
+        fg->connect(src, 0, hd, 0)->set_custom_buffer(counted_buffer::make, nullptr);
+        fg->connect(hd, 0, snk, 0)->set_custom_buffer(counted_buffer::make, nullptr);
+        auto sched = schedulers::scheduler_mt::make();
+        fg->set_scheduler(sched);
+        fg->validate();
+        EXPECT_EQ(g_live_buffers.load(), 2);
+        fg->start();
+        fg->wait();
+        EXPECT_EQ(snk->data().size(), (size_t)40000);
+        EXPECT_EQ(g_live_buffers.load(), 0); // edge buffers go with the run, not with the process
+        weak_sink = snk;
+        weak_fg = fg;
+    }
+    EXPECT_TRUE(weak_sink.expired());
+    EXPECT_TRUE(weak_fg.expired());
+}
+
 QA_TEST(Buffers, VmcircWindowIsLinear)
 {
     auto buf = vmcirc_buffer::make(1024, sizeof(int), nullptr);

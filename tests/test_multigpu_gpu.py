@@ -1,7 +1,10 @@
-"""GPU, >= 2 devices (skipped on a 1-GPU box): BASELINE configs 4 and 5 over NCCL.
-config 5: one long stream split into time segments, (ntaps-1)-sample halo from the left
-neighbour, NCCL gather of the outputs == the single-GPU result.
-config 4: channelizer output channels sharded per GPU == the columns of the full output."""
+"""GPU, >= 2 devices (skipped on a 1-GPU box): BASELINE configs 4 and 5 over NCCL / NVLink, checked
+against the CPU ORACLE (not against a 1-GPU run of the same kernels).
+config 5: one long stream split into time segments; the (ntaps-1)-sample halo is read in place from the
+left neighbour's buffer (PeerHalo: CUDA IPC + peer access) and, as the portable form, exchanged
+point-to-point; NCCL gather of the outputs == oracle.fir of the whole stream.
+config 4: channelizer, both partitions of SURVEY.md 8(e): output channels sharded per GPU == the
+columns of oracle.pfb_channelizer; time segments with a (P-1)*M-sample halo == its rows."""
 import os
 import socket
 
@@ -24,47 +27,69 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     import scipy.signal as sig
     import newsched_b200 as nb
+    import oracle as o
     from newsched_b200 import multigpu as mg
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    ok = True
+    ok, notes = True, []
     try:
         rng = np.random.default_rng(11)
-        n = 1 << 21
-        x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
-        for T, D, algo in ((64, 1, 1), (4096, 1, 3), (1024, 4, 0)):
+        n_all = 1 << 20
+        x_all = (rng.uniform(-1, 1, n_all) + 1j * rng.uniform(-1, 1, n_all)).astype(np.complex64)
+        for T, D, algo, n in ((64, 1, 1, 1 << 20), (4096, 1, 3, 1 << 18), (1024, 4, 0, 1 << 20), (256, 1, 2, 1 << 20)):
+            x = x_all[:n]
             taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
-            lo, hi = mg.time_segments(n, world, D)[rank]
+            lo, hi = mg.time_segments(n, world, D, halo_len=T - 1)[rank]
             seg = torch.from_numpy(x[lo:hi]).cuda()
-            fir = nb.FirFilter(taps, D, algorithm=algo)
-            y = mg.SegmentedFir(fir, rank, world).run(seg)
-            full = mg.gather_concat(y, rank, world)
-            if rank == 0:
-                ref = nb.FirFilter(taps, D, algorithm=algo).work(torch.from_numpy(x).cuda())[0]
-                err = (full - ref).abs().pow(2).mean().sqrt() / ref.abs().pow(2).mean().sqrt()
-                ok &= bool(full.shape == ref.shape) and float(err) < 1e-5
-                if algo == 1:
-                    ok &= bool(torch.equal(full, ref))      # direct form: bit-exact across segments
-        # config 4: channels sharded, every GPU reads the whole stream
+            ref = o.fir(x, taps, D) if rank == 0 else None
+            for peer in (True, False):
+                fir = nb.FirFilter(taps, D, algorithm=algo)
+                y = mg.SegmentedFir(fir, rank, world, peer=peer).run(seg)
+                full = mg.gather_concat(y, rank, world)
+                if rank == 0:
+                    err = o.rel_rms(full.cpu().numpy(), ref)
+                    good = full.numel() == ref.size and err < 1e-5
+                    notes.append((T, D, fir.algorithm, "peer" if peer else "p2p", float(err)))
+                    ok &= bool(good)
+                    if algo == 1:      # direct form: bit-identical to the single stream
+                        one = nb.FirFilter(taps, D, algorithm=1).work(torch.from_numpy(x).cuda())[0]
+                        ok &= bool(torch.equal(full, one))
+        # config 4
         M, P = 64, 16
         pt = sig.firwin(M * P, 1.0 / M).astype(np.float32)
-        xs = torch.from_numpy(x[: M * 4096]).cuda()
+        nx = M * 8192
+        x = x_all[:nx]
+        refc = o.pfb_channelizer(x, pt, M) if rank == 0 else None          # [frames, M]
+        # (a) channels sharded, every GPU reads the whole stream
+        xs = torch.from_numpy(x).cuda()
         b, c = mg.channel_slice(M, rank, world)
         part = nb.PfbChannelizer(pt, M, channel_begin=b, channel_count=c).work(xs)[0]
-        cols = mg.gather_concat(part.t().contiguous(), rank, world)   # gather along channels
+        cols = mg.gather_concat(part.t().contiguous(), rank, world)       # gather along channels
         if rank == 0:
-            ref = nb.PfbChannelizer(pt, M).work(xs)[0]
-            ok &= bool(torch.equal(cols.t(), ref))
+            err = o.rel_rms(cols.t().cpu().numpy().reshape(-1), refc.reshape(-1))
+            notes.append(("pfb", "channels", float(err)))
+            ok &= bool(err < 1e-5)
+        # (b) time segments, (P-1)*M halo read from the neighbour in place
+        lo, hi = mg.time_segments(nx, world, M, halo_len=(P - 1) * M)[rank]
+        seg = torch.from_numpy(x[lo:hi]).cuda()
+        pfb = nb.PfbChannelizer(pt, M)
+        for peer in (True, False):
+            rows = mg.SegmentedFir(pfb, rank, world, peer=peer, halo_len=(P - 1) * M).run(seg)
+            allrows = mg.gather_concat(rows.contiguous(), rank, world)
+            if rank == 0:
+                err = o.rel_rms(allrows.cpu().numpy().reshape(-1), refc.reshape(-1))
+                notes.append(("pfb", "time", "peer" if peer else "p2p", float(err)))
+                ok &= bool(err < 1e-5)
         torch.cuda.synchronize()
         if rank == 0:
-            q.put(ok)
+            q.put((ok, notes))
     finally:
         dist.destroy_process_group()
 
 
-def test_configs_4_and_5_on_two_gpus():
+def test_configs_4_and_5_on_two_gpus_match_the_oracle():
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -76,6 +101,7 @@ def test_configs_4_and_5_on_two_gpus():
     for p in procs:
         p.start()
     for p in procs:
-        p.join(300)
+        p.join(600)
         assert p.exitcode == 0
-    assert q.get(timeout=5) is True
+    ok, notes = q.get(timeout=5)
+    assert ok is True, notes

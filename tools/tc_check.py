@@ -10,12 +10,21 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-PARITY = [(64, 1), (100, 1), (128, 1), (256, 1), (512, 1), (1024, 1), (257, 1), (1024, 4), (512, 2), (96, 3), (2048, 8)]
-TIMING = [(128, 1), (256, 1), (512, 1), (1024, 1), (1024, 4), (512, 4), (2048, 4), (512, 2)]
+PARITY = [(64, 1), (100, 1), (128, 1), (256, 1), (448, 1), (449, 1), (33, 1), (257, 1), (5, 1), (1024, 4)]
+TIMING = [(48, 1), (64, 1), (96, 1), (128, 1), (192, 1), (256, 1), (384, 1), (512, 1), (1024, 1), (1024, 4), (512, 4), (256, 2)]
+
+
+VARIANTS = {   # name -> environment of the library
+    "ts": {"B200_TC_TS": "1", "B200_TC_PIPE": "1"},            # tap-stationary (taps in TMEM); falls back to pipe when K > 512 or D > 1
+    "ts_swap": {"B200_TC_TS": "1", "B200_TC_TS_SWAP": "1"},    # diagnostic: other packing of the bf16 pairs in TMEM
+    "pipe": {"B200_TC_TS": "0", "B200_TC_PIPE": "1"},          # warp-specialised, taps streamed through a smem ring
+    "v0": {"B200_TC_TS": "0", "B200_TC_PIPE": "0"},            # one tile per CTA, phases serialised
+}
 
 
 def child(kind, T, D, mode):
-    os.environ["B200_TC_DESC_MODE"] = str(mode)
+    variant = mode
+    os.environ.update(VARIANTS[variant])
     import numpy as np
     import torch
     import newsched_b200 as nb
@@ -23,7 +32,7 @@ def child(kind, T, D, mode):
     taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
     if kind == "parity":
         import oracle as o
-        n = (8192 * 3 + 1000) * D + (D - 1)
+        n = (8192 * 301 + 1000) * D + (D - 1)          # > 2 tiles per SM for the persistent form, ragged tail
         x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
         dx = torch.from_numpy(x).cuda()
         f = nb.FirFilter(taps, D, algorithm=2)
@@ -33,7 +42,7 @@ def child(kind, T, D, mode):
         err = o.rel_rms(y.cpu().numpy(), ref)
         # streaming: two chunks must continue the history
         f2 = nb.FirFilter(taps, D, algorithm=2)
-        cut = (8192 + 333) * D
+        cut = (8192 * 150 + 333) * D
         ya, _ = f2.work(dx[:cut])
         yb, _ = f2.work(dx[cut:])
         err2 = o.rel_rms(torch.cat([ya, yb]).cpu().numpy(), ref)
@@ -48,8 +57,10 @@ def child(kind, T, D, mode):
         g = torch.Generator(device="cuda").manual_seed(1)
         x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
         out = torch.empty(n // D, dtype=torch.complex64, device="cuda")
-        res = {"kind": kind, "T": T, "D": D, "mode": mode}
-        for algo in (2, 0):
+        res = {"kind": kind, "T": T, "D": D}
+        for algo, pipe in ((2, variant), (2, "pipe"), (0, "")):
+            if pipe:
+                os.environ.update(VARIANTS[pipe])
             f = nb.FirFilter(taps, D, algorithm=algo)
             for _ in range(3):
                 f.work_segment(x, None, out)
@@ -62,9 +73,10 @@ def child(kind, T, D, mode):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             gs = n / (ms * 1e-3) / 1e9
-            res[f"algo{f.algorithm}_GSs"] = round(gs, 1)
-            res[f"algo{f.algorithm}_hbm_frac"] = round(gs * (8 + 8 / D) / 6556.5, 3)
-            if algo == 2:
+            tag = f"algo{f.algorithm}" + (("_" + pipe) if algo == 2 else "")
+            res[f"{tag}_GSs"] = round(gs, 1)
+            res[f"{tag}_hbm_frac"] = round(gs * (8 + 8 / D) / 6556.5, 3)
+            if algo == 2 and pipe == variant:
                 # executed tensor flops: 4 MMAs of 128x128x16 per K-step, ksteps = (roundup16(ceil(T/D)-1)+64)/16 per branch
                 tq = (T + D - 1) // D
                 ksteps = ((tq - 1 + 15) // 16 * 16 + 64) // 16
@@ -77,8 +89,8 @@ def child(kind, T, D, mode):
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "child":
-        return child(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
-    modes = [int(m) for m in os.environ.get("TC_MODES", "0,1").split(",")]
+        return child(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), sys.argv[5])
+    modes = os.environ.get("TC_VARIANTS", "ts,ts_swap").split(",")
     good_mode = None
     if what in ("parity", "all"):
         for mode in modes:
@@ -97,7 +109,7 @@ def main():
                 good_mode = mode
         print(json.dumps({"good_desc_mode": good_mode}), flush=True)
     if what in ("time", "all"):
-        mode = good_mode if good_mode is not None else modes[0]
+        mode = good_mode if good_mode is not None else "pipe"
         for T, D in TIMING:
             r = subprocess.run([sys.executable, __file__, "child", "time", str(T), str(D), str(mode)],
                                capture_output=True, text=True, timeout=300)
