@@ -143,9 +143,94 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "n_samples": len(self.samples)}
 
 
+def gpu_numa_cpus(torch, dev_index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None."""
+    try:
+        p = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None, node
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus, node
+    except Exception:
+        return None, None
+
+
+class PinnedHost:
+    """Page-locked host buffer from the C-ABI (b200_host_alloc), first-touched while the process is bound to
+    the GPU's NUMA node so its pages are local to the PCIe root the copies go through."""
+
+    def __init__(self, torch, nb, nbytes, dtype, dev_index):
+        import ctypes as C
+        self.nb, self.ptr = nb, C.c_void_p()
+        cpus, self.node = gpu_numa_cpus(torch, dev_index)
+        old = None
+        try:
+            if cpus:
+                old = os.sched_getaffinity(0)
+                allowed = cpus & old
+                if allowed:
+                    os.sched_setaffinity(0, allowed)
+            nb._check(nb.lib().b200_host_alloc(C.byref(self.ptr), nbytes))
+            buf = (C.c_byte * nbytes).from_address(self.ptr.value)
+            self.tensor = torch.frombuffer(buf, dtype=dtype)
+            self.tensor.zero_()                                   # first touch here, on the local node
+        finally:
+            if old is not None:
+                os.sched_setaffinity(0, old)
+
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            self.nb.lib().b200_host_free(self.ptr)
+            self.ptr = None
+
+
 def dist_env():
     return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
             int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def fir_executed(T, D, algo):
+    """Work the selected FIR kernel EXECUTES per input sample (not the direct-form algorithmic count), and the
+    pipe it runs on: algorithm 1 = direct FFMA2 form, 2 = block-Toeplitz GEMM on tcgen05 (bf16 hi/lo, four
+    partial products), 3 = overlap-save (4096-point transforms, 5 N log2 N flop each plus the spectrum product)."""
+    if algo == 1:
+        return 4.0 * T / D, "fp32"
+    if algo == 2:
+        tq = -(-T // D)
+        ksteps = ((tq - 1 + 15) // 16 * 16 + 64) // 16
+        tile = 4096 if (D == 1 and ksteps * 16 <= 512) else 8192       # outputs per tile (tap-stationary / ring form)
+        mma = 2 * 128 * (tile // 64) * 16                             # one 128 x (tile/64) x 16 MMA
+        return D * ksteps * 4 * mma / (tile * D), "tensor"
+    if algo == 3:
+        fft = 5 * 4096 * 12 + 6 * 4096
+        if D == 1 and T < 1024:
+            return 2 * fft / (4096 - (T - 1)), "fp32"
+        if D == 1:
+            return 4 * fft / (2 * (4095 - -(-T // 2))), "fp32"
+        return (D + 1) * fft / ((4096 - -(-T // D)) * D), "fp32"
+    return float("nan"), "fp32"
+
+
+def fir_record(gs, T, D, algo, peak_gbs, fp32_tf, bf16_tf, ms):
+    """One FIR measurement as a roofline record: HBM fraction from the ALGORITHMIC bytes (8 + 8/D per input
+    sample), and the executed-work fraction of the pipe the kernel runs on."""
+    flop, pipe = fir_executed(T, D, algo)
+    bps = 8 + 8.0 / D
+    rec = {"algorithm": algo, "Msamples_s": gs * 1e3, "ms": ms, "bound": "hbm", "unit": "GB/s",
+           "achieved": gs * bps, "peak": peak_gbs, "frac": gs * bps / peak_gbs,
+           "algorithmic_bytes_per_sample": bps, "executed_flop_per_sample": flop,
+           "executed_tflops": gs * flop / 1e3, "executed_on": pipe}
+    if pipe == "tensor" and bf16_tf:
+        rec["executed_frac_of_measured_bf16_peak"] = gs * flop / 1e3 / bf16_tf
+    elif fp32_tf:
+        rec["executed_frac_of_measured_fp32_peak"] = gs * flop / 1e3 / fp32_tf
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------
@@ -183,6 +268,31 @@ def cpu_fft_mag_rate(steps, warmup, target_s=0.5):
     }
 
 
+def cpu_fft_mag_rate_tuned(steps=3, nv=2048):
+    """The same workload through a tuned CPU library, for scale: scipy.fft (pocketfft, complex64 in / out,
+    workers = all host threads) + window + |.|.  Labelled as such; the reference arm itself stays the C port."""
+    import numpy as np
+    try:
+        import scipy.fft as sfft
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "error": repr(e)}
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    w = blackman_harris(N_FFT)
+    rng = np.random.default_rng(0x5EED)
+    x = (rng.uniform(-1, 1, (nv, N_FFT)) + 1j * rng.uniform(-1, 1, (nv, N_FFT))).astype(np.complex64)
+    np.abs(sfft.fft(x * w, axis=1, workers=cores))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        np.abs(sfft.fft(x * w, axis=1, workers=cores))
+    dt = time.perf_counter() - t0
+    return {"value": x.size * steps / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "tuned library",
+            "sample": f"{nv} vectors x {N_FFT} complex64 x {steps}: numpy window multiply + scipy.fft.fft(workers={cores}) "
+                      "(pocketfft, single precision) + numpy abs"}
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -195,6 +305,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": CONFIG,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_tuned_library": cpu_fft_mag_rate_tuned(),
         "e2e": {"value": cb["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -282,12 +393,19 @@ def run_b200(args):
                 "kernel": "fft4096_tma_kernel<fwd, mag> (TMA prefetch + window + 3x radix-16 + |.|)",
                 "algorithmic_bytes_per_sample": 12, "peak_source": peak_src,
                 "launch_ms": k_ms}
-    traffic_file = os.path.join(ROOT, "profiles", "r01_fft4096_traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel, stamped with the commit
+    # the capture was taken at (newest file wins)
+    for tf in ("r02_fft4096_traffic.json", "r01_fft4096_traffic.json"):
+        traffic_file = os.path.join(ROOT, "profiles", tf)
+        if os.path.exists(traffic_file):
+            try:
+                tj = json.load(open(traffic_file))
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = {"file": "profiles/" + tf, "captured_at_commit": tj.get("commit"),
+                                              "kernel_ms_under_ncu": tj.get("kernel_ms_under_ncu")}
+                break
+            except Exception:
+                pass
 
     # ---- e2e: host buffers through the C-ABI streaming call
     e2e = None
@@ -295,9 +413,10 @@ def run_b200(args):
         chunk = N_FFT * 512                             # 16 MiB in / 8 MiB out per chunk (measured best of 16/64/256:
         # the pipeline runs at the box's bidirectional PCIe limit, 76-78 GB/s of 75.8 measured with plain copies)
         chain = nb.Chain([fft], in_item_bytes=8, chunk_items=chunk)
-        hx = torch.empty(SAMPLES, dtype=torch.complex64).pin_memory()
+        phx = PinnedHost(torch, nb, SAMPLES * 8, torch.complex64, local_rank)
+        phy = PinnedHost(torch, nb, SAMPLES * 4, torch.float32, local_rank)
+        hx, hy = phx.tensor, phy.tensor
         hx.copy_(x)
-        hy = torch.empty(SAMPLES, dtype=torch.float32).pin_memory()
         e_steps = max(1, min(steps, 10))
         for _ in range(2):
             chain.run_host(hx, hy)
@@ -315,8 +434,38 @@ def run_b200(args):
                "h2d_bytes_per_step": SAMPLES * 8, "d2h_bytes_per_step": SAMPLES * 4,
                "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "matches_device_run": ok,
                "api": "b200_chain_run_host (pinned host in/out, 3-stream H2D/compute/D2H overlap)",
-               "pcie_gbs": (SAMPLES * 12 * e_steps) / dt / 1e9}
+               "pcie_gbs": (SAMPLES * 12 * e_steps) / dt / 1e9,
+               "host_buffers": f"b200_host_alloc, first touch bound to the GPU's NUMA node (node {phx.node})"}
+        # the box's own ceiling for this traffic pattern: the same bytes as plain page-locked copies, H2D and D2H
+        # concurrently on two streams, every rank at once, no kernel -- what the PCIe / host-memory fabric gives
+        try:
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            xin = torch.empty_like(x)
+
+            def copies():
+                with torch.cuda.stream(s_in):
+                    xin.copy_(hx, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hy.copy_(out, non_blocking=True)
+            copies()
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                copies()
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - t0
+            barrier()
+            dtc = max_over_ranks(dtc) / 3
+            e2e["ceiling"] = {"value": world * SAMPLES / dtc / 1e6, "unit": "Msamples/s", "pcie_gbs_per_gpu": SAMPLES * 12 / dtc / 1e9,
+                              "what": "1 GiB H2D + 0.5 GiB D2H as plain cudaMemcpyAsync on two streams, all ranks concurrently, no kernel"}
+            e2e["frac_of_ceiling"] = e2e["value"] / e2e["ceiling"]["value"]
+            del xin
+        except Exception as e:  # pragma: no cover
+            e2e["ceiling_error"] = repr(e)
         del hx, hy, chain
+        phx.free()
+        phy.free()
     except Exception as e:  # pragma: no cover
         e2e = {"value": None, "unit": "Msamples/s", "error": repr(e)}
 
@@ -329,59 +478,48 @@ def run_b200(args):
         rng = np.random.default_rng(1)
         fp32_tf, _ = nb.measure_fp32_tflops(8192)
         fp32_tf, _ = nb.measure_fp32_tflops(8192)
-        for T in (64, 256, 1024):
+        bf16_tf = float(peaks.get("bf16_tflops", 0) or 0)
+        for T in (64, 128, 256, 512, 1024):
             taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
             fir = nb.FirFilter(taps, 1)
             reps = max(3, min(steps, 20 if T <= 256 else 5))
             t = timed(torch, lambda: fir.work_segment(x1, None, y1), reps, 3, lambda: None) / reps
-            gs = n1 / (t * 1e-3) / 1e9
-            extras[f"fir_ccf_{T}taps_16Mi"] = {
-                "algorithm": fir.algorithm,   # 1 = direct FFMA2 form, 3 = overlap-save FFT (auto for >= 96 taps)
-                "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 4 * T / 1e3,
-                "frac_of_measured_fp32": gs * 4 * T / 1e3 / fp32_tf,
-                "hbm_gbs": gs * 16, "frac_of_hbm": gs * 16 / peak_gbs}
-        # the same 64-tap kernel on the whole 1 GiB stream: 16 Mi samples are 79 us of kernel, of which
-        # ~7 us are launch ramp and tail; a stream-sized call shows what the kernel sustains
-        taps = (rng.uniform(-1, 1, 64) / 64).astype(np.float32)
-        fir = nb.FirFilter(taps, 1)
+            extras[f"fir_ccf_{T}taps_16Mi"] = fir_record(n1 / (t * 1e-3) / 1e9, T, 1, fir.algorithm, peak_gbs, fp32_tf,
+                                                         bf16_tf, t)
+        # config 1's 64 taps through the SIMT direct form, for the A/B against the tensor-core form above
+        taps64 = (rng.uniform(-1, 1, 64) / 64).astype(np.float32)
+        fir = nb.FirFilter(taps64, 1, algorithm=1)
+        t = timed(torch, lambda: fir.work_segment(x1, None, y1), 10, 3, lambda: None) / 10
+        extras["fir_ccf_64taps_16Mi_simt_direct"] = fir_record(n1 / (t * 1e-3) / 1e9, 64, 1, 1, peak_gbs, fp32_tf, bf16_tf, t)
+        # the same 64-tap kernel on the whole 1 GiB stream (a 16 Mi-sample call is ~50 us, a few of them ramp and tail)
+        fir = nb.FirFilter(taps64, 1)
         y1b = torch.empty(SAMPLES, dtype=torch.complex64, device=dev)
         t = timed(torch, lambda: fir.work_segment(x, None, y1b), 5, 2, lambda: None) / 5
-        gs = SAMPLES / (t * 1e-3) / 1e9
-        extras["fir_ccf_64taps_128Mi"] = {
-            "algorithm": fir.algorithm, "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 256 / 1e3,
-            "frac_of_measured_fp32": gs * 256 / 1e3 / fp32_tf, "hbm_gbs": gs * 16, "frac_of_hbm": gs * 16 / peak_gbs}
+        extras["fir_ccf_64taps_128Mi"] = fir_record(SAMPLES / (t * 1e-3) / 1e9, 64, 1, fir.algorithm, peak_gbs, fp32_tf,
+                                                    bf16_tf, t)
         del y1b
-        # short decimating filters run folded into the same TMA-staged kernel: HBM-bound (10 B per input at D = 4)
+        # short decimating filters run folded into the TMA-staged SIMT kernel: HBM-bound (10 B per input at D = 4)
         for Td, Dd in ((32, 4), (64, 4), (64, 8)):
             taps = (rng.uniform(-1, 1, Td) / Td).astype(np.float32)
             fir = nb.FirFilter(taps, Dd)
             yd = torch.empty(SAMPLES // Dd, dtype=torch.complex64, device=dev)
             t = timed(torch, lambda: fir.work_segment(x, None, yd), 5, 2, lambda: None) / 5
-            gs = SAMPLES / (t * 1e-3) / 1e9
-            extras[f"fir_ccf_{Td}taps_decim{Dd}_128Mi"] = {
-                "algorithm": fir.algorithm, "Msamples_s": gs * 1e3, "ms": t,
-                "hbm_gbs": gs * (8 + 8 / Dd), "frac_of_hbm": gs * (8 + 8 / Dd) / peak_gbs,
-                "frac_of_measured_fp32": gs * 4 * Td / Dd / 1e3 / fp32_tf}
+            extras[f"fir_ccf_{Td}taps_decim{Dd}_128Mi"] = fir_record(SAMPLES / (t * 1e-3) / 1e9, Td, Dd, fir.algorithm,
+                                                                     peak_gbs, fp32_tf, bf16_tf, t)
             del yd
         taps = (rng.uniform(-1, 1, 1024) / 1024).astype(np.float32)
         fir = nb.FirFilter(taps, 4, multiply_const=0.5 - 0.25j)
         n3 = 1 << 26
         y3 = torch.empty(n3 // 4, dtype=torch.complex64, device=dev)
         t = timed(torch, lambda: fir.work_segment(x[:n3], None, y3), 3, 2, lambda: None) / 3
-        gs = n3 / (t * 1e-3) / 1e9
-        extras["fir_ccf_1024taps_decim4_mulc_64Mi"] = {
-            "Msamples_s": gs * 1e3, "ms": t, "tflops": gs * 1024 / 1e3,
-            "frac_of_measured_fp32": gs * 1024 / 1e3 / fp32_tf}
-        extras["fir_ccf_1024taps_decim4_mulc_64Mi"]["algorithm"] = fir.algorithm  # 3 = overlap-save FFT
-        extras["fir_ccf_1024taps_decim4_mulc_64Mi"]["note"] = (
-            "tflops = direct-form algorithmic flops (1024/sample) / time; overlap-save executes fewer")
+        extras["fir_ccf_1024taps_decim4_mulc_64Mi"] = fir_record(n3 / (t * 1e-3) / 1e9, 1024, 4, fir.algorithm, peak_gbs,
+                                                                 fp32_tf, bf16_tf, t)
         taps = (rng.uniform(-1, 1, 4096) / 4096).astype(np.float32)
         fir5 = nb.FirFilter(taps, 1)
         y5 = torch.empty(n3, dtype=torch.complex64, device=dev)
         t = timed(torch, lambda: fir5.work_segment(x[:n3], None, y5), 3, 2, lambda: None) / 3
-        extras["fir_ccf_4096taps_64Mi"] = {"Msamples_s": n3 / (t * 1e-3) / 1e6, "ms": t,
-                                          "algorithm": fir5.algorithm,
-                                          "direct_form_equiv_tflops": n3 * 4 * 4096 / (t * 1e-3) / 1e12}
+        extras["fir_ccf_4096taps_64Mi"] = fir_record(n3 / (t * 1e-3) / 1e9, 4096, 1, fir5.algorithm, peak_gbs, fp32_tf,
+                                                     bf16_tf, t)
         del y5
         extras["fp32_fma_tflops_measured"] = fp32_tf
         yc = torch.empty(SAMPLES, dtype=torch.complex64, device=dev)
@@ -564,20 +702,42 @@ def run_b200(args):
             except Exception as e:  # pragma: no cover
                 extras["config4_error"] = repr(e)
 
-    cpu_baseline = None
+    cpu_baseline, cpu_tuned = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_fft_mag_rate(10, 1, target_s=1.5)
             cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "error": repr(e)}
+        try:
+            cpu_tuned = cpu_fft_mag_rate_tuned()
+        except Exception as e:  # pragma: no cover
+            cpu_tuned = {"value": None, "error": repr(e)}
+
+    # ---- the metric names "FIR-ccf & FFT-4096": every config's dominant kernel as a roofline row, at top level
+    kernels = {"config2_fft4096_window_mag_1Gi": {k: roofline[k] for k in ("bound", "achieved", "peak", "frac", "unit")}}
+    kernels["config2_fft4096_window_mag_1Gi"]["ms"] = k_ms
+    for name, key in (("config1_fir_ccf_64taps_16Mi", "fir_ccf_64taps_16Mi"),
+                      ("config1_fir_ccf_64taps_16Mi_simt_direct", "fir_ccf_64taps_16Mi_simt_direct"),
+                      ("config3_head_fir_ccf_1024taps_decim4_mulc_64Mi", "fir_ccf_1024taps_decim4_mulc_64Mi"),
+                      ("config5_body_fir_ccf_4096taps_64Mi", "fir_ccf_4096taps_64Mi")):
+        if key in extras:
+            kernels[name] = {k: extras[key][k] for k in extras[key]
+                             if k in ("algorithm", "bound", "achieved", "peak", "frac", "unit", "ms", "executed_tflops",
+                                      "executed_on", "executed_frac_of_measured_bf16_peak",
+                                      "executed_frac_of_measured_fp32_peak")}
+    if "pfb_channelizer_64ch_16tpc_1Gi" in extras:
+        e4 = extras["pfb_channelizer_64ch_16tpc_1Gi"]
+        kernels["config4_pfb_channelizer_64ch_1Gi"] = {"bound": "hbm", "achieved": e4["hbm_gbs"], "peak": peak_gbs,
+                                                       "frac": e4["frac_of_hbm"], "unit": "GB/s", "ms": e4["ms"]}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "cpu_tuned_library": cpu_tuned, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": sampler.summary(), "extras": extras,
             "gpu_name": torch.cuda.get_device_name(dev),
         }

@@ -9,6 +9,10 @@
 #pragma once
 #include <gnuradio/blocklib/cuda/cuda_block.hpp>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace gr {
 namespace cuda {
 
@@ -43,6 +47,15 @@ public:
         d_taps = taps;
         build();
     }
+    // Time-segment sharding (BASELINE config 5): the (ntaps-1) items that precede this block's
+    // segment, read from DEVICE memory -- typically the tail of the left neighbour GPU's resident segment, a
+    // peer copy over NVLink on this block's stream (b200_enable_peer_access makes it a direct one).
+    void set_history_device(const void* d_hist)
+    {
+        check(b200_stream_activate(d_stream), "cuda::fir_filter");
+        check(b200_fir_set_history(d_fir, d_hist, d_stream), "cuda::fir_filter");
+    }
+    int algorithm() const { return b200_fir_algorithm(d_fir); }
     std::vector<float> taps() const { return d_taps; }
     bool has_fused_multiply_const() const { return d_fuse; }
     size_t decimation() const { return d_decim; }
@@ -54,10 +67,21 @@ public:
         int64_t n_in = std::min<int64_t>(work_input[0].n_items, (int64_t)work_output[0].n_items * (int64_t)d_decim);
         int64_t nc = 0, np = 0;
         if (n_in >= (int64_t)d_decim) {
+            static const bool trace = getenv("B200_TRACE_FIR") != nullptr;
+            auto t0 = std::chrono::steady_clock::now();
             work_guard g(work_input, work_output, d_stream);
+            auto t1 = std::chrono::steady_clock::now();
             check(b200_fir_run(d_fir, work_input[0].buffer->read_ptr(), work_output[0].buffer->write_ptr(),
                                n_in, &nc, &np, d_stream),
                   "cuda::fir_filter");
+            if (trace) {
+                auto t2 = std::chrono::steady_clock::now();
+                std::fprintf(stderr, "fir work: t=%.1f us n_in=%lld guard %.1f us run %.1f us in=%p out=%p\n",
+                             std::chrono::duration<double, std::micro>(t0.time_since_epoch()).count(), (long long)n_in,
+                             std::chrono::duration<double, std::micro>(t1 - t0).count(),
+                             std::chrono::duration<double, std::micro>(t2 - t1).count(), work_input[0].buffer->read_ptr(),
+                             work_output[0].buffer->write_ptr());
+            }
         }
         work_input[0].n_consumed = (int)nc;
         work_output[0].n_produced = (int)np;

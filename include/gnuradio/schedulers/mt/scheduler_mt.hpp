@@ -22,6 +22,9 @@
 #include <gnuradio/scheduler.hpp>
 #include <gnuradio/vmcircbuf.hpp>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <exception>
@@ -82,6 +85,8 @@ class thread_wrapper : public neighbor_interface
     bool _notified = false;
     std::atomic<bool> _stop{ false }, _started{ false };
     std::exception_ptr _error = nullptr;
+    std::vector<unsigned int> _affinity; // CPUs this thread may run on (empty: anywhere); thread_wrapper.cpp:23-31
+    bool _rt_prio = false;
 
     void finish_block(size_t bi)
     {
@@ -279,10 +284,24 @@ public:
         }
         _cv.notify_one();
     }
+    void set_affinity(const std::vector<unsigned int>& cpus) { _affinity = cpus; }
+    void set_rt_prio(bool on) { _rt_prio = on; }
     void start()
     {
         _started = true;
         _thread = std::thread([this] { thread_body(); });
+        if (!_affinity.empty()) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (auto c : _affinity)
+                CPU_SET(c % CPU_SETSIZE, &set);
+            pthread_setaffinity_np(_thread.native_handle(), sizeof(set), &set); // best effort, like the reference
+        }
+        if (_rt_prio) {
+            sched_param sp{};
+            sp.sched_priority = sched_get_priority_min(SCHED_FIFO);
+            pthread_setschedparam(_thread.native_handle(), SCHED_FIFO, &sp); // needs CAP_SYS_NICE; ignored otherwise
+        }
     }
     void stop()
     {
@@ -303,6 +322,9 @@ class scheduler_mt : public scheduler
 {
     const int s_fixed_buf_size;
     std::vector<std::vector<block_sptr>> _block_groups;
+    std::vector<std::vector<unsigned int>> _group_affinity;
+    std::vector<unsigned int> _thread_cpus; // round-robin over the per-block threads (bm_copy.cpp --cpus)
+    bool _rt_prio = false;
     std::vector<thread_wrapper::sptr> _threads;
     buffer_manager::sptr _bufman;
 
@@ -319,10 +341,13 @@ public:
         _default_buf_properties = vmcirc_buffer_properties::make(vmcirc_buffer_type::AUTO);
     }
     void add_block_group(const std::vector<block_sptr>& blocks, const std::string& = "",
-                         const std::vector<unsigned int>& = {})
+                         const std::vector<unsigned int>& cpu_affinity = {})
     {
         _block_groups.push_back(blocks);
+        _group_affinity.push_back(cpu_affinity);
     }
+    void set_thread_affinity(const std::vector<unsigned int>& cpus) { _thread_cpus = cpus; }
+    void set_rt_prio(bool on) { _rt_prio = on; }
     buffer_manager::sptr buffers() { return _bufman; }
 
     void initialize(flat_graph_sptr fg) override
@@ -331,20 +356,26 @@ public:
         _bufman->initialize_buffers(fg, _default_buf_factory, _default_buf_properties);
         auto blocks = fg->calc_used_blocks();
         std::vector<block_sptr> grouped;
-        auto make_thread = [&](const std::vector<block_sptr>& grp) {
+        auto make_thread = [&](const std::vector<block_sptr>& grp, const std::vector<unsigned int>& aff) {
             auto t = std::make_shared<thread_wrapper>(grp, _bufman);
             for (auto& b : grp)
                 for (auto& p : b->all_ports())
                     p->set_parent_intf(t);
+            if (!aff.empty())
+                t->set_affinity(aff);
+            else if (!_thread_cpus.empty())
+                t->set_affinity({ _thread_cpus[_threads.size() % _thread_cpus.size()] });
+            t->set_rt_prio(_rt_prio);
             _threads.push_back(t);
         };
-        for (auto& grp : _block_groups) {
-            make_thread(grp);
+        for (size_t gi = 0; gi < _block_groups.size(); gi++) {
+            auto& grp = _block_groups[gi];
+            make_thread(grp, _group_affinity[gi]);
             grouped.insert(grouped.end(), grp.begin(), grp.end());
         }
         for (auto& b : blocks)
             if (std::find(grouped.begin(), grouped.end(), b) == grouped.end())
-                make_thread({ b });
+                make_thread({ b }, {});
         for (auto& b : blocks) {
             std::vector<buffer_sptr> ins;
             std::vector<std::vector<buffer_sptr>> outs;
@@ -369,24 +400,24 @@ public:
     {
         for (auto& t : _threads)
             t->wait();
-        std::exception_ptr first = nullptr;
         for (auto& t : _threads)
-            if (t->error() && !first)
-                first = t->error();
-        // the run is over: drop the threads and the edge buffers now (device rings, pinned staging, streams,
-        // events) instead of when the last reference to the scheduler happens to go away
-        _threads.clear();
-        _bufman.reset();
-        if (first)
-            std::rethrow_exception(first); // first failure, after every thread has stopped
+            if (t->error())
+                std::rethrow_exception(t->error()); // first failure, after every thread has stopped
     }
-    ~scheduler_mt() override
+    // Drops the threads and the edge buffers (device rings, pinned staging, streams, events).  Not done inside
+    // wait(): unmapping a 256 MiB VMM ring or unpinning 128 MiB of host memory takes milliseconds and would
+    // land inside every start()->wait() timing.  The destructor calls it; nothing keeps the scheduler alive
+    // once the flowgraph goes (ports and neighbours hold weak references only).
+    void release()
     {
         for (auto& t : _threads) {
             t->stop();
             t->wait();
         }
+        _threads.clear();
+        _bufman.reset();
     }
+    ~scheduler_mt() override { release(); }
 };
 
 } // namespace schedulers

@@ -712,11 +712,15 @@ constexpr int TS_IN_STAGES = 3;           // staging ring (raw input tiles)
 constexpr int TS_A_COLS = 256;
 constexpr uint32_t TS_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TS_NROW >> 3) << 17) | ((128u >> 4) << 24);
 
-// interior tile: its whole input span [j0, j0 + plane_elems) lies inside this call's stream and is 16-byte aligned,
-// so it can travel as ONE bulk copy; edge tiles (history in front, ragged end) are read element-wise
+// interior tile: its whole input span [j0, j0 + plane_elems) lies inside this call's stream, so it can travel as
+// ONE bulk copy; edge tiles (history in front, ragged end) are read element-wise.  A ring hands out windows
+// that start on any item (8 bytes): when x is only 8-byte aligned the copy starts one sample early (`shift` = 1,
+// the bulk copy needs 16-byte alignment) and the converters skip that sample.
+__device__ __forceinline__ int ts_shift(const tc_args& a) { return (int)((reinterpret_cast<uintptr_t>(a.x) >> 3) & 1); }
 __device__ __forceinline__ bool ts_fast_tile(const tc_args& a, long long j0)
 {
-    return j0 >= 0 && j0 + a.ts_plane_elems <= a.n_in && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    const int sh = ts_shift(a);
+    return j0 - sh >= 0 && j0 + a.ts_plane_elems + sh <= a.n_in;
 }
 
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
@@ -842,12 +846,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
             const int slot = nf % TS_IN_STAGES;
             mbar_wait(&in_empty[slot], ((nf / TS_IN_STAGES) & 1) ^ 1);
             if (lane == 0) {
-                const uint32_t bytes = (uint32_t)a.ts_plane_elems * 8u;
+                const int sh = ts_shift(a);
+                const uint32_t bytes = (uint32_t)(a.ts_plane_elems + 2 * sh) * 8u;
                 if (a.dbg & 8) {
                     mbar_arrive(&in_full[slot]);
                 } else {
                     mbar_arrive_expect_tx(&in_full[slot], bytes);
-                    bulk_copy_g2s(staging + (size_t)slot * a.ts_stage_bytes, a.x + j0, bytes, &in_full[slot]);
+                    bulk_copy_g2s(staging + (size_t)slot * a.ts_stage_bytes, a.x + j0 - sh, bytes, &in_full[slot]);
                 }
             }
             __syncwarp();
@@ -909,11 +914,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
                 const int slot = nf % TS_IN_STAGES;
                 mbar_wait(&in_full[slot], (nf / TS_IN_STAGES) & 1);
                 if (!(a.dbg & 1)) {
-                    const float4* src = reinterpret_cast<const float4*>(staging + (size_t)slot * a.ts_stage_bytes);
+                    const float2* src = reinterpret_cast<const float2*>(staging + (size_t)slot * a.ts_stage_bytes) + ts_shift(a);
                     const int npairs = a.ts_plane_elems >> 1;
+                    const bool al16 = ts_shift(a) == 0;
 #pragma unroll 4
                     for (int q = ctid; q < npairs; q += TS_CONV) {
-                        const float4 v = src[q];
+                        float4 v;
+                        if (al16) {
+                            v = *reinterpret_cast<const float4*>(src + 2 * q);
+                        } else {
+                            const float2 s0 = src[2 * q], s1 = src[2 * q + 1];
+                            v = make_float4(s0.x, s0.y, s1.x, s1.y);
+                        }
                         const __nv_bfloat162 rh = __floats2bfloat162_rn(v.x, v.z);
                         const __nv_bfloat162 ih = __floats2bfloat162_rn(v.y, v.w);
                         const float2 rhf = __bfloat1622float2(rh), ihf = __bfloat1622float2(ih);
@@ -1085,7 +1097,7 @@ int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre
         }
         p->ts_plane_elems = TC_PH * (TS_NROW - 1) + K;
         p->ts_plane_bytes = ((p->ts_plane_elems + 63) / 64 * 128 + 1023) / 1024 * 1024;
-        p->ts_stage_bytes = (p->ts_plane_elems * 8 + 1023) / 1024 * 1024;
+        p->ts_stage_bytes = (p->ts_plane_elems * 8 + 16 + 1023) / 1024 * 1024; // + one sample each side for 8-byte-aligned streams
         int st = TS_MAX_STAGES;
         while (st > 2 && 1024 + (size_t)st * 4 * p->ts_plane_bytes + (size_t)TS_IN_STAGES * p->ts_stage_bytes + 256 > 227 * 1024)
             st--;

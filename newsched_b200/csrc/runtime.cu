@@ -33,18 +33,19 @@ int set_err(int code, const char* fmt, ...)
 
 int sm_count()
 {
-    static thread_local int cached_dev = -1, cached = 0;
+    // per-device, process-wide cache.  (Round 1 cached per THREAD and asked cudaGetDeviceProperties, which takes
+    // 5-10 ms: every new scheduler thread paid that inside its first work() call -- most of a 10 ms flowgraph run.)
+    static std::atomic<int> cache[64];
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess)
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
         return 148;
-    if (dev != cached_dev) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess)
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             return 148;
-        cached = p.multiProcessorCount;
-        cached_dev = dev;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
 }
 
 tmap_encode_fn tmap_encode_tiled()

@@ -16,6 +16,7 @@
 #include <gnuradio/blocklib/cuda/pfb_channelizer.hpp>
 #include <gnuradio/blocklib/cuda/rational_resampler.hpp>
 #include <gnuradio/blocklib/cuda/stream_to_vector.hpp>
+#include <gnuradio/blocklib/cuda/vector_source.hpp>
 #include <gnuradio/cudabuffer.hpp>
 #include <gnuradio/cudabuffer_pinned.hpp>
 #include <gnuradio/flowgraph.hpp>
@@ -567,6 +568,100 @@ QA_TEST(SchedulerMTTags, TagsAcrossDeviceBuffers)
     for (size_t i = 0; ok && i < tags.size(); i++)
         ok &= got[i] == tags[i];
     EXPECT_TRUE(ok);
+}
+
+// BASELINE config 5 as ONE newsched flowgraph on several GPUs of one process (SURVEY.md 8e "single process,
+// 8 devices"; reference edges are created per flowgraph in one process,
+// schedulers/mt/lib/buffer_management.cpp:78-82): a long stream is cut into time segments, GPU g owns
+// segment g resident in its memory, filters it with the 4096-tap FIR and needs the 4095 samples that
+// precede it -- a peer copy from GPU g-1's segment, ordered on the FIR block's stream.  Every block,
+// ring, stream and event lives on its own device; one mt scheduler drives them all.  Oracle-checked.
+static void time_segmented_fir(int G, size_t n_all, int T)
+{
+    auto x = noise(n_all, 77);
+    auto taps = rtaps(T, 78);
+    const size_t seg = n_all / G;
+    std::vector<std::shared_ptr<cuda::vector_source_c>> src(G);
+    std::vector<std::shared_ptr<cuda::fir_filter_ccf>> fir(G);
+    std::vector<std::shared_ptr<blocks::vector_sink_c>> snk(G);
+    auto fg = flowgraph::make();
+    for (int g = 0; g < G; g++) {
+        EXPECT_EQ(b200_set_device(g), 0);
+        std::vector<gr_complex> part(x.begin() + g * seg, x.begin() + (g + 1) * seg);
+        src[g] = cuda::vector_source_c::make(part);
+        fir[g] = cuda::fir_filter_ccf::make(1, taps);
+        snk[g] = blocks::vector_sink_c::make(1, seg);
+        EXPECT_EQ(src[g]->device(), g);
+        EXPECT_EQ(fir[g]->device(), g);
+        fg->connect(src[g], 0, fir[g], 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_ON(D2D, 8u << 20, g));
+        fg->connect(fir[g], 0, snk[g], 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_ON(D2H, 8u << 20, g));
+    }
+    for (int g = 1; g < G; g++) { // halo: tail of the left neighbour's segment, device to device
+        EXPECT_EQ(b200_set_device(g), 0);
+        EXPECT_EQ(b200_enable_peer_access(g - 1), 0);
+        fir[g]->set_history_device(src[g - 1]->device_data() + seg - (T - 1));
+    }
+    b200_set_device(0);
+    fg->set_scheduler(schedulers::scheduler_mt::make("sched", 32768));
+    fg->validate();
+    fg->run();
+    std::vector<gr_complex> got;
+    for (int g = 0; g < G; g++) {
+        auto d = snk[g]->data();
+        EXPECT_EQ(d.size(), seg);
+        got.insert(got.end(), d.begin(), d.end());
+    }
+    std::vector<gr_complex> ref(n_all);
+    orc_fir_ccf_f64((float*)ref.data(), (const float*)x.data(), (int64_t)n_all, taps.data(), T, 1, nullptr);
+    const double err = rel_rms(got, ref);
+    std::printf("  %d GPUs, %zu samples, %d taps (algorithm %d): rel rms %.3g\n", G, n_all, T, fir[0]->algorithm(), err);
+    EXPECT_TRUE(err < TOL);
+}
+QA_TEST(Config5, TimeSegmentedTwoGpus)
+{
+    int ngpu = 0;
+    b200_device_count(&ngpu);
+    if (ngpu < 2) {
+        std::printf("  skipped: needs 2 GPUs (found %d)\n", ngpu);
+        return;
+    }
+    time_segmented_fir(2, (size_t)1 << 21, 4096);
+    time_segmented_fir(2, (size_t)1 << 20, 128); // tensor-core form
+    b200_set_device(0);
+}
+// the same flowgraph shape on ONE device: every piece of the multi-device plumbing except the peer copy
+QA_TEST(Config5, TimeSegmentedOneGpuTwoSegments)
+{
+    const size_t n_all = (size_t)1 << 20;
+    const int T = 4096, G = 2;
+    auto x = noise(n_all, 79);
+    auto taps = rtaps(T, 80);
+    const size_t seg = n_all / G;
+    std::vector<std::shared_ptr<cuda::vector_source_c>> src(G);
+    std::vector<std::shared_ptr<cuda::fir_filter_ccf>> fir(G);
+    std::vector<std::shared_ptr<blocks::vector_sink_c>> snk(G);
+    auto fg = flowgraph::make();
+    for (int g = 0; g < G; g++) {
+        std::vector<gr_complex> part(x.begin() + g * seg, x.begin() + (g + 1) * seg);
+        src[g] = cuda::vector_source_c::make(part);
+        fir[g] = cuda::fir_filter_ccf::make(1, taps);
+        snk[g] = blocks::vector_sink_c::make(1, seg);
+        fg->connect(src[g], 0, fir[g], 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_ON(D2D, 8u << 20, 0));
+        fg->connect(fir[g], 0, snk[g], 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_ON(D2H, 8u << 20, 0));
+    }
+    fir[1]->set_history_device(src[0]->device_data() + seg - (T - 1));
+    fg->set_scheduler(schedulers::scheduler_mt::make("sched", 32768));
+    fg->validate();
+    fg->run();
+    std::vector<gr_complex> got;
+    for (int g = 0; g < G; g++) {
+        auto d = snk[g]->data();
+        got.insert(got.end(), d.begin(), d.end());
+    }
+    std::vector<gr_complex> ref(n_all);
+    orc_fir_ccf_f64((float*)ref.data(), (const float*)x.data(), (int64_t)n_all, taps.data(), T, 1, nullptr);
+    EXPECT_EQ(got.size(), n_all);
+    EXPECT_TRUE(rel_rms(got, ref) < TOL);
 }
 
 int main(int argc, char** argv) { return qa_main(argc, argv); }

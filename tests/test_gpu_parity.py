@@ -189,9 +189,16 @@ def test_fir_impulse_and_decimation_phase_exact(cuda, golden):
     taps = golden["fir_imp_taps"]
     imp = np.zeros(4096, np.complex64)
     imp[0] = 1
-    y, _ = nb.FirFilter(taps, 1).work(dev(cuda, imp))
+    y, _ = nb.FirFilter(taps, 1, algorithm=1).work(dev(cuda, imp))
     y = host(y)
     assert np.array_equal(y[:48].real, taps) and not y[48:].any() and not y.imag.any()
+    # 48 taps at full rate are auto-routed to the tensor-core form: indexing (where the response starts and
+    # ends, nothing in the imaginary plane) is exact, the values carry the bf16 hi+lo split (<= 2^-17 relative)
+    f2 = nb.FirFilter(taps, 1)
+    assert f2.algorithm == 2
+    y2 = host(f2.work(dev(cuda, imp))[0])
+    assert not y2[48:].any() and not y2.imag.any()
+    assert np.allclose(y2[:48].real, taps, rtol=2.0 ** -16, atol=0)
     for D in (2, 3, 4, 7):
         yd, _ = nb.FirFilter(taps, D).work(dev(cuda, imp))
         yd = host(yd)
@@ -604,10 +611,67 @@ def test_fir_real_stream_as_float_pairs(cuda, T):
     assert o.rel_rms(one, host(ys)) < TOL_RMS
 
 
+@pytest.mark.parametrize("T,D", [(5, 1), (33, 1), (64, 1), (100, 1), (128, 1), (256, 1), (384, 1), (448, 1), (449, 1),
+                                 (1024, 1), (96, 3), (512, 2), (1024, 4), (2048, 8)])
+def test_fir_tensor_core_form(cuda, T, D):
+    """algorithm 2: block-Toeplitz GEMM on tcgen05 (bf16 hi/lo split, fp32 accumulation in TMEM).  Tap-stationary
+    persistent kernel for D = 1 and K <= 512 (T <= 448), ring form beyond and for D > 1.  Against the fp64
+    oracle: one shot, any 8-byte pointer alignment (a ring hands out windows on item boundaries), chunked
+    streaming with ragged chunks, a time segment with its halo, and the fused multiply_const epilogue."""
+    import newsched_b200 as nb
+    rng = np.random.default_rng(T * 7 + D)
+    n = (4096 * 150 * 2 + 1234) * D + (D - 1)           # > 2 tiles per SM for the persistent form, ragged tail
+    x = cplx(rng, n + 1)
+    taps = (rng.uniform(-1, 1, T) / np.sqrt(T)).astype(np.float32)
+    dx = dev(cuda, x)
+    ref = o.fir(x[:n], taps, D, mt=True)
+    f = nb.FirFilter(taps, D, algorithm=2)
+    assert f.algorithm == 2
+    y, nc = f.work(dx[:n])
+    assert nc == (n // D) * D and o.rel_rms(host(y), ref) < TOL_RMS
+    # an 8-byte-only aligned input / output window
+    f1 = nb.FirFilter(taps, D, algorithm=2)
+    buf = cuda.zeros(n // D + 3, dtype=cuda.complex64, device="cuda")
+    y1, _ = f1.work(dx[1:], buf[1:1 + n // D])
+    assert o.rel_rms(host(y1), o.fir(x[1:], taps, D, mt=True)) < TOL_RMS and buf[0].item() == 0 and buf[-1].item() == 0
+    # streaming in ragged chunks: the history carries over
+    f2 = nb.FirFilter(taps, D, algorithm=2)
+    outs, pos = [], 0
+    for c in (7 * D, 4096 * D + D, 100003 * D, n):
+        c = min(c, n - pos)
+        if c <= 0:
+            break
+        yy, used = f2.work(dx[pos:pos + c])
+        outs.append(host(yy))
+        pos += used
+    got = np.concatenate(outs)
+    assert o.rel_rms(got, ref[: got.size]) < TOL_RMS and got.size >= ref.size - 1
+    # a time segment with its halo (multi-GPU sharding) == the same outputs of the whole stream
+    cut = (4096 * 100 + 8) * D
+    seg = f.work_segment(dx[cut:n], dx[cut - (T - 1):cut] if T > 1 else None)
+    assert o.rel_rms(host(seg), ref[cut // D:]) < TOL_RMS
+    # fused multiply_const epilogue
+    k = 0.5 - 0.25j
+    yk, _ = nb.FirFilter(taps, D, algorithm=2, multiply_const=k).work(dx[:n])
+    assert o.rel_rms(host(yk), ref * np.complex64(k)) < TOL_RMS
+
+
+def test_fir_tensor_core_form_rejects_what_it_cannot_do(cuda):
+    import newsched_b200 as nb
+    with pytest.raises(nb.B200Error):
+        nb.FirFilter(np.ones(64, np.float32), 1, is_complex=False, algorithm=2)    # real streams: SIMT forms
+    with pytest.raises(nb.B200Error):
+        nb.FirFilter(np.ones(64, np.float32), 9, algorithm=2)                      # decimation > 8
+
+
 def test_fir_auto_algorithm_choice(cuda):
     import newsched_b200 as nb
-    t = np.ones(64, np.float32)
-    assert nb.FirFilter(t, 1).algorithm == 1                      # short: direct FFMA2 form
+    assert nb.FirFilter(np.ones(32, np.float32), 1).algorithm == 1     # short: direct FFMA2 form (HBM-bound)
+    assert nb.FirFilter(np.ones(64, np.float32), 1).algorithm == 2     # config 1: block-Toeplitz GEMM on tcgen05
+    assert nb.FirFilter(np.ones(384, np.float32), 1).algorithm == 2
+    assert nb.FirFilter(np.ones(385, np.float32), 1).algorithm == 3    # beyond: overlap-save
+    assert nb.FirFilter(np.ones(64, np.float32), 1, is_complex=False).algorithm == 1   # real streams stay SIMT
+    assert nb.FirFilter(np.ones(64, np.float32), 1, algorithm=1).algorithm == 1        # and the SIMT forms stay selectable
     assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
     assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 3
     assert nb.FirFilter(np.ones(300, np.float32), 40).algorithm == 3   # huge D: overlap-save instead of the fallback
@@ -684,11 +748,13 @@ def test_fir_config1_size_linearity(cuda):
         assert o.rel_rms(host(y1[s:s + 4096]), ref) < TOL_RMS
 
 
-@pytest.mark.parametrize("T,D,log2n", [(1024, 4, 28), (4096, 1, 27), (256, 1, 26)])
-def test_fir_long_filters_full_size_properties(cuda, T, D, log2n):
+@pytest.mark.parametrize("T,D,log2n,algo", [(1024, 4, 28, 3), (4096, 1, 27, 3), (512, 1, 26, 3), (256, 1, 26, 2),
+                                             (64, 1, 27, 2)])
+def test_fir_long_filters_full_size_properties(cuda, T, D, log2n, algo):
     """BASELINE config 3 head (2^28 samples, 1024 taps, decim 4: polyphase overlap-save), config 5
-    per-GPU segment (2^27 samples, 4096 taps: two-phase overlap-save) and a one-phase overlap-save
-    size, through size-independent properties: linearity, oracle spot checks on windows at the
+    per-GPU segment (2^27 samples, 4096 taps: two-phase overlap-save), a one-phase overlap-save
+    size and two tensor-core (tcgen05 block-Toeplitz) sizes incl. config 1's 64 taps on a 1 GiB stream,
+    through size-independent properties: linearity, oracle spot checks on windows at the
     start / middle / end of the stream, and the response to impulses placed deep in the stream
     (output index = input index / D exactly: decimation phase and 64-bit indexing)."""
     import newsched_b200 as nb
@@ -699,7 +765,7 @@ def test_fir_long_filters_full_size_properties(cuda, T, D, log2n):
     rng = np.random.default_rng(T)
     taps = (rng.uniform(-1, 1, T) / np.sqrt(T)).astype(np.float32)
     f = nb.FirFilter(taps, D)
-    assert f.algorithm == 3
+    assert f.algorithm == algo
     y1 = f.work_segment(x1)
     y2 = f.work_segment(x2)
     x1 += x2

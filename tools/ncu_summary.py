@@ -10,7 +10,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size"]
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 out = {}
 for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_raw.csv"))):
@@ -29,12 +32,26 @@ for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_raw.csv"))):
         rec["dram_bytes_per_launch"] = rec["dram__bytes_read.sum"] + rec["dram__bytes_write.sum"]
     out[os.path.basename(path).replace("_raw.csv", "")] = rec
 json.dump(out, open(os.path.join(ROOT, "profiles", "SUMMARY.json"), "w"), indent=1)
-latest = [k for k in sorted(out) if k.startswith("r01_fft4096_mag")]
-if latest:
+import subprocess
+for rnd in ("r01", "r02"):
+    latest = [k for k in sorted(out) if k.startswith(rnd + "_fft4096_mag")]
+    if not latest:
+        continue
     r = out[latest[-1]]
-    json.dump({"source": latest[-1] + "_raw.csv (ncu --set full, one launch, 2^27 samples)",
-               "dram_bytes_per_launch": r["dram_bytes_per_launch"],
-               "algorithmic_bytes_per_launch": 12 * 4096 * 32768},
-              open(os.path.join(ROOT, "profiles", "r01_fft4096_traffic.json"), "w"), indent=1)
+    rec = {"source": latest[-1] + "_raw.csv (ncu --set full, one launch, 2^27 samples)",
+           "dram_bytes_per_launch": r["dram_bytes_per_launch"],
+           "algorithmic_bytes_per_launch": 12 * 4096 * 32768,
+           "kernel_ms_under_ncu": r.get("gpu__time_duration.sum", 0) / 1e3}
+    path = os.path.join(ROOT, "profiles", rnd + "_fft4096_traffic.json")
+    if rnd != "r01":
+        try:    # commit whose build produced the capture: recorded next to the csv by the capture script, else HEAD
+            cfile = os.path.join(ROOT, "profiles", latest[-1] + "_commit.txt")
+            rec["commit"] = open(cfile).read().strip() if os.path.exists(cfile) else subprocess.check_output(
+                ["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], text=True).strip()
+        except Exception:
+            pass
+    elif os.path.exists(path):
+        continue
+    json.dump(rec, open(path, "w"), indent=1)
 for k, r in out.items():
     print(k, {kk: (round(v, 2) if isinstance(v, float) else v) for kk, v in r.items() if kk != "kernel"})
