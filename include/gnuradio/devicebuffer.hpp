@@ -10,7 +10,8 @@
 //     read_ptr()/write_ptr() windows are linearly addressable with no mirror copies -- the
 //     reference copies every written span a second time (cudabuffer.cu:130-169);
 //   * nothing synchronises the device on a D2D edge: ordering between the producer's and the
-//     consumer's streams is carried by two CUDA events owned by the buffer (written / read);
+//     consumer's streams is carried by CUDA events owned by the buffer, each tagged with the item
+//     position it covers, so a waiter waits for exactly the lap of the ring it is about to touch;
 //     the reference calls cudaStreamSynchronize under the buffer mutex in every post_write
 //     (cudabuffer.cu:118,175);
 //   * the ring is sized from the PROPERTIES (default 64 MiB), not from the scheduler's
@@ -102,7 +103,42 @@ class device_buffer : public buffer, public stream_ordered_buffer, public host_d
     uint8_t* _dev = nullptr;
     uint8_t* _host = nullptr; // pinned staging (H2D: producer side, D2H: consumer side)
     b200_stream_t _stream = nullptr;
-    b200_event_t _ev_written = nullptr, _ev_read = nullptr;
+
+    // ---- ordering across streams, by POSITION.  One event per direction ("all writes / all reads enqueued so
+    // far") orders more than the ring needs: with several chunks in flight the H2D copy of chunk k+1 would wait
+    // for the kernel that read chunk k, which waits for the copy of chunk k -- copies and kernels take turns and
+    // the PCIe link idles between them (configs[0]: 2.6 GS/s).  What a writer of [W, W+n) really needs is that the
+    // reads of the items that occupied that space ONE LAP AGO are done, i.e. reads up to item W+n-capacity; a
+    // reader of [R, R+n) needs the writes up to R+n.  Every recorded event is therefore kept with the cumulative
+    // item count it covers, and a waiter picks the OLDEST event that covers its position (usually long complete).
+    struct mark {
+        b200_event_t ev = nullptr;
+        uint64_t pos = 0;
+    };
+    static constexpr int NMARK = 32;
+    mark _wmarks[NMARK], _rmarks[NMARK]; // circular, newest at (_wn - 1) % NMARK
+    uint64_t _wn = 0, _rn = 0;
+    b200_event_t _w_open = nullptr, _r_open = nullptr; // recorded by the block's guard, position known at post_*()
+    uint64_t _offer_w = 0, _offer_r = 0;               // windows handed out by the last write_info / read_info
+
+    void push_mark(mark* ring, uint64_t& n, b200_event_t ev, uint64_t pos)
+    {
+        mark& m = ring[n % NMARK];
+        if (m.ev)
+            _free_events.push_back(m.ev); // oldest one falls out; waiters then use the next older-than-needed one
+        m.ev = ev;
+        m.pos = pos;
+        n++;
+    }
+    // oldest event that covers `pos` (nullptr: nothing recorded covers it -- nobody touched those items on a GPU)
+    b200_event_t covering(const mark* ring, uint64_t n, uint64_t pos) const
+    {
+        const uint64_t first = n > (uint64_t)NMARK ? n - NMARK : 0;
+        for (uint64_t i = first; i < n; i++)
+            if (ring[i % NMARK].pos >= pos)
+                return ring[i % NMARK].ev;
+        return nullptr;
+    }
 
     // ---- H2D: up to H2D_SLOTS - 1 copies in flight; an offered window is at most capacity / H2D_SLOTS
     // items, so the staging spans of the copies still in flight are never the ones being refilled
@@ -205,13 +241,8 @@ public:
         _buf_size = b200_ring_size(_ring);
         _num_items = _buf_size / item_size;
         ck(b200_stream_create(&_stream), "stream_create");
-        ck(b200_event_create(&_ev_written, 0), "event_create");
-        ck(b200_event_create(&_ev_read, 0), "event_create");
         for (auto& e : _ev_copy)
             ck(b200_event_create(&e, 0), "event_create");
-        // make the events "complete" so the first waits fall through
-        ck(b200_event_record(_ev_written, _stream), "event_record");
-        ck(b200_event_record(_ev_read, _stream), "event_record");
         if (type != device_buffer_type::D2D)
             ck(b200_host_alloc((void**)&_host, _buf_size), "host_alloc");
         set_type("device_buffer_" + std::to_string((int)type));
@@ -228,9 +259,18 @@ public:
         for (auto& sp : _pending)
             if (sp.ev)
                 b200_event_destroy(sp.ev);
+        for (auto& m : _wmarks)
+            if (m.ev)
+                b200_event_destroy(m.ev);
+        for (auto& m : _rmarks)
+            if (m.ev)
+                b200_event_destroy(m.ev);
+        for (auto e : { _w_open, _r_open })
+            if (e)
+                b200_event_destroy(e);
         for (auto e : _free_events)
             b200_event_destroy(e);
-        for (auto e : { _ev_written, _ev_read, _ev_copy[0], _ev_copy[1], _ev_copy[2], _ev_copy[3] })
+        for (auto e : { _ev_copy[0], _ev_copy[1], _ev_copy[2], _ev_copy[3] })
             if (e)
                 b200_event_destroy(e);
         if (_stream)
@@ -278,6 +318,7 @@ public:
         if (_buffer_type != device_buffer_type::D2H) {
             info.ptr = (void*)(_dev + _read_index);
             info.n_items = size();
+            _offer_r = (uint64_t)info.n_items;
             return true;
         }
         publish_landed();
@@ -320,6 +361,7 @@ public:
             n = std::min<int>(n, capacity() / H2D_SLOTS); // keeps the in-flight H2D source spans untouched
         }
         info.n_items = std::max(0, n);
+        _offer_w = (uint64_t)info.n_items;
         info.item_size = _item_size;
         info.total_items = (int)_total_written;
         return true;
@@ -327,6 +369,13 @@ public:
     void post_read(int n) override
     {
         std::scoped_lock g(_buf_mutex);
+        if (_r_open) { // the reading block's event now has a position: reads up to here are done when it fires
+            if (n > 0)
+                push_mark(_rmarks, _rn, _r_open, _total_read + (uint64_t)n);
+            else
+                _free_events.push_back(_r_open);
+            _r_open = nullptr;
+        }
         if (_buffer_type == device_buffer_type::D2H) {
             uint64_t left = (uint64_t)n;
             while (left && !_ready.empty()) {
@@ -347,17 +396,20 @@ public:
         std::scoped_lock g(_buf_mutex);
         const size_t nbytes = (size_t)n * _item_size;
         if (_buffer_type == device_buffer_type::H2D) {
-            // device destination may still be read by an in-flight consumer kernel
-            ck(b200_stream_wait_event(_stream, _ev_read), "wait_event");
+            // the device destination may still be read by a consumer kernel -- the one that read this space a lap ago
+            if (_total_written + (uint64_t)n > _num_items)
+                if (b200_event_t e = covering(_rmarks, _rn, _total_written + (uint64_t)n - _num_items))
+                    ck(b200_stream_wait_event(_stream, e), "wait_event");
+            b200_event_t wev = get_event();
             if (_ext_src) {
                 // the block handed over caller-owned page-locked memory (write_from_host): copy from there,
                 // nothing of ours is reused, so there is nothing to throttle
                 ck(b200_memcpy_h2d(_dev + _write_index, _ext_src, nbytes, _stream), "memcpy_h2d");
-                ck(b200_event_record(_ev_written, _stream), "event_record");
+                ck(b200_event_record(wev, _stream), "event_record");
                 _ext_src = nullptr;
             } else {
                 ck(b200_memcpy_h2d(_dev + _write_index, _host + _write_index, nbytes, _stream), "memcpy_h2d");
-                ck(b200_event_record(_ev_written, _stream), "event_record");
+                ck(b200_event_record(wev, _stream), "event_record");
                 // H2D_SLOTS - 1 copies stay in flight: before the producer refills, wait for the copy that
                 // was enqueued H2D_SLOTS - 1 calls ago (its staging span is the next one to be reused)
                 ck(b200_event_record(_ev_copy[_copy_slot], _stream), "event_record");
@@ -368,10 +420,15 @@ public:
                     _copy_pending[_copy_slot] = false;
                 }
             }
+            push_mark(_wmarks, _wn, wev, _total_written + (uint64_t)n);
         } else if (_buffer_type == device_buffer_type::D2H) {
-            // the producer block recorded _ev_written after its launches: enqueue the copy behind it and
+            // the producer block recorded its event after its launches: enqueue the copy behind it and
             // return; the span becomes visible to the reader when its completion event has fired
-            ck(b200_stream_wait_event(_stream, _ev_written), "wait_event");
+            if (_w_open) {
+                ck(b200_stream_wait_event(_stream, _w_open), "wait_event");
+                _free_events.push_back(_w_open);
+                _w_open = nullptr;
+            }
             uint64_t left = (uint64_t)n;
             size_t src = _write_index;
             if (_land && _land_used < _land_items) { // straight into the consumer's own storage
@@ -387,7 +444,16 @@ public:
                 left -= take;
                 src = (src + take * _item_size) % _buf_size;
             }
-            ck(b200_event_record(_ev_read, _stream), "event_record"); // device span free again
+            // the device span is free again once these copies are done: that IS the read of this edge's device side
+            b200_event_t rev = get_event();
+            ck(b200_event_record(rev, _stream), "event_record");
+            push_mark(_rmarks, _rn, rev, _total_written + (uint64_t)n);
+        } else if (_w_open) { // D2D: the producing block's event now has a position
+            if (n > 0)
+                push_mark(_wmarks, _wn, _w_open, _total_written + (uint64_t)n);
+            else
+                _free_events.push_back(_w_open);
+            _w_open = nullptr;
         }
         _write_index = (_write_index + nbytes) % _buf_size;
         _total_written += n;
@@ -411,10 +477,20 @@ public:
             memcpy(_host + _write_index, src->_host + src->_write_index, nbytes);
             return;
         }
-        ck(b200_stream_wait_event(_stream, src->_ev_written), "wait_event");
-        ck(b200_stream_wait_event(_stream, _ev_read), "wait_event");
+        // source: what the producing block just launched (its open event); destination: readers of the space a lap ago
+        {
+            std::scoped_lock gs(src->_buf_mutex);
+            if (src->_w_open)
+                ck(b200_stream_wait_event(_stream, src->_w_open), "wait_event");
+        }
+        if (_total_written + (uint64_t)nitems > _num_items)
+            if (b200_event_t e = covering(_rmarks, _rn, _total_written + (uint64_t)nitems - _num_items))
+                ck(b200_stream_wait_event(_stream, e), "wait_event");
         ck(b200_memcpy_d2d(_dev + _write_index, src->_dev + src->_write_index, nbytes, _stream), "memcpy_d2d");
-        ck(b200_event_record(_ev_written, _stream), "event_record");
+        if (_w_open)
+            _free_events.push_back(_w_open);
+        _w_open = get_event();
+        ck(b200_event_record(_w_open, _stream), "event_record"); // gets its position in our post_write
     }
 
     // ---- host_direct_io (gnuradio/buffer.hpp): zero-copy hand-over with host blocks
@@ -446,10 +522,36 @@ public:
     }
 
     // ---- stream ordering used by GPU blocks (see device_stream_guard)
-    void wait_readable(b200_stream_t s) override { ck(b200_stream_wait_event(s, _ev_written), "wait_event"); }
-    void wait_writable(b200_stream_t s) override { ck(b200_stream_wait_event(s, _ev_read), "wait_event"); }
-    void record_read(b200_stream_t s) override { ck(b200_event_record(_ev_read, s), "event_record"); }
-    void record_write(b200_stream_t s) override { ck(b200_event_record(_ev_written, s), "event_record"); }
+    // the block is about to read the window read_info() offered: writes up to its end must have landed
+    void wait_readable(b200_stream_t s) override
+    {
+        std::scoped_lock g(_buf_mutex);
+        if (b200_event_t e = covering(_wmarks, _wn, _total_read + _offer_r))
+            ck(b200_stream_wait_event(s, e), "wait_event");
+    }
+    // ... and to write (at most) the window write_info() offered: reads of what sat there a lap ago must be done
+    void wait_writable(b200_stream_t s) override
+    {
+        std::scoped_lock g(_buf_mutex);
+        const uint64_t end = _total_written + _offer_w;
+        if (end > _num_items)
+            if (b200_event_t e = covering(_rmarks, _rn, end - _num_items))
+                ck(b200_stream_wait_event(s, e), "wait_event");
+    }
+    void record_read(b200_stream_t s) override
+    {
+        std::scoped_lock g(_buf_mutex);
+        if (!_r_open)
+            _r_open = get_event();
+        ck(b200_event_record(_r_open, s), "event_record"); // position assigned in post_read()
+    }
+    void record_write(b200_stream_t s) override
+    {
+        std::scoped_lock g(_buf_mutex);
+        if (!_w_open)
+            _w_open = get_event();
+        ck(b200_event_record(_w_open, s), "event_record"); // position assigned in post_write()
+    }
 
 private:
     static device_buffer* from_checked(const buffer_sptr& b)

@@ -81,7 +81,8 @@ struct b200_fir {
     int dg = 0;      // > 1: decimation by a non-divisor of 16 folded into the full-rate kernel (D rows per thread)
     int dd = 0;      // > 1: decimation folded into the TMA-staged full-rate kernel (geometry as for D = 1)
     ols_plan* ols = nullptr; // algorithm 3
-    tc_plan* tc = nullptr;   // algorithm 2
+    tc_plan* tc = nullptr;   // algorithm 2 (bf16 split) / 6 (tf32 split)
+    int tc_tf32 = 0;
     ffa_plan* ffa = nullptr; // algorithm 5
     int algorithm = 1;
     fir_epilogue ep{ 0, 1.f, 0.f };
@@ -492,7 +493,19 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
             else if (p->algorithm == 0 && atoi(e) != 0)
                 want2 = false;
         }
-        if (want2) {
+        if (p->algorithm == 6) { // TF32 measurement variant of the same formulation
+            if (h->vec != 2 || h->D != 1) {
+                b200_fir_destroy(h);
+                return set_err(B200_ERR_UNSUPPORTED, "fir_create: the tf32 tensor-core variant needs a complex stream and decimation 1");
+            }
+            int rc = tc_create_tf32(p->taps, h->T, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
+            if (rc != B200_OK) {
+                b200_fir_destroy(h);
+                return rc;
+            }
+            h->algorithm = 2;
+            h->tc_tf32 = 1;
+        } else if (want2) {
             int rc = tc_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
             if (rc != B200_OK) {
                 b200_fir_destroy(h);
@@ -662,7 +675,7 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
     return B200_OK;
 }
 
-int b200_fir_algorithm(const b200_fir* h) { return h ? h->algorithm : 0; }
+int b200_fir_algorithm(const b200_fir* h) { return h ? (h->tc_tf32 ? 6 : h->algorithm) : 0; }
 
 int b200_fir_geometry(const b200_fir* h, int* decimation, int* item_bytes)
 {

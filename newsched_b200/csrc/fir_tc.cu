@@ -412,6 +412,163 @@ __global__ void __launch_bounds__(TC_THREADS, 2) fir_tc_kernel(const tc_args a)
 }
 
 // =================================================================================================
+// TF32 variant (algorithm 6): the same block-Toeplitz / Hankel-descriptor formulation with kind::tf32 operands,
+// built to MEASURE the second precision the tensor cores offer for this job, not to be fast:
+// decimation 1, one 4096-output tile per CTA, element-wise conversion.  A 128-byte swizzle row holds 32 tf32
+// values, so the Hankel shift is 32 samples and only 32 phases x {hi, lo} = 64 of the 128 tap rows carry data --
+// half of every MMA multiplies zeros -- K advances 8 per MMA instead of 16 and the tf32 pipe has half the bf16
+// rate: per useful product it costs ~8x the bf16 form, which is why the bf16 hi/lo split (3e-6 rel. RMS, inside
+// the 1e-5 bar) is the production form and this one (hi + lo carries 22 significand bits: ~1e-7) is not.
+constexpr int TF_PH = 32;
+constexpr int TF_TILE = TC_NROW * TF_PH;
+constexpr uint32_t TF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NROW >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                 "}\n" ::"r"(d_tmem),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t tf_plane_off(uint32_t i)
+{
+    return (i >> 5) * 128u + ((((i >> 2) & 7u) ^ ((i >> 5) & 7u)) << 4) + (i & 3u) * 4u;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) fir_tc_tf32_kernel(const tc_args a)
+{
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* planes = smem;                                   // [re_hi][re_lo][im_hi][im_lo], tf32 in fp32 containers
+    uint8_t* ring = smem + 4 * (size_t)a.plane_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * TC_ATOM_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + TC_MAX_STAGES;
+    uint64_t* done = bars + 2 * TC_MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 1);
+    const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
+    const long long m0 = (long long)blockIdx.x * TF_TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc_alloc(tmem_slot, TC_TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const long long j0 = m0 - a.P;
+    for (int i = tid; i < a.plane_elems; i += TC_THREADS) {
+        const long long n = j0 + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (n >= 0) {
+            if (n < a.n_in)
+                v = __ldg(a.x + n);
+        } else if (a.hist != nullptr && n >= -(long long)a.Tm1) {
+            v = __ldg(a.hist + (a.Tm1 + n));
+        }
+        const float rh = tf32_rna(v.x), ih = tf32_rna(v.y);
+        const uint32_t off = tf_plane_off((uint32_t)i);
+        *reinterpret_cast<float*>(planes + off) = rh;
+        *reinterpret_cast<float*>(planes + a.plane_bytes + off) = tf32_rna(v.x - rh);
+        *reinterpret_cast<float*>(planes + 2 * a.plane_bytes + off) = ih;
+        *reinterpret_cast<float*>(planes + 3 * a.plane_bytes + off) = tf32_rna(v.y - ih);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == 0) {
+        const uint32_t planes_s = smem_u32(planes), ring_s = smem_u32(ring);
+        for (int at = 0; at < a.KA; at++) {
+            const int s = at % a.stages, use = at / a.stages;
+            if (at >= a.stages)
+                mbar_wait(&empty[s], (use & 1) ^ 1);
+            if (tc_elect_one()) {
+                mbar_arrive_expect_tx(&full[s], TC_ATOM_BYTES);
+                bulk_copy_g2s(ring + (size_t)s * TC_ATOM_BYTES, a.gA + (size_t)at * TC_ATOM_BYTES, TC_ATOM_BYTES, &full[s]);
+            }
+            __syncwarp();
+            mbar_wait(&full[s], use & 1);
+            tc_fence_after();
+            if (tc_elect_one()) {
+                const int nst = min(4, a.ksteps - 4 * at); // K-steps of 8 tf32 = 32 bytes
+                for (int t = 0; t < nst; t++) {
+                    const uint64_t adesc = tc_desc(ring_s + s * TC_ATOM_BYTES + t * 32, 0);
+                    const uint32_t boff = at * 128 + t * 32, acc = (at | t) != 0;
+                    tc_mma_tf32(tmem, adesc, tc_desc(planes_s + boff, 0), TF_IDESC, acc);
+                    tc_mma_tf32(tmem, adesc, tc_desc(planes_s + a.plane_bytes + boff, 0), TF_IDESC, 1);
+                    tc_mma_tf32(tmem + TC_NROW, adesc, tc_desc(planes_s + 2 * a.plane_bytes + boff, 0), TF_IDESC, acc);
+                    tc_mma_tf32(tmem + TC_NROW, adesc, tc_desc(planes_s + 3 * a.plane_bytes + boff, 0), TF_IDESC, 1);
+                }
+                tc_commit(&empty[s]);
+                if (at == a.KA - 1)
+                    tc_commit(done);
+            }
+            __syncwarp();
+        }
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+
+    // lanes 0..31 (warp 0): hi-tap sums of phase c = lane, lanes 32..63 (warp 1): lo-tap sums; 64..127 are zero rows
+    float2* tile = reinterpret_cast<float2*>(planes);
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        float re[32], im[32];
+        tc_ld32(tl + q * 32, re);
+        tc_ld32(tl + TC_NROW + q * 32, im);
+        tc_wait_ld();
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                tile[(q * 32 + i) * TF_PH + lane] = make_float2(re[i], im[i]);
+        }
+        __syncthreads();
+        if (warp == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                float2 v = tile[(q * 32 + i) * TF_PH + lane];
+                v.x += re[i];
+                v.y += im[i];
+                if (a.fuse)
+                    v = cmul_nofma(v, a.kre, a.kim);
+                tile[(q * 32 + i) * TF_PH + lane] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    const long long left = a.n_out - m0;
+    const int count = left < TF_TILE ? (int)left : TF_TILE;
+    for (int i = tid; i < count; i += TC_THREADS)
+        a.y[m0 + i] = tile[i];
+    if (warp == 0) {
+        __syncwarp();
+        tc_fence_after();
+        tc_dealloc(tmem, TC_TMEM_COLS);
+    }
+}
+
+// =================================================================================================
 // Pipelined form: one persistent CTA per SM, warp-specialised.
 //   warp 0       MMA issuer (one elected lane), owns the TMEM allocation (2 accumulator stages x 256 columns)
 //   warp 1       tap-atom producer (1-D bulk copies into a ring)
@@ -961,6 +1118,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
 
 // ---- host side ---------------------------------------------------------------------------------
 struct tc_plan {
+    int tf32 = 0;          // 1: TF32 measurement variant (fir_tc_tf32_kernel)
     int T = 0, D = 1;
     int Tq = 0, P = 0, ksteps = 0, KA = 0, plane_elems = 0, plane_bytes = 0, stages = 2;
     int fuse = 0;
@@ -1000,6 +1158,66 @@ bool tc_supported(int n_taps, int decimation, int real)
         return false;
     const int tq = (n_taps + decimation - 1) / decimation;
     return tq <= 2048;
+}
+
+static inline float tc_tf32_rna(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u = (u + 0x1000u) & ~0x1fffu; // round to nearest, ties away, 10 explicit mantissa bits
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// TF32 measurement variant: decimation 1 only
+int tc_create_tf32(const float* taps, int n_taps, int fuse, float kre, float kim, tc_plan** out)
+{
+    *out = nullptr;
+    if (n_taps < 1 || n_taps > 2048)
+        return set_err(B200_ERR_UNSUPPORTED, "fir(tensor core, tf32): 1..2048 taps, decimation 1");
+    tc_plan* p = new tc_plan();
+    p->tf32 = 1;
+    p->T = n_taps;
+    p->D = 1;
+    p->Tq = n_taps;
+    p->P = (n_taps - 1 + 7) / 8 * 8;
+    const int kneed = p->P + TF_PH;
+    p->ksteps = kneed / 8;
+    p->KA = (kneed + 31) / 32;
+    p->plane_elems = TF_PH * (TC_NROW - 1) + kneed;
+    p->plane_bytes = ((p->plane_elems + 31) / 32 * 128 + 1023) / 1024 * 1024;
+    if (4 * p->plane_bytes < (int)(TF_TILE * sizeof(float2)))
+        p->plane_bytes = TF_TILE * sizeof(float2) / 4;
+    p->fuse = fuse;
+    p->kre = kre;
+    p->kim = kim;
+    p->stages = std::min(2, p->KA);
+    p->smem = 1024 + 4 * (size_t)p->plane_bytes + (size_t)p->stages * TC_ATOM_BYTES + 256;
+    std::vector<float> atoms((size_t)p->KA * TC_ATOM_BYTES / 4, 0.f);
+    for (int at = 0; at < p->KA; at++)
+        for (int row = 0; row < 64; row++) {
+            const int c = row & 31, lo = row >> 5;
+            for (int e = 0; e < 32; e++) {
+                const long long k = (long long)c + p->P - (32 * at + e);
+                const float hv = (k >= 0 && k < n_taps) ? taps[k] : 0.f;
+                const float hi = tc_tf32_rna(hv);
+                atoms[(size_t)at * (TC_ATOM_BYTES / 4) + (size_t)row * 32 + (size_t)(((e >> 2) ^ (row & 7)) << 2) + (e & 3)] =
+                    lo ? tc_tf32_rna(hv - hi) : hi;
+            }
+        }
+    cudaError_t e = cudaMalloc(&p->d_atoms, atoms.size() * 4);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(p->d_atoms, atoms.data(), atoms.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fir_tc_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+        e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        tc_destroy(p);
+        return set_err(B200_ERR_CUDA, "fir(tensor core, tf32) create: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return B200_OK;
 }
 
 int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre, float kim, tc_plan** out)
@@ -1174,6 +1392,11 @@ int tc_launch(tc_plan* p, const float* d_hist, const void* d_in, void* d_out, lo
     a.desc_mode = p->desc_mode;
     if (const char* e = getenv("B200_TC_DBG"))
         a.dbg = atoi(e);
+    if (p->tf32) {
+        const long long tf_tiles = (n_out + TF_TILE - 1) / TF_TILE;
+        B200_LAUNCH(fir_tc_tf32_kernel, (unsigned)tf_tiles, TC_THREADS, p->smem, s, a);
+        return B200_OK;
+    }
     if (p->ts) {
         a.gAt = p->d_at;
         a.ts_plane_elems = p->ts_plane_elems;

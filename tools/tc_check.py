@@ -19,12 +19,17 @@ VARIANTS = {   # name -> environment of the library
     "ts_swap": {"B200_TC_TS": "1", "B200_TC_TS_SWAP": "1"},    # diagnostic: other packing of the bf16 pairs in TMEM
     "pipe": {"B200_TC_TS": "0", "B200_TC_PIPE": "1"},          # warp-specialised, taps streamed through a smem ring
     "v0": {"B200_TC_TS": "0", "B200_TC_PIPE": "0"},            # one tile per CTA, phases serialised
+    "tf32": {},                                                # algorithm 6: the same formulation with kind::tf32 operands
 }
 
 
 def child(kind, T, D, mode):
     variant = mode
     os.environ.update(VARIANTS[variant])
+    ALGO = 6 if variant == "tf32" else 2
+    if variant == "tf32" and D != 1:
+        print(json.dumps({"kind": kind, "T": T, "D": D, "mode": mode, "ok": True, "skipped": "tf32 variant: decimation 1 only"}))
+        return
     import numpy as np
     import torch
     import newsched_b200 as nb
@@ -35,19 +40,19 @@ def child(kind, T, D, mode):
         n = (8192 * 301 + 1000) * D + (D - 1)          # > 2 tiles per SM for the persistent form, ragged tail
         x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
         dx = torch.from_numpy(x).cuda()
-        f = nb.FirFilter(taps, D, algorithm=2)
+        f = nb.FirFilter(taps, D, algorithm=ALGO)
         y, nc = f.work(dx)
         torch.cuda.synchronize()
         ref = o.fir(x, taps, D)
         err = o.rel_rms(y.cpu().numpy(), ref)
         # streaming: two chunks must continue the history
-        f2 = nb.FirFilter(taps, D, algorithm=2)
+        f2 = nb.FirFilter(taps, D, algorithm=ALGO)
         cut = (8192 * 150 + 333) * D
         ya, _ = f2.work(dx[:cut])
         yb, _ = f2.work(dx[cut:])
         err2 = o.rel_rms(torch.cat([ya, yb]).cpu().numpy(), ref)
         # fused multiply_const epilogue
-        f3 = nb.FirFilter(taps, D, algorithm=2, multiply_const=0.5 - 0.25j)
+        f3 = nb.FirFilter(taps, D, algorithm=ALGO, multiply_const=0.5 - 0.25j)
         y3, _ = f3.work(dx)
         err3 = o.rel_rms(y3.cpu().numpy(), ref * (0.5 - 0.25j))
         print(json.dumps({"kind": kind, "T": T, "D": D, "mode": mode, "algorithm": f.algorithm, "rel_rms": err,
@@ -58,7 +63,7 @@ def child(kind, T, D, mode):
         x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
         out = torch.empty(n // D, dtype=torch.complex64, device="cuda")
         res = {"kind": kind, "T": T, "D": D}
-        for algo, pipe in ((2, variant), (2, "pipe"), (0, "")):
+        for algo, pipe in ((ALGO, variant), (2, "pipe"), (3, ""), (0, "")):
             if pipe:
                 os.environ.update(VARIANTS[pipe])
             f = nb.FirFilter(taps, D, algorithm=algo)
@@ -73,10 +78,10 @@ def child(kind, T, D, mode):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             gs = n / (ms * 1e-3) / 1e9
-            tag = f"algo{f.algorithm}" + (("_" + pipe) if algo == 2 else "")
+            tag = (f"algo{f.algorithm}" + (("_" + pipe) if algo in (2, 6) else "")) if algo else f"auto(algo{f.algorithm})"
             res[f"{tag}_GSs"] = round(gs, 1)
             res[f"{tag}_hbm_frac"] = round(gs * (8 + 8 / D) / 6556.5, 3)
-            if algo == 2 and pipe == variant:
+            if algo == 2 and pipe == variant and variant != "tf32":
                 # executed tensor flops: 4 MMAs of 128x128x16 per K-step, ksteps = (roundup16(ceil(T/D)-1)+64)/16 per branch
                 tq = (T + D - 1) // D
                 ksteps = ((tq - 1 + 15) // 16 * 16 + 64) // 16
