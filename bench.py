@@ -566,7 +566,7 @@ def run_b200(args):
                     ("config1_fir_ccf_64taps_8Gi_stream", ["--config", "1", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_1Gi", ["--config", "3", "--samples", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_8Gi_stream", ["--config", "3", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
-                    ("config0_vector_source_fir64_vector_sink_16Mi", ["--config", "10", "--samples", str(1 << 24), "--buffer_size", str(1 << 24)]),
+                    ("config0_vector_source_fir64_vector_sink_16Mi", ["--config", "10", "--samples", str(1 << 24), "--buffer_size", str(1 << 25)]),
                     ("cuda_copy_x4_1Gi", ["--config", "0", "--samples", str(1 << 30)])):
                 best = None
                 for _ in range(3):
@@ -701,6 +701,46 @@ def run_b200(args):
                 del yt
             except Exception as e:  # pragma: no cover
                 extras["config4_error"] = repr(e)
+
+    # ---- multi-GPU only: the same configs as newsched flowgraphs on ALL GPUs of ONE process (C++ blocks, one mt
+    # scheduler, every block / ring / stream on its own device; SURVEY.md 8e "single process, 8 devices"), next to
+    # the one-process-per-GPU numbers above.  Rank 0 runs it; the other ranks wait on a HOST barrier (gloo), so no
+    # NCCL kernel is spinning on their GPUs meanwhile.
+    if dist is not None:
+        try:
+            torch.cuda.synchronize()
+            hostgrp = dist.new_group(backend="gloo")
+            dist.barrier(group=hostgrp)
+            if rank == 0:
+                import subprocess
+                exe = os.path.join(ROOT, "newsched_b200", "host", "build", "bm_flowgraph")
+                if not os.path.exists(exe):
+                    subprocess.check_call(["make", "-C", os.path.join(ROOT, "newsched_b200", "host"), "-s"])
+                env = dict(os.environ)
+                fgm = {}
+                for name, argv in (
+                        ("config2_fft4096_mag_1Gi_per_gpu", ["--config", "2", "--samples", str(1 << 30)]),
+                        ("config1_fir_ccf_64taps_1Gi_per_gpu", ["--config", "1", "--samples", str(1 << 30)]),
+                        ("config3_fir1024d4_mulc_fft_1Gi_per_gpu", ["--config", "3", "--samples", str(1 << 30)]),
+                        ("config5_time_segmented_fir4096_128Mi_per_gpu", ["--config", "5", "--samples", str(1 << 27)])):
+                    best = None
+                    for _ in range(2):
+                        o_ = subprocess.run([exe] + argv + ["--gpus", str(world)], capture_output=True, text=True,
+                                            timeout=180, env=env)
+                        try:
+                            rec = json.loads(o_.stdout.strip().splitlines()[-1])
+                        except Exception:
+                            rec = {"Msamples_s": 0.0, "error": (o_.stderr or o_.stdout)[-300:]}
+                        if best is None or rec.get("Msamples_s", 0) > best.get("Msamples_s", 0):
+                            best = rec
+                    fgm[name] = {k: best.get(k) for k in ("Msamples_s", "seconds", "gpus", "kernel_launches", "error") if k in best}
+                fgm["how"] = (f"newsched_b200/host/bm_flowgraph --gpus {world}: ONE process, one mt scheduler, {world} device-resident "
+                              "replicas (config 5: time segments, halo peer-copied from the left neighbour's resident segment); "
+                              "wall clock start()->wait(), aggregate over the GPUs, best of 2")
+                extras["flowgraph_one_process_all_gpus"] = fgm
+            dist.barrier(group=hostgrp)
+        except Exception as e:  # pragma: no cover
+            extras["flowgraph_multi_gpu_error"] = repr(e)
 
     cpu_baseline, cpu_tuned = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
