@@ -34,6 +34,14 @@
 #define B200_FFT_TW2 1
 #endif
 // 1 = third barrier moved in front of the pass-1 stores of the next vector (measured -1.5 %)
+// pass-2 -> pass-3 exchange of fft4096_tma_kernel by warp shuffles instead of shared memory (north_star names
+// "warp-shuffle butterflies"): with pass 3 mapped as (k0 = tid >> 4, k1 = tid & 15) the exchange is a 16 x 16
+// transpose inside each group of 16 lanes, four butterfly stages of shfl.xor.  A/B measured on the B200
+// (tools/pk_ab.py): it removes one of the three shared-memory exchanges, and costs 64 SHFL per
+// thread plus stores that are no longer coalesced (lanes then step through k1, i.e. 64 bytes apart).  Default off.
+#ifndef B200_FFT_SHFL
+#define B200_FFT_SHFL 0
+#endif
 #ifndef B200_FFT_LATEBAR
 #define B200_FFT_LATEBAR 0
 #endif
@@ -238,6 +246,58 @@ __global__ void __launch_bounds__(256, 2)
             mbar_arrive_expect_tx(bar, 4096 * 8);
             bulk_copy_g2s(sIn, in + (vec + (long long)NBUF * gridDim.x) * 4096, 4096 * 8, bar);
         }
+#if B200_FFT_SHFL
+        {
+            const int k0 = tid >> 4, n0 = tid & 15;
+            const float2* row = sA + k0 * F4K_STRIDE + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = row[i * 16];
+            dft16<FWD>(v);
+            float2 w[16];
+            w[0] = v[pos16(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; k1++)
+                w[k1] = cmul(v[pos16(k1)], t2r[k1]);
+            // 16 x 16 transpose inside the 16-lane group: afterwards w[i] = the value lane i held for k1 = my lane
+#pragma unroll
+            for (int sft = 1; sft < 16; sft <<= 1) {
+                const bool up = (n0 & sft) != 0;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (i & sft)
+                        continue;
+                    const float2 send = up ? w[i] : w[i | sft];
+                    float2 recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, sft);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, sft);
+                    if (up)
+                        w[i] = recv;
+                    else
+                        w[i | sft] = recv;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                v[i] = w[i];
+            dft16<FWD>(v);
+            const int k1 = n0; // this thread now owns (k0, k1): X[k0 + 16 k1 + 256 k2]
+            if (OUT == B200_FFT_OUT_COMPLEX) {
+                float2* y = reinterpret_cast<float2*>(out) + vec * 4096;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++)
+                    __stcs(y + k2 * 256 + k1 * 16 + k0, v[pos16(k2)]);
+            } else {
+                float* y = reinterpret_cast<float*>(out) + vec * 4096;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; k2++) {
+                    float2 z = v[pos16(k2)];
+                    float p = fmaf(z.x, z.x, z.y * z.y);
+                    __stcs(y + k2 * 256 + k1 * 16 + k0, OUT == B200_FFT_OUT_MAG ? sqrt_approx(p) : p);
+                }
+            }
+        }
+#else
         {
             const int k0 = tid >> 4, n0 = tid & 15;
             float2* row = sA + k0 * F4K_STRIDE + n0;
@@ -277,6 +337,7 @@ __global__ void __launch_bounds__(256, 2)
                 }
             }
         }
+#endif
 #if !B200_FFT_LATEBAR && !B200_FFT_DBUF
         __syncthreads();
 #endif
@@ -1206,6 +1267,12 @@ int b200_fft_create(const b200_fft_params* p, b200_fft** out)
         }
     }
 #undef FFT_CUDA
+    // the uploads above went through the legacy default stream (cudaMemcpy / cudaMemset); the caller's streams are
+    // non-blocking and not ordered against it, so finish them before the handle can be used
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        b200_fft_destroy(h);
+        return set_err(B200_ERR_CUDA, "fft_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = h;
     return B200_OK;
 }

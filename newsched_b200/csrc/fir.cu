@@ -359,6 +359,12 @@ int fir_interp_create(const float* taps, int T, int L, int M, int is_complex, b2
         b200_fir_destroy(h);
         return set_err(B200_ERR_CUDA, "fir resampling fold: %s", cudaGetErrorString(e));
     }
+    // the uploads above went through the legacy default stream (cudaMemcpy / cudaMemset); the caller's streams are
+    // non-blocking and not ordered against it, so finish them before the handle can be used
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        b200_fir_destroy(h);
+        return set_err(B200_ERR_CUDA, "fir_interp_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = h;
     return B200_OK;
 }
@@ -671,6 +677,12 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         }
     }
 #undef FIR_CUDA
+    // the uploads above went through the legacy default stream (cudaMemcpy / cudaMemset); the caller's streams are
+    // non-blocking and not ordered against it, so finish them before the handle can be used
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        b200_fir_destroy(h);
+        return set_err(B200_ERR_CUDA, "fir_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = h;
     return B200_OK;
 }

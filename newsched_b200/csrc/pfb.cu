@@ -993,6 +993,12 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
         }
     }
 #undef PFB_CUDA
+    // the uploads above went through the legacy default stream (cudaMemcpy / cudaMemset); the caller's streams are
+    // non-blocking and not ordered against it, so finish them before the handle can be used
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        b200_pfb_destroy(h);
+        return set_err(B200_ERR_CUDA, "pfb_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = h;
     return B200_OK;
 }

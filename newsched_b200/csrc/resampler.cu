@@ -396,6 +396,12 @@ int b200_resampler_create(const b200_resampler_params* p, b200_resampler** out)
         }
     }
 #undef RS_CUDA
+    // the uploads above went through the legacy default stream (cudaMemcpy / cudaMemset); the caller's streams are
+    // non-blocking and not ordered against it, so finish them before the handle can be used
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        b200_resampler_destroy(h);
+        return set_err(B200_ERR_CUDA, "resampler_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = h;
     return B200_OK;
 }

@@ -105,3 +105,79 @@ def test_configs_4_and_5_on_two_gpus_match_the_oracle():
         assert p.exitcode == 0
     ok, notes = q.get(timeout=5)
     assert ok is True, notes
+
+
+# ---- the same sharding logic on ONE GPU: two ranks (processes) share cuda:0, host plumbing over gloo, the halo
+# read in place through the CUDA IPC mapping -- so the driver's 1-GPU box exercises configs 4 / 5 at N = 2 too
+def _worker_one_gpu(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import scipy.signal as sig
+    import newsched_b200 as nb
+    import oracle as o
+    from newsched_b200 import multigpu as mg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok, notes = True, []
+
+    def gather_cpu(t):
+        parts = [None] * world
+        dist.all_gather_object(parts, t.cpu().numpy())
+        return np.concatenate(parts)
+
+    try:
+        rng = np.random.default_rng(13)
+        n = 1 << 19
+        x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+        for T, D, algo in ((64, 1, 1), (128, 1, 2), (4096, 1, 3), (1024, 4, 0)):
+            taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+            lo, hi = mg.time_segments(n, world, D, halo_len=T - 1)[rank]
+            seg = torch.from_numpy(x[lo:hi]).cuda()
+            fir = nb.FirFilter(taps, D, algorithm=algo)
+            sf = mg.SegmentedFir(fir, rank, world, peer=True)
+            y = sf.run(seg)
+            torch.cuda.synchronize()
+            full = gather_cpu(y)
+            err = o.rel_rms(full, o.fir(x, taps, D, mt=True))
+            notes.append((T, D, fir.algorithm, float(err)))
+            ok &= bool(err < 1e-5)
+            dist.barrier()          # nobody unmaps / frees while the neighbour may still read
+            sf._peer.close()
+        M, P = 64, 16
+        pt = sig.firwin(M * P, 1.0 / M).astype(np.float32)
+        nx = M * 4096
+        lo, hi = mg.time_segments(nx, world, M, halo_len=(P - 1) * M)[rank]
+        seg = torch.from_numpy(x[lo:hi]).cuda()
+        st = mg.SegmentedFir(nb.PfbChannelizer(pt, M), rank, world, peer=True, halo_len=(P - 1) * M)
+        rows = st.run(seg)
+        torch.cuda.synchronize()
+        allrows = gather_cpu(rows.contiguous())
+        err = o.rel_rms(allrows.reshape(-1), o.pfb_channelizer(x[:nx], pt, M).reshape(-1))
+        notes.append(("pfb", float(err)))
+        ok &= bool(err < 1e-5)
+        dist.barrier()
+        st._peer.close()
+        if rank == 0:
+            q.put((ok, notes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_segments_two_ranks_on_one_gpu_match_the_oracle():
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_one_gpu, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    ok, notes = q.get(timeout=5)
+    assert ok is True, notes
