@@ -241,6 +241,13 @@ B200_API int b200_pfb_run_segment(b200_pfb* h, const void* d_halo, const void* d
                                   int64_t n_in_items, int64_t* n_produced_vectors, b200_stream_t s);
 B200_API int b200_pfb_reset(b200_pfb* h, b200_stream_t s);
 B200_API int b200_pfb_geometry(const b200_pfb* h, int* n_channels, int* channel_count);
+/* Form of the M = 64 channelizer (BASELINE.json configs[3] "filterbank + DFT as tensor-core GEMM"):
+ *   0 = auto (the faster one as measured), 1 = branch filters + 64-point DFT on the SIMT pipes,
+ *   2 = branch filters on the SIMT pipes, the DFT across branches as a 128 x 64 x 128 bf16-split GEMM per
+ *       64-frame tile on tcgen05 with the DFT matrix resident in tensor memory (64 channels, <= 16 taps per
+ *       channel; B200_ERR_UNSUPPORTED otherwise).  Same results within the 1e-5 relative-RMS bar. */
+B200_API int b200_pfb_set_algorithm(b200_pfb* h, int32_t algorithm);
+B200_API int b200_pfb_get_algorithm(const b200_pfb* h, int32_t* algorithm);
 
 /* ---- host-buffer streaming driver (the e2e path a host-resident source/sink sees) ---
  * A chain is an ordered list of op handles executed back to back on device buffers; the

@@ -10,10 +10,13 @@ class pfb_channelizer_ccf : public block, public stream_owner
 {
 public:
     typedef std::shared_ptr<pfb_channelizer_ccf> sptr;
+    // algorithm: 0 auto, 1 SIMT DFT, 2 DFT across branches as a tensor-core GEMM (b200_pfb_set_algorithm)
     static sptr make(size_t numchans, const std::vector<float>& taps, size_t channel_begin = 0,
-                     size_t channel_count = 0)
+                     size_t channel_count = 0, int algorithm = 0)
     {
         auto ptr = std::make_shared<pfb_channelizer_ccf>(numchans, taps, channel_begin, channel_count);
+        if (algorithm)
+            check(b200_pfb_set_algorithm(ptr->d_pfb, algorithm), "cuda::pfb_channelizer");
         ptr->add_port(port<gr_complex>::make("input", port_direction_t::INPUT));
         ptr->add_port(port<gr_complex>::make("output", port_direction_t::OUTPUT, { ptr->d_count }));
         return ptr;

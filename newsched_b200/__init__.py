@@ -155,6 +155,8 @@ SIGNATURES = {
     "b200_pfb_run_segment": (_I, [_V, _V, _V, _V, _I64, _PI64, _V]),
     "b200_pfb_reset": (_I, [_V, _V]),
     "b200_pfb_geometry": (_I, [_V, C.POINTER(_I), C.POINTER(_I)]),
+    "b200_pfb_set_algorithm": (_I, [_V, C.c_int32]),
+    "b200_pfb_get_algorithm": (_I, [_V, C.POINTER(C.c_int32)]),
     "b200_chain_create": (_I, [C.POINTER(_ChainOp), C.c_int32, C.c_int32, _I64, C.POINTER(_V)]),
     "b200_chain_destroy": (_I, [_V]),
     "b200_chain_run": (_I, [_V, _V, _V, _I64, _PI64, _V]),
@@ -529,13 +531,22 @@ class RationalResampler:
 class PfbChannelizer:
     """Critically sampled M-channel polyphase analysis bank; work() returns [n_t, channels]."""
 
-    def __init__(self, taps, n_channels: int, channel_begin: int = 0, channel_count: int = 0):
+    def __init__(self, taps, n_channels: int, channel_begin: int = 0, channel_count: int = 0,
+                 algorithm: int = 0):
+        """algorithm: 0 auto, 1 SIMT DFT, 2 DFT across branches as a tensor-core GEMM (64 channels only)."""
         arr, ptr = _floats(taps)
         assert arr.size % n_channels == 0
         p = _PfbParams(ptr, int(n_channels), arr.size // n_channels, int(channel_begin), int(channel_count))
         h = C.c_void_p()
         _check(lib().b200_pfb_create(C.byref(p), C.byref(h)))
         self._h = h
+        if algorithm:
+            try:
+                _check(lib().b200_pfb_set_algorithm(self._h, int(algorithm)))
+            except Exception:
+                lib().b200_pfb_destroy(self._h)
+                self._h = None
+                raise
         self.m = int(n_channels)
         self.p = arr.size // n_channels
         self.channels = int(channel_count) if channel_count else self.m - int(channel_begin)
@@ -543,6 +554,12 @@ class PfbChannelizer:
     @property
     def handle(self):
         return self._h
+
+    @property
+    def algorithm(self) -> int:
+        a = C.c_int32()
+        _check(lib().b200_pfb_get_algorithm(self._h, C.byref(a)))
+        return a.value
 
     def work(self, x, out=None, stream=None):
         torch = _torch()

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 // stage-1 DFT twiddles in registers instead of the shared table (measured +2.9 %: 359 -> 369 GS/s)
 #ifndef B200_PFB_TWREG
@@ -284,6 +285,211 @@ __global__ void __launch_bounds__(256, 2)
             }
         }
         __syncthreads(); // U free for the next tile's branch filters
+    }
+}
+
+// ---- M = 64, the 64-point DFT across branches as a GEMM on the tensor cores (algorithm 2) -------
+// BASELINE.json configs[3]: "64-channel polyphase channelizer (filterbank + DFT as tensor-core GEMM)";
+// build the GEMM form, measure it against the SIMT DFT and keep the faster one.
+// Only the DFT is a dense contraction worth the tensor pipe (the fused filterbank x DFT matrix executes
+// 8T = 8192 flop/sample x 3 split products: 57 GS/s at the measured bf16 peak, against ~370 measured for
+// this form), so the branch filters stay the register-window FFMA2 code of pfb64_kernel and
+//
+//   [y_re ; y_im][c][t] = sum_k A[2c + part][k] * B[t][k],   k = 2 i + (re | im) of branch output u_i[t]
+//   A[2c][2i] = cos th, A[2c][2i+1] = -sin th, A[2c+1][2i] = sin th, A[2c+1][2i+1] = cos th, th = 2 pi i c / 64
+//
+// is one 128 x 64 x 128 GEMM per 64-frame tile: M = 128 rows (channel, re/im), N = 64 frames, K = 128.
+// Precision: both operands split into bf16 hi + lo; hi*hi + lo*hi + hi*lo (lo*lo is below fp32 rounding)
+// = 3 x 8 MMAs of 128 x 64 x 16 per tile, fp32 accumulation in TMEM.  The DFT matrix never changes: it is
+// written once per CTA into tensor memory (A from TMEM: 64 + 64 columns), the MMAs read only the branch
+// outputs from shared memory.  B is K-major SWIZZLE_128B: a frame's 128 k-values are two 128-byte rows
+// (K-atoms: branches 0..31 / 32..63); the filter thread of branch i writes (re, im) of a frame as ONE
+// 32-bit store per plane, a warp covers a whole row -- the same 8 B/sample of shared-memory stores the SIMT
+// kernel spends on U, and nothing else: no DFT loads, stores, twiddles or butterflies.
+// Epilogue: TMEM lane 2c + part holds y_part[c] of 32 frames per warp; neighbouring lanes swap odd/even
+// frames with one shuffle each and store (re, im) pairs, 16 consecutive channels = one 128-byte line per
+// half-warp.  Tiles are software-pipelined: the MMAs of tile i run while the CTA drains tile i-1 and the
+// other resident CTA filters (2 CTAs/SM, 256 TMEM columns each: DFT 128 + 2 accumulator stages of 64).
+constexpr int PFBT_PLANE = 2 * 64 * 128; // one plane (hi or lo) of a tile: 2 K-atoms x 64 frames x 128 bytes
+constexpr int PFBT_TMEM_COLS = 256;
+constexpr uint32_t PFBT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+template <int P4T>
+__global__ void __launch_bounds__(256, 2)
+    pfb64_tc_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
+                    const float* __restrict__ taps_rm /* [P4][64] */, const uint4* __restrict__ gA /* [128][hi 128 | lo 128] bf16 */,
+                    int P4, int Ptrue, long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok)
+{
+    extern __shared__ uint8_t pfbt_raw[];
+    uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pfbt_raw) + 1023) & ~(uintptr_t)1023);
+    const int rows = PFB64_TT + P4 - 1;
+    float2* X = reinterpret_cast<float2*>(planes + 4 * PFBT_PLANE); // [stage][hi, lo] planes in front
+    float* hT = reinterpret_cast<float*>(X + rows * 64);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + P4 * 64);      // [0]: X landed, [1], [2]: accumulator stage complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+    const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_init(bar + 2, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tc_alloc(tmem_slot, PFBT_TMEM_COLS);
+    }
+    for (int i = tid; i < P4 * 64; i += 256)
+        hT[i] = __ldg(taps_rm + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0); // warp-uniform for the compiler (MMA operands)
+    if (warp < 4) {
+        // one-off: row m = 32 warp + lane of the DFT matrix -> this thread's TMEM lane, hi then lo
+        const uint4* row = gA + (size_t)(warp * 32 + lane) * 32;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 4
+        for (int k = 0; k < 16; k++) {
+            const uint4 a = __ldg(row + 2 * k), b = __ldg(row + 2 * k + 1);
+            const uint32_t v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+            tc_st8(tl + k * 8, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const long long nh = (long long)(Ptrue - 1) * 64;
+    const long long n_tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
+    const uint32_t tile_bytes = (uint32_t)rows * 64u * 8u;
+    auto tma_tile = [&](long long t) {
+        const long long g0 = (t * PFB64_TT - (P4 - 1)) * 64;
+        return tma_ok && g0 >= 0 && g0 + (long long)rows * 64 <= n_in;
+    };
+    // drain accumulator stage `st` (tile starting at frame f0) into out
+    auto epilogue = [&](int st, uint32_t parity, long long f0) {
+        mbar_wait(bar + 1 + st, parity);
+        tc_fence_after();
+        const int quarter = warp & 3, half = warp >> 2;
+        float v[32];
+        tc_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + st * 64 + half * 32, v);
+        tc_wait_ld();
+        tc_fence_before();
+        const int part = lane & 1, c = quarter * 16 + (lane >> 1);
+        const bool ch_ok = c >= ch_begin && c < ch_begin + ch_count;
+        float2* y = out + (f0 + half * 32 + part) * ch_count - ch_begin + c;
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            // even lane: re of frames 2p, 2p+1; odd lane: im.  Even keeps frame 2p, odd keeps frame 2p+1.
+            const float recv = __shfl_xor_sync(0xffffffffu, part ? v[2 * p] : v[2 * p + 1], 1);
+            const float2 r = part ? make_float2(recv, v[2 * p + 1]) : make_float2(v[2 * p], recv);
+            if (ch_ok && f0 + half * 32 + 2 * p + part < n_frames)
+                __stcs(y + (long long)(2 * p) * ch_count, r);
+        }
+    };
+
+    long long tile = blockIdx.x;
+    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
+        mbar_arrive_expect_tx(bar, tile_bytes);
+        bulk_copy_g2s(X, x + (tile * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
+    }
+    uint32_t xphase = 0;
+    int it = 0;
+    long long prev_f0 = 0;
+    const uint32_t planes_s = smem_u32(planes);
+    for (; tile < n_tiles; tile += gridDim.x, it++) {
+        const long long f0 = tile * PFB64_TT;
+        const int st = it & 1;
+        if (tma_tile(tile)) {
+            mbar_wait(bar, xphase);
+            xphase ^= 1;
+        } else {
+            const long long g0 = (f0 - (P4 - 1)) * 64;
+            for (int i0 = tid; i0 < rows * 64; i0 += 256 * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * 64)
+                        v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (i0 + u * 256 < rows * 64)
+                        X[i0 + u * 256] = v[u];
+            }
+            __syncthreads();
+        }
+        // ---- branch filters: thread = (branch i, 16 consecutive frames), as in pfb64_kernel
+        {
+            const int i = tid & 63, tg = tid >> 6;
+            const float2* col = X + (63 - i) + (tg * 16) * 64;
+            float2 acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                acc[j] = make_float2(0.f, 0.f);
+            float hreg[P4T];
+#pragma unroll
+            for (int r = 0; r < P4T; r++)
+                hreg[r] = hT[r * 64 + i];
+#pragma unroll
+            for (int rho = 0; rho < 16 + P4T - 1; rho++) {
+                const float2 v = col[rho * 64];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int r = j + P4T - 1 - rho;
+                    if (r >= 0 && r < P4T)
+                        acc[j] = __ffma2_rn(v, make_float2(hreg[r], hreg[r]), acc[j]);
+                }
+            }
+            // (re, im) of u_i[t] -> k = 2i, 2i + 1 of frame row t: bf16 hi and lo planes of stage st.
+            // The MMAs of tile it-2 that read this stage completed before this CTA drained them (epilogue below).
+            uint8_t* pl = planes + st * 2 * PFBT_PLANE + (i >> 5) * 8192 + (i & 3) * 4;
+            const int chunk = (i & 31) >> 2;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int n = tg * 16 + j;
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(acc[j].x, acc[j].y);
+                const float2 hf = __bfloat1622float2(hi);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[j].x - hf.x, acc[j].y - hf.y);
+                const int off = n * 128 + ((chunk ^ (n & 7)) << 4);
+                *reinterpret_cast<__nv_bfloat162*>(pl + off) = hi;
+                *reinterpret_cast<__nv_bfloat162*>(pl + PFBT_PLANE + off) = lo;
+            }
+        }
+        fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        tc_fence_before();
+        __syncthreads();     // planes complete; X fully consumed; accumulator stage st drained (tile it-2)
+        {
+            const long long nxt = tile + gridDim.x;
+            if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
+                mbar_arrive_expect_tx(bar, tile_bytes);
+                bulk_copy_g2s(X, x + (nxt * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
+            }
+        }
+        if (warp == 0) {
+            tc_fence_after();
+            const uint32_t pb = planes_s + st * 2 * PFBT_PLANE, d = tmem + 128 + st * 64;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                const uint32_t boff = (ks >> 2) * 8192 + (ks & 3) * 32;
+                const uint64_t bh = tc_desc(pb + boff, 0), bl = tc_desc(pb + PFBT_PLANE + boff, 0);
+                tc_mma_bf16_ts_w(d, tmem + ks * 8, bh, PFBT_IDESC, ks != 0);   // F_hi u_hi
+                tc_mma_bf16_ts_w(d, tmem + 64 + ks * 8, bh, PFBT_IDESC, 1);    // F_lo u_hi
+                tc_mma_bf16_ts_w(d, tmem + ks * 8, bl, PFBT_IDESC, 1);         // F_hi u_lo
+            }
+            tc_commit_w(smem_u32(bar + 1 + st));
+        }
+        if (it > 0)
+            epilogue(st ^ 1, (uint32_t)(((it - 1) >> 1) & 1), prev_f0);
+        prev_f0 = f0;
+    }
+    if (it > 0)
+        epilogue((it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1), prev_f0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tc_dealloc(tmem, PFBT_TMEM_COLS);
     }
 }
 
@@ -739,6 +945,26 @@ __global__ void pfb_tail_kernel(const float2* __restrict__ x, const float2* __re
 
 using namespace b200;
 
+// auto-selection of the M = 64 form: 0 = SIMT DFT, 1 = tensor-core DFT (set from the measured A/B)
+#ifndef PFB64_TC_DEFAULT
+#define PFB64_TC_DEFAULT 0
+#endif
+
+static inline uint16_t pfb_bf16_rn(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float pfb_bf16_f(uint16_t b)
+{
+    const uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
 struct b200_pfb {
     int M = 0, P = 0, P4 = 0;
     int ch_begin = 0, ch_count = 0;
@@ -748,6 +974,10 @@ struct b200_pfb {
     size_t smem = 0;
     int TT = 0;
     int grid = 296;
+    int tc = 0;            // M = 64: 1 = DFT across branches on the tensor cores (pfb64_tc_kernel), 0 = SIMT DFT
+    int tc_ok = 0;         // the tensor-core form exists for this (M, P)
+    uint4* d_dft = nullptr; // [128 rows = (channel, re/im)][hi 128 | lo 128] bf16 DFT matrix
+    size_t smem_tc = 0;
     int fusedM = 0; // 1: M = 16 / 32 / 128 / 256 on pfbm_kernel; 2: M = 4 / 8 on pfbs_kernel (single pass both)
     // generic M >= 16: branch filters -> scratch -> the library's own reverse FFT of length M
     b200_fft* ifft = nullptr;
@@ -761,7 +991,21 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
 {
     if (n_frames <= 0)
         return B200_OK;
-    if (h->M == 64) {
+    if (h->M == 64 && h->tc) {
+        long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
+        long long g = tiles < h->grid ? tiles : h->grid;
+#define PFBT_GO(PT)                                                                               \
+    B200_LAUNCH(pfb64_tc_kernel<PT>, (unsigned)g, 256, h->smem_tc, s, (const float2*)d_in,           \
+                (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->d_dft, h->P4, h->P, n_frames, \
+                n_in, h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
+        switch (h->P4) {
+        case 4: PFBT_GO(4); break;
+        case 8: PFBT_GO(8); break;
+        case 12: PFBT_GO(12); break;
+        default: PFBT_GO(16); break;
+        }
+#undef PFBT_GO
+    } else if (h->M == 64) {
         long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
         long long g = tiles < h->grid ? tiles : h->grid;
 #define PFB64_GO(PT)                                                                              \
@@ -867,6 +1111,7 @@ int b200_pfb_destroy(b200_pfb* h)
     cudaFree(h->d_tail[1]);
     cudaFree(h->d_u);
     cudaFree(h->d_full);
+    cudaFree(h->d_dft);
     b200_fft_destroy(h->ifft);
     delete h;
     return B200_OK;
@@ -925,6 +1170,32 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->grid = 2 * sm_count();
+        if (h->P4 <= 16) {
+            // tensor-core DFT form: DFT matrix rows m = 2c + part, columns k = 2i + (re | im), bf16 hi | lo
+            std::vector<uint16_t> F((size_t)128 * 256);
+            for (int m = 0; m < 128; m++)
+                for (int k = 0; k < 128; k++) {
+                    const int c = m >> 1, po = m & 1, i = k >> 1, pi = k & 1;
+                    const double th = 2.0 * M_PI * (double)((i * c) & 63) / 64.0;
+                    const double v = po == pi ? std::cos(th) : (po ? std::sin(th) : -std::sin(th));
+                    const float f = (float)v;
+                    const uint16_t hi = pfb_bf16_rn(f);
+                    F[(size_t)m * 256 + k] = hi;
+                    F[(size_t)m * 256 + 128 + k] = pfb_bf16_rn(f - pfb_bf16_f(hi));
+                }
+            PFB_CUDA(cudaMalloc(&h->d_dft, F.size() * 2));
+            PFB_CUDA(cudaMemcpy(h->d_dft, F.data(), F.size() * 2, cudaMemcpyHostToDevice));
+            h->smem_tc = 1024 + 4 * (size_t)PFBT_PLANE + sizeof(float2) * (size_t)rows * 64 +
+                         sizeof(float) * (size_t)h->P4 * 64 + 64;
+            PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
+            PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
+            PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
+            PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
+            h->tc_ok = 1;
+            h->tc = PFB64_TC_DEFAULT;
+            if (const char* e = getenv("B200_PFB_TC"))
+                h->tc = atoi(e) != 0;
+        }
     } else if ((M == 4 || M == 8) && !getenv("B200_PFB_TWOPASS") &&
                sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)M * (4096 / M + 1)) +
                        sizeof(float) * ((size_t)h->P4 * M + 1) + 16 <= 110 * 1024) {
@@ -1036,6 +1307,26 @@ int b200_pfb_run_segment(b200_pfb* h, const void* d_halo, const void* d_in, void
     if (rc == B200_OK && n_produced_vectors)
         *n_produced_vectors = n_frames;
     return rc;
+}
+
+int b200_pfb_set_algorithm(b200_pfb* h, int32_t algorithm)
+{
+    if (!h)
+        return set_err(B200_ERR_ARG, "pfb_set_algorithm: null handle");
+    if (algorithm < 0 || algorithm > 2)
+        return set_err(B200_ERR_ARG, "pfb_set_algorithm: algorithm must be 0 (auto), 1 (SIMT DFT) or 2 (tensor-core DFT)");
+    if (algorithm == 2 && !h->tc_ok)
+        return set_err(B200_ERR_UNSUPPORTED, "pfb_set_algorithm: the tensor-core DFT form needs 64 channels and <= 16 taps per channel");
+    h->tc = algorithm == 2 ? 1 : algorithm == 1 ? 0 : (h->tc_ok ? PFB64_TC_DEFAULT : 0);
+    return B200_OK;
+}
+
+int b200_pfb_get_algorithm(const b200_pfb* h, int32_t* algorithm)
+{
+    if (!h || !algorithm)
+        return set_err(B200_ERR_ARG, "pfb_get_algorithm: null argument");
+    *algorithm = h->tc ? 2 : 1;
+    return B200_OK;
 }
 
 int b200_pfb_geometry(const b200_pfb* h, int* n_channels, int* channel_count)

@@ -946,6 +946,67 @@ def test_pfb_matches_oracle_and_streams(cuda, M, P):
     assert np.array_equal(host(part), host(y)[:, M // 4:M // 4 + M // 2])
 
 
+@pytest.mark.parametrize("P", [16, 3, 8, 12])
+def test_pfb_dft_on_tensor_cores(cuda, P):
+    """BASELINE configs[3] 'filterbank + DFT as tensor-core GEMM': algorithm 2 (the 64-point DFT across branches as a
+    bf16-split tcgen05 GEMM, DFT matrix in tensor memory) against the fp64 oracle, the SIMT form, chunked streaming,
+    a channel slice and time segments with a halo."""
+    import scipy.signal as sig
+    import newsched_b200 as nb
+    M = 64
+    rng = np.random.default_rng(640 + P)
+    taps = sig.firwin(M * P, 1.0 / M).astype(np.float32)
+    x = cplx(rng, M * (64 * 7 + 29) + 11)                   # several 64-frame tiles and a ragged one
+    dx = dev(cuda, x)
+    ref = o.pfb_channelizer(x, taps, M)
+    tc = nb.PfbChannelizer(taps, M, algorithm=2)
+    assert tc.algorithm == 2
+    y, nc = tc.work(dx)
+    err = o.rel_rms(host(y), ref)
+    assert nc == (x.size // M) * M and err < TOL_RMS, err
+    # per channel too: no channel (row of the DFT matrix) may hide behind the others
+    yh = host(y).astype(np.complex128)
+    per_ch = np.sqrt((np.abs(yh - ref) ** 2).sum(axis=0) / (np.abs(ref) ** 2).sum(axis=0).clip(1e-30))
+    assert per_ch.max() < 4 * TOL_RMS, per_ch.max()         # stop-band channels carry little energy: looser
+    y1, _ = nb.PfbChannelizer(taps, M, algorithm=1).work(dx)
+    assert o.rel_rms(host(y), host(y1).astype(np.complex128)) < TOL_RMS
+    # chunked == one-shot, bit for bit (same arithmetic per frame whatever the tiling)
+    ch = nb.PfbChannelizer(taps, M, algorithm=2)
+    outs, pos = [], 0
+    for n_fr in (1, 2, 64, 100, 166, 67, 10 ** 6):
+        if pos + M > x.size:
+            break
+        yy, c = ch.work(dx[pos:pos + n_fr * M])
+        outs.append(host(yy))
+        pos += c
+    got = np.concatenate(outs)
+    assert np.array_equal(got, host(y)[: got.shape[0]]), "chunked tensor-core channelizer != one-shot"
+    part, _ = nb.PfbChannelizer(taps, M, channel_begin=16, channel_count=32, algorithm=2).work(dx)
+    assert np.array_equal(host(part), host(y)[:, 16:48])
+    # time segment with a halo == the same frames of the stream
+    cut = M * 200
+    seg = nb.PfbChannelizer(taps, M, algorithm=2).work_segment(dx[cut:], halo=dx[cut - (P - 1) * M:cut] if P > 1 else None)
+    assert np.array_equal(host(seg), host(y)[200:200 + seg.shape[0]])
+    # 8-byte aligned (not 16) input pointer: the tile is fetched without the bulk copy
+    xo = cuda.empty(x.size + 1, dtype=cuda.complex64, device="cuda")
+    xo[1:] = dx
+    yo, _ = nb.PfbChannelizer(taps, M, algorithm=2).work(xo[1:])
+    assert np.array_equal(host(yo), host(y))
+
+
+def test_pfb_tensor_core_form_rejects_what_it_cannot_do(cuda):
+    import scipy.signal as sig
+    import newsched_b200 as nb
+    with pytest.raises(nb.B200Error):
+        nb.PfbChannelizer(sig.firwin(32 * 8, 1 / 32).astype(np.float32), 32, algorithm=2)
+    with pytest.raises(nb.B200Error):
+        nb.PfbChannelizer(sig.firwin(64 * 32, 1 / 64).astype(np.float32), 64, algorithm=2)
+    tone = np.exp(2j * np.pi * 5 / 64 * np.arange(64 * 600)).astype(np.complex64)
+    y = host(nb.PfbChannelizer(sig.firwin(64 * 16, 1 / 64).astype(np.float32), 64, algorithm=2).work(dev(cuda, tone))[0])
+    p = (np.abs(y[16:]) ** 2).mean(axis=0)
+    assert int(np.argmax(p)) == 5 and p[5] > 1e3 * np.delete(p, 5).max()
+
+
 def test_pfb_tone(cuda):
     import scipy.signal as sig
     import newsched_b200 as nb
