@@ -79,7 +79,7 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 __global__ void __launch_bounds__(TC_THREADS, 2) fir_tc_kernel(const tc_args a)
 {
     extern __shared__ uint8_t tc_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = tc_align1024(tc_smem_raw);
     uint8_t* planes = smem;                                   // [re_hi][re_lo][im_hi][im_lo]
     uint8_t* ring = smem + 4 * (size_t)a.plane_bytes;         // tap atoms
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * TC_ATOM_BYTES);
@@ -321,7 +321,7 @@ __device__ __forceinline__ uint32_t tf_plane_off(uint32_t i)
 __global__ void __launch_bounds__(TC_THREADS, 2) fir_tc_tf32_kernel(const tc_args a)
 {
     extern __shared__ uint8_t tc_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = tc_align1024(tc_smem_raw);
     uint8_t* planes = smem;                                   // [re_hi][re_lo][im_hi][im_lo], tf32 in fp32 containers
     uint8_t* ring = smem + 4 * (size_t)a.plane_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * TC_ATOM_BYTES);
@@ -535,7 +535,7 @@ __device__ __forceinline__ void tc_convert(const tc_args& a, uint8_t* planes, in
 __global__ void __launch_bounds__(TCP_THREADS, 1) fir_tc_pipe_kernel(const tc_args a)
 {
     extern __shared__ uint8_t tc_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = tc_align1024(tc_smem_raw);
     uint8_t* planes = smem;                                          // [2 stages][re_hi, re_lo, im_hi, im_lo]
     uint8_t* ring = smem + 8 * (size_t)a.plane_bytes;                // tap atoms
     uint8_t* xbuf = ring + (size_t)a.stages * TC_ATOM_BYTES;         // [2] exchange buffers
@@ -758,7 +758,7 @@ __device__ __forceinline__ bool ts_fast_tile(const tc_args& a, long long j0)
 __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args a)
 {
     extern __shared__ uint8_t tc_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = tc_align1024(tc_smem_raw);
     uint8_t* planes = smem;                                          // [stages][re_hi, re_lo, im_hi, im_lo]
     uint8_t* staging = planes + (size_t)a.ts_stages * 4 * a.ts_plane_bytes; // [TS_IN_STAGES] raw complex64 tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (size_t)TS_IN_STAGES * a.ts_stage_bytes);

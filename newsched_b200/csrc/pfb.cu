@@ -306,9 +306,9 @@ __global__ void __launch_bounds__(256, 2)
 // (K-atoms: branches 0..31 / 32..63); the filter thread of branch i writes (re, im) of a frame as ONE
 // 32-bit store per plane, a warp covers a whole row -- the same 8 B/sample of shared-memory stores the SIMT
 // kernel spends on U, and nothing else: no DFT loads, stores, twiddles or butterflies.
-// Epilogue: TMEM lane 2c + part holds y_part[c] of 32 frames per warp; neighbouring lanes swap odd/even
-// frames with one shuffle each and store (re, im) pairs, 16 consecutive channels = one 128-byte line per
-// half-warp.  Tiles are software-pipelined: the MMAs of tile i run while the CTA drains tile i-1 and the
+// Epilogue: TMEM lane 2c + part holds y_part[c] of 32 frames per warp, i.e. the lanes of a warp are the 32
+// consecutive floats (16 channels x re, im) of a frame: every store instruction writes one whole 128-byte line,
+// with no exchange between lanes.  Tiles are software-pipelined: the MMAs of tile i run while the CTA drains tile i-1 and the
 // other resident CTA filters (2 CTAs/SM, 256 TMEM columns each: DFT 128 + 2 accumulator stages of 64).
 constexpr int PFBT_PLANE = 2 * 64 * 128; // one plane (hi or lo) of a tile: 2 K-atoms x 64 frames x 128 bytes
 constexpr int PFBT_TMEM_COLS = 256;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256, 2)
                     int P4, int Ptrue, long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok)
 {
     extern __shared__ uint8_t pfbt_raw[];
-    uint8_t* planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pfbt_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* planes = tc_align1024(pfbt_raw);
     const int rows = PFB64_TT + P4 - 1;
     float2* X = reinterpret_cast<float2*>(planes + 4 * PFBT_PLANE); // [stage][hi, lo] planes in front
     float* hT = reinterpret_cast<float*>(X + rows * 64);
@@ -376,16 +376,20 @@ __global__ void __launch_bounds__(256, 2)
         tc_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + st * 64 + half * 32, v);
         tc_wait_ld();
         tc_fence_before();
-        const int part = lane & 1, c = quarter * 16 + (lane >> 1);
-        const bool ch_ok = c >= ch_begin && c < ch_begin + ch_count;
-        float2* y = out + (f0 + half * 32 + part) * ch_count - ch_begin + c;
+        // lane 2c + part of the quarter holds y_part[c] of 32 frames: lanes store their own float, so a warp writes
+        // the 16 (re, im) pairs of one frame as ONE contiguous 128-byte line per instruction -- no exchange at all
+        const int c = quarter * 16 + (lane >> 1);
+        float* y = reinterpret_cast<float*>(out + (f0 + half * 32) * ch_count - ch_begin + c) + (lane & 1);
+        if (ch_count == 64 && f0 + PFB64_TT <= n_frames) {
 #pragma unroll
-        for (int p = 0; p < 16; p++) {
-            // even lane: re of frames 2p, 2p+1; odd lane: im.  Even keeps frame 2p, odd keeps frame 2p+1.
-            const float recv = __shfl_xor_sync(0xffffffffu, part ? v[2 * p] : v[2 * p + 1], 1);
-            const float2 r = part ? make_float2(recv, v[2 * p + 1]) : make_float2(v[2 * p], recv);
-            if (ch_ok && f0 + half * 32 + 2 * p + part < n_frames)
-                __stcs(y + (long long)(2 * p) * ch_count, r);
+            for (int n = 0; n < 32; n++)
+                __stcs(y + n * 128, v[n]);
+        } else {
+            const bool ch_ok = c >= ch_begin && c < ch_begin + ch_count;
+#pragma unroll
+            for (int n = 0; n < 32; n++)
+                if (ch_ok && f0 + half * 32 + n < n_frames)
+                    __stcs(y + (long long)n * 2 * ch_count, v[n]);
         }
     };
 

@@ -6,6 +6,15 @@
 
 namespace b200 {
 
+// 1024-byte aligned start inside a dynamic shared-memory array.  The offset is computed from the 32-bit shared
+// address and ADDED to the array, so the compiler keeps the shared address space of everything derived from it
+// (LDS / STS with 32-bit addresses); rounding the generic pointer as an integer loses that and turns every
+// access into a generic LD / ST with 64-bit address arithmetic.
+__device__ __forceinline__ uint8_t* tc_align1024(uint8_t* raw)
+{
+    return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 // ---- tcgen05 / TMEM PTX ------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

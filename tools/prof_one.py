@@ -1,5 +1,5 @@
 """Runs one hot-path kernel a few times on synthetic data (for ncu captures / launch lists).
-usage: python tools/prof_one.py fftmag|fft|fftnN|tcT|fir64simt|fir64|firdec64d4|firdec64d5|rs32|fir1024d4|fir4096|ffa64|pfb|pfb16|copy [reps]"""
+usage: python tools/prof_one.py fftmag|fft|fftnN|tcT|fir64simt|fir64|firdec64d4|firdec64d5|rs32|fir1024d4|fir4096|ffa64|pfb|pfbtc|pfb16|copy [reps]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -49,9 +49,13 @@ elif what == "fir1024d4":
 elif what == "fir4096":
     n = 1 << 26; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
     op = nb.FirFilter((rng.uniform(-1, 1, 4096) / 4096).astype(np.float32), 1); out = torch.empty_like(x); fn = lambda: op.work_segment(x, None, out)
+elif what == "pfbtc":               # 64 channels, the DFT on the tensor cores (algorithm 2)
+    import scipy.signal as sig
+    n = N * 32768; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    op = nb.PfbChannelizer(sig.firwin(1024, 1 / 64).astype(np.float32), 64, algorithm=2); out = torch.empty_like(x).view(-1, 64); fn = lambda: op.work_segment(x, None, out)
 elif what == "pfb":
     import scipy.signal as sig
-    op = nb.PfbChannelizer(sig.firwin(1024, 1 / 64).astype(np.float32), 64); out = torch.empty_like(x).view(-1, 64); fn = lambda: op.work_segment(x, None, out)
+    op = nb.PfbChannelizer(sig.firwin(1024, 1 / 64).astype(np.float32), 64, algorithm=1); out = torch.empty_like(x).view(-1, 64); fn = lambda: op.work_segment(x, None, out)
 else:
     out = torch.empty_like(x); fn = lambda: nb.copy(x, out)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

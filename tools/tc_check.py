@@ -64,8 +64,7 @@ def child(kind, T, D, mode):
         out = torch.empty(n // D, dtype=torch.complex64, device="cuda")
         res = {"kind": kind, "T": T, "D": D}
         for algo, pipe in ((ALGO, variant), (2, "pipe"), (3, ""), (0, "")):
-            if pipe:
-                os.environ.update(VARIANTS[pipe])
+            os.environ.update(VARIANTS[pipe] if pipe else VARIANTS["ts"])   # algorithms 3 / 0: the library's defaults
             f = nb.FirFilter(taps, D, algorithm=algo)
             for _ in range(3):
                 f.work_segment(x, None, out)
@@ -114,7 +113,7 @@ def main():
                 good_mode = mode
         print(json.dumps({"good_desc_mode": good_mode}), flush=True)
     if what in ("time", "all"):
-        mode = good_mode if good_mode is not None else "pipe"
+        mode = good_mode if good_mode is not None else "ts"
         for T, D in TIMING:
             r = subprocess.run([sys.executable, __file__, "child", "time", str(T), str(D), str(mode)],
                                capture_output=True, text=True, timeout=300)
