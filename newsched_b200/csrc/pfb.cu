@@ -308,38 +308,48 @@ __global__ void __launch_bounds__(256, 2)
 // kernel spends on U, and nothing else: no DFT loads, stores, twiddles or butterflies.
 // Epilogue: TMEM lane 2c + part holds y_part[c] of 32 frames per warp, i.e. the lanes of a warp are the 32
 // consecutive floats (16 channels x re, im) of a frame: every store instruction writes one whole 128-byte line,
-// with no exchange between lanes.  Tiles are software-pipelined: the MMAs of tile i run while the CTA drains tile i-1 and the
-// other resident CTA filters (2 CTAs/SM, 256 TMEM columns each: DFT 128 + 2 accumulator stages of 64).
+// with no exchange between lanes.  Tiles are software-pipelined: the MMAs of tile i run while the CTA drains tile
+// i-1 and filters tile i+1, whose input arrived a whole tile earlier (two input buffers: with one, the copy had only
+// the short epilogue to hide behind and a fifth of all warp samples sat on its mbarrier).  2 CTAs/SM, 256 TMEM
+// columns each (DFT matrix 128 + 2 accumulator stages of 64); the branch taps live in registers.
 constexpr int PFBT_PLANE = 2 * 64 * 128; // one plane (hi or lo) of a tile: 2 K-atoms x 64 frames x 128 bytes
 constexpr int PFBT_TMEM_COLS = 256;
 constexpr uint32_t PFBT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
+constexpr int PFBT_THREADS = 288; // 8 worker warps (filters, conversion, epilogue) + 1 issuer warp (TMA refills, MMAs)
+
+__device__ __forceinline__ void pfbt_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(PFBT_THREADS) : "memory"); }
+__device__ __forceinline__ void pfbt_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(PFBT_THREADS) : "memory"); }
+__device__ __forceinline__ void pfbt_workers_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+
 template <int P4T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(PFBT_THREADS, 2)
     pfb64_tc_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
                     const float* __restrict__ taps_rm /* [P4][64] */, const uint4* __restrict__ gA /* [128][hi 128 | lo 128] bf16 */,
                     int P4, int Ptrue, long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok)
 {
     extern __shared__ uint8_t pfbt_raw[];
-    uint8_t* planes = tc_align1024(pfbt_raw);
+    uint8_t* planes = tc_align1024(pfbt_raw);                       // [hi, lo] planes of the tile being multiplied
     const int rows = PFB64_TT + P4 - 1;
-    float2* X = reinterpret_cast<float2*>(planes + 4 * PFBT_PLANE); // [stage][hi, lo] planes in front
-    float* hT = reinterpret_cast<float*>(X + rows * 64);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + P4 * 64);      // [0]: X landed, [1], [2]: accumulator stage complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+    float2* X0 = reinterpret_cast<float2*>(planes + 2 * PFBT_PLANE); // two input tiles: the copy of tile i+1 lands while tile i is filtered
+    uint64_t* bar = reinterpret_cast<uint64_t*>(X0 + 2 * rows * 64); // [0], [1]: input tile landed; [2], [3]: accumulator stage complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 4);
     const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
     if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
-        mbar_init(bar + 2, 1);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            mbar_init(bar + b, 1);
         fence_mbar_init();
     }
     if (warp == 0) {
         __syncwarp();
         tc_alloc(tmem_slot, PFBT_TMEM_COLS);
     }
-    for (int i = tid; i < P4 * 64; i += 256)
-        hT[i] = __ldg(taps_rm + i);
+    // this thread's branch taps: constants of the thread, register resident for the lifetime of the CTA
+    float hreg[P4T];
+#pragma unroll
+    for (int r = 0; r < P4T; r++)
+        hreg[r] = __ldg(taps_rm + r * 64 + (tid & 63));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -367,10 +377,12 @@ __global__ void __launch_bounds__(256, 2)
         const long long g0 = (t * PFB64_TT - (P4 - 1)) * 64;
         return tma_ok && g0 >= 0 && g0 + (long long)rows * 64 <= n_in;
     };
-    // drain accumulator stage `st` (tile starting at frame f0) into out
-    auto epilogue = [&](int st, uint32_t parity, long long f0) {
-        mbar_wait(bar + 1 + st, parity);
-        tc_fence_after();
+    auto issue = [&](long long t, int b) { // one elected thread
+        mbar_arrive_expect_tx(bar + b, tile_bytes);
+        bulk_copy_g2s(X0 + b * rows * 64, x + (t * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar + b);
+    };
+    // drain accumulator stage `st` (tile starting at frame f0) into out; the caller has waited for its MMAs
+    auto epilogue = [&](int st, long long f0) {
         const int quarter = warp & 3, half = warp >> 2;
         float v[32];
         tc_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + 128 + st * 64 + half * 32, v);
@@ -394,47 +406,76 @@ __global__ void __launch_bounds__(256, 2)
     };
 
     long long tile = blockIdx.x;
-    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
-        mbar_arrive_expect_tx(bar, tile_bytes);
-        bulk_copy_g2s(X, x + (tile * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
-    }
-    uint32_t xphase = 0;
-    int it = 0;
-    long long prev_f0 = 0;
     const uint32_t planes_s = smem_u32(planes);
-    for (; tile < n_tiles; tile += gridDim.x, it++) {
-        const long long f0 = tile * PFB64_TT;
-        const int st = it & 1;
-        if (tma_tile(tile)) {
-            mbar_wait(bar, xphase);
-            xphase ^= 1;
-        } else {
-            const long long g0 = (f0 - (P4 - 1)) * 64;
-            for (int i0 = tid; i0 < rows * 64; i0 += 256 * 8) {
-                float2 v[8];
+    if (warp == 8) {
+        // ================= issuer warp: input copies and MMAs =================
+        if (lane == 0) {
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + u * 256 < rows * 64)
-                        v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (i0 + u * 256 < rows * 64)
-                        X[i0 + u * 256] = v[u];
+            for (int b = 0; b < 2; b++) {
+                const long long t = tile + (long long)b * gridDim.x;
+                if (t < n_tiles && tma_tile(t))
+                    issue(t, b);
             }
-            __syncthreads();
         }
-        // ---- branch filters: thread = (branch i, 16 consecutive frames), as in pfb64_kernel
-        {
+        __syncwarp();
+        for (int it = 0; tile < n_tiles; tile += gridDim.x, it++) {
+            const int st = it & 1;
+            // every worker has written its part of the planes (and fenced it for the async proxy), is done with
+            // input buffer st, and has drained accumulator stage st (tile it-2)
+            pfbt_bar_sync(1 + st);
+            tc_fence_after();
+            const long long nxt = tile + 2LL * gridDim.x; // refill the buffer just consumed: two tiles ahead
+            if (lane == 0 && nxt < n_tiles && tma_tile(nxt))
+                issue(nxt, st);
+            __syncwarp();
+            const uint32_t d = tmem + 128 + st * 64;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                const uint32_t boff = (ks >> 2) * 8192 + (ks & 3) * 32;
+                const uint64_t bh = tc_desc(planes_s + boff, 0), bl = tc_desc(planes_s + PFBT_PLANE + boff, 0);
+                tc_mma_bf16_ts_w(d, tmem + ks * 8, bh, PFBT_IDESC, ks != 0);   // F_hi u_hi
+                tc_mma_bf16_ts_w(d, tmem + 64 + ks * 8, bh, PFBT_IDESC, 1);    // F_lo u_hi
+                tc_mma_bf16_ts_w(d, tmem + ks * 8, bl, PFBT_IDESC, 1);         // F_hi u_lo
+            }
+            tc_commit_w(smem_u32(bar + 2 + st));
+        }
+    } else {
+        // ================= worker warps: no barrier among themselves in the steady state =================
+        uint32_t xph = 0; // bit b: parity of the next completion of bar[b]
+        int it = 0;
+        long long prev_f0 = 0;
+        for (; tile < n_tiles; tile += gridDim.x, it++) {
+            const long long f0 = tile * PFB64_TT;
+            const int st = it & 1;
+            float2* X = X0 + st * rows * 64;
+            if (tma_tile(tile)) {
+                mbar_wait(bar + st, (xph >> st) & 1u);
+                xph ^= 1u << st;
+            } else {
+                // edge tile (history in front of the call, ragged end, unaligned stream): fetched element-wise.  The
+                // buffer is free: the issuer refills it only for tiles that pass tma_tile
+                const long long g0 = (f0 - (P4 - 1)) * 64;
+                pfbt_workers_sync(); // nobody still filters the tile that used this buffer two tiles ago
+                for (int i0 = tid; i0 < rows * 64; i0 += 256 * 8) {
+                    float2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (i0 + u * 256 < rows * 64)
+                            v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (i0 + u * 256 < rows * 64)
+                            X[i0 + u * 256] = v[u];
+                }
+                pfbt_workers_sync();
+            }
+            // ---- branch filters: thread = (branch i, 16 consecutive frames), as in pfb64_kernel
             const int i = tid & 63, tg = tid >> 6;
             const float2* col = X + (63 - i) + (tg * 16) * 64;
             float2 acc[16];
 #pragma unroll
             for (int j = 0; j < 16; j++)
                 acc[j] = make_float2(0.f, 0.f);
-            float hreg[P4T];
-#pragma unroll
-            for (int r = 0; r < P4T; r++)
-                hreg[r] = hT[r * 64 + i];
 #pragma unroll
             for (int rho = 0; rho < 16 + P4T - 1; rho++) {
                 const float2 v = col[rho * 64];
@@ -445,9 +486,15 @@ __global__ void __launch_bounds__(256, 2)
                         acc[j] = __ffma2_rn(v, make_float2(hreg[r], hreg[r]), acc[j]);
                 }
             }
-            // (re, im) of u_i[t] -> k = 2i, 2i + 1 of frame row t: bf16 hi and lo planes of stage st.
-            // The MMAs of tile it-2 that read this stage completed before this CTA drained them (epilogue below).
-            uint8_t* pl = planes + st * 2 * PFBT_PLANE + (i >> 5) * 8192 + (i & 3) * 4;
+            // the MMAs of the previous tile must have read the planes before they are overwritten (they were
+            // issued a whole filter pass ago: this wait is normally over already); it also publishes that
+            // tile's accumulator stage for the epilogue below
+            if (it > 0) {
+                mbar_wait(bar + 2 + (st ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
+                tc_fence_after();
+            }
+            // (re, im) of u_i[t] -> k = 2i, 2i + 1 of frame row t: bf16 hi and lo planes
+            uint8_t* pl = planes + (i >> 5) * 8192 + (i & 3) * 4;
             const int chunk = (i & 31) >> 2;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
@@ -459,36 +506,19 @@ __global__ void __launch_bounds__(256, 2)
                 *reinterpret_cast<__nv_bfloat162*>(pl + off) = hi;
                 *reinterpret_cast<__nv_bfloat162*>(pl + PFBT_PLANE + off) = lo;
             }
+            fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            tc_fence_before();
+            pfbt_bar_arrive(1 + st); // hand the tile to the issuer and carry on: no wait here
+            if (it > 0)
+                epilogue(st ^ 1, prev_f0);
+            prev_f0 = f0;
         }
-        fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        tc_fence_before();
-        __syncthreads();     // planes complete; X fully consumed; accumulator stage st drained (tile it-2)
-        {
-            const long long nxt = tile + gridDim.x;
-            if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
-                mbar_arrive_expect_tx(bar, tile_bytes);
-                bulk_copy_g2s(X, x + (nxt * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
-            }
-        }
-        if (warp == 0) {
+        if (it > 0) {
+            mbar_wait(bar + 2 + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
             tc_fence_after();
-            const uint32_t pb = planes_s + st * 2 * PFBT_PLANE, d = tmem + 128 + st * 64;
-#pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-                const uint32_t boff = (ks >> 2) * 8192 + (ks & 3) * 32;
-                const uint64_t bh = tc_desc(pb + boff, 0), bl = tc_desc(pb + PFBT_PLANE + boff, 0);
-                tc_mma_bf16_ts_w(d, tmem + ks * 8, bh, PFBT_IDESC, ks != 0);   // F_hi u_hi
-                tc_mma_bf16_ts_w(d, tmem + 64 + ks * 8, bh, PFBT_IDESC, 1);    // F_lo u_hi
-                tc_mma_bf16_ts_w(d, tmem + ks * 8, bl, PFBT_IDESC, 1);         // F_hi u_lo
-            }
-            tc_commit_w(smem_u32(bar + 1 + st));
+            epilogue((it - 1) & 1, prev_f0);
         }
-        if (it > 0)
-            epilogue(st ^ 1, (uint32_t)(((it - 1) >> 1) & 1), prev_f0);
-        prev_f0 = f0;
     }
-    if (it > 0)
-        epilogue((it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1), prev_f0);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -999,7 +1029,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
         long long g = tiles < h->grid ? tiles : h->grid;
 #define PFBT_GO(PT)                                                                               \
-    B200_LAUNCH(pfb64_tc_kernel<PT>, (unsigned)g, 256, h->smem_tc, s, (const float2*)d_in,           \
+    B200_LAUNCH(pfb64_tc_kernel<PT>, (unsigned)g, PFBT_THREADS, h->smem_tc, s, (const float2*)d_in,           \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->d_dft, h->P4, h->P, n_frames, \
                 n_in, h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
         switch (h->P4) {
@@ -1189,8 +1219,7 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
                 }
             PFB_CUDA(cudaMalloc(&h->d_dft, F.size() * 2));
             PFB_CUDA(cudaMemcpy(h->d_dft, F.data(), F.size() * 2, cudaMemcpyHostToDevice));
-            h->smem_tc = 1024 + 4 * (size_t)PFBT_PLANE + sizeof(float2) * (size_t)rows * 64 +
-                         sizeof(float) * (size_t)h->P4 * 64 + 64;
+            h->smem_tc = 1024 + 2 * (size_t)PFBT_PLANE + 2 * sizeof(float2) * (size_t)rows * 64 + 64;
             PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
             PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
             PFB_CUDA(cudaFuncSetAttribute(pfb64_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_tc));
