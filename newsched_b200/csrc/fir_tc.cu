@@ -69,6 +69,8 @@ struct tc_args {
     const uint32_t* gAt; // TMEM-resident form: tap matrix [128 lanes][16*ksteps / 2] bf16 pairs, K contiguous
     int ts_plane_elems, ts_plane_bytes, ts_stages, ts_stage_bytes;
     int ts_swap;     // diagnostic: swap the bf16 halves of every 32-bit TMEM column of A
+    int ts_nohead;   // A/B: head tile through the element-wise path (B200_TC_TS_HEAD=0)
+    int ts_pdl;      // launched with programmatic stream serialization: griddepcontrol.wait after the prologue
     int dbg;         // bottleneck attribution (B200_TC_DBG): 1 = skip conversion, 2 = skip epilogue, 4 = skip MMAs, 8 = skip input copies
 };
 
@@ -748,10 +750,17 @@ constexpr uint32_t TS_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 // that start on any item (8 bytes): when x is only 8-byte aligned the copy starts one sample early (`shift` = 1,
 // the bulk copy needs 16-byte alignment) and the converters skip that sample.
 __device__ __forceinline__ int ts_shift(const tc_args& a) { return (int)((reinterpret_cast<uintptr_t>(a.x) >> 3) & 1); }
+// head tile of a call: its first P samples are history (or zeros), the other 4096 are x[0 .. 4096).  The producer
+// warp copies the history part itself and sends the rest as a bulk copy, so the tile runs through the same staged
+// conversion as an interior one (the element-wise path costs ~3 us, on the CTA that has the most tiles).
+__device__ __forceinline__ bool ts_head_tile(const tc_args& a, long long j0)
+{
+    return j0 == -(long long)a.P && a.P > 0 && ts_shift(a) == 0 && a.ts_plane_elems - a.P <= a.n_in && !a.ts_nohead;
+}
 __device__ __forceinline__ bool ts_fast_tile(const tc_args& a, long long j0)
 {
     const int sh = ts_shift(a);
-    return j0 - sh >= 0 && j0 + a.ts_plane_elems + sh <= a.n_in;
+    return (j0 - sh >= 0 && j0 + a.ts_plane_elems + sh <= a.n_in) || ts_head_tile(a, j0);
 }
 
 
@@ -772,7 +781,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
 
     const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
     const long long n_tiles = (a.n_out + TS_TILE - 1) / TS_TILE;
-    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    // CTA order reversed: the head tile (history in front of the call) goes to the LAST CTA, which has one tile
+    // fewer than the first ones whenever the tiles do not divide evenly
+    const long long bid = (long long)(gridDim.x - 1 - blockIdx.x);
+    const int my_tiles = (int)((n_tiles - bid + gridDim.x - 1) / gridDim.x);
     const int S = a.ts_stages;
 
     if (tid == 0) {
@@ -822,6 +834,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
     __syncthreads();
     tc_fence_after();
     const uint32_t d_base = tmem + TS_A_COLS;
+    if (a.ts_pdl) {
+        // programmatic dependent launch: everything above (barriers, TMEM, the tap upload) overlapped the tail of
+        // the previous kernel in the stream; nothing below may start before that kernel has completed and flushed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     if (warp == 0) {
         // ================= MMA issuer =================
@@ -854,12 +872,26 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
         // ================= input producer =================
         int nf = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const long long j0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TS_TILE - a.P;
+            const long long j0 = (bid + (long long)it * gridDim.x) * TS_TILE - a.P;
             if (!ts_fast_tile(a, j0))
                 continue;                                            // edge tile: the converters read it themselves
             const int slot = nf % TS_IN_STAGES;
             mbar_wait(&in_empty[slot], ((nf / TS_IN_STAGES) & 1) ^ 1);
-            if (lane == 0) {
+            if (j0 < 0) {
+                // head tile: history (or zeros) by this warp, x[0 .. 4096) as a bulk copy behind it; the mbarrier
+                // arrive below releases the generic stores to the converters
+                float2* st = reinterpret_cast<float2*>(staging + (size_t)slot * a.ts_stage_bytes);
+                for (int i = lane; i < a.P; i += 32) {
+                    const int n = i - a.P;
+                    st[i] = (a.hist != nullptr && n >= -a.Tm1) ? __ldg(a.hist + (a.Tm1 + n)) : make_float2(0.f, 0.f);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)(a.ts_plane_elems - a.P) * 8u;
+                    mbar_arrive_expect_tx(&in_full[slot], bytes);
+                    bulk_copy_g2s(st + a.P, a.x, bytes, &in_full[slot]);
+                }
+            } else if (lane == 0) {
                 const int sh = ts_shift(a);
                 const uint32_t bytes = (uint32_t)(a.ts_plane_elems + 2 * sh) * 8u;
                 if (a.dbg & 8) {
@@ -880,7 +912,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
         const uint32_t tl = d_base + ((uint32_t)(quarter * 32) << 16);
         for (int it = 0; it < my_tiles; it++) {
             const int acc = it & 1;
-            const long long m0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TS_TILE;
+            const long long m0 = (bid + (long long)it * gridDim.x) * TS_TILE;
             const long long left = a.n_out - m0;
             const int count = left < TS_TILE ? (int)left : TS_TILE;
             float2* dst = a.y + m0;
@@ -920,7 +952,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
         const int ctid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
         int nf = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const long long m0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TS_TILE;
+            const long long m0 = (bid + (long long)it * gridDim.x) * TS_TILE;
             const int ps = it % S;
             uint8_t* pl = planes + (size_t)ps * 4 * a.ts_plane_bytes;
             mbar_wait(&planes_empty[ps], ((it / S) & 1) ^ 1);
@@ -1262,7 +1294,30 @@ int tc_launch(tc_plan* p, const float* d_hist, const void* d_in, void* d_out, lo
         a.ts_stage_bytes = p->ts_stage_bytes;
         a.ts_swap = p->ts_swap;
         const long long ts_tiles = (n_out + TS_TILE - 1) / TS_TILE, sms = sm_count();
-        B200_LAUNCH(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
+        static const int no_head = [] { const char* e = getenv("B200_TC_TS_HEAD"); return e && atoi(e) == 0; }();
+        static const int use_pdl = [] { const char* e = getenv("B200_TC_PDL"); return !e || atoi(e) != 0; }();
+        a.ts_nohead = no_head;
+        a.ts_pdl = use_pdl;
+        if (!use_pdl) {
+            B200_LAUNCH(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
+            return B200_OK;
+        }
+        // programmatic dependent launch: this kernel's CTAs may become resident (and run their prologue) while the
+        // previous kernel in the stream drains; the kernel orders itself with griddepcontrol.wait
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(ts_tiles < sms ? ts_tiles : sms));
+        cfg.blockDim = dim3(TS_THREADS);
+        cfg.dynamicSmemBytes = p->ts_smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, fir_tc_ts_kernel, a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess)
+            return set_err(B200_ERR_CUDA, "fir(tensor core): launch fir_tc_ts_kernel -> %s", cudaGetErrorString(le));
         return B200_OK;
     }
     if (p->pipe) {
