@@ -38,6 +38,31 @@ inline cudaStream_t cs(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(
                                    __LINE__, #kernel, cudaGetErrorString(e__));          \
     } while (0)
 
+// Launch with programmatic stream serialization (programmatic dependent launch): the kernel's CTAs may become
+// resident while the previous kernel in the stream drains.  The KERNEL must order itself: griddepcontrol.wait
+// before it touches anything a predecessor in the stream may have written or may still read.
+#define B200_LAUNCH_PDL(kernel, grid_, block_, smem_, stream_, ...)                          \
+    do {                                                                                 \
+        cudaLaunchConfig_t cfg__{};                                                      \
+        cfg__.gridDim = dim3(grid_);                                                     \
+        cfg__.blockDim = dim3(block_);                                                   \
+        cfg__.dynamicSmemBytes = (smem_);                                                \
+        cfg__.stream = (stream_);                                                        \
+        cudaLaunchAttribute attr__[1];                                                   \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;               \
+        attr__[0].val.programmaticStreamSerializationAllowed = 1;                        \
+        cfg__.attrs = attr__;                                                            \
+        cfg__.numAttrs = 1;                                                              \
+        cudaError_t e__ = cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);               \
+        ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+        if (e__ != cudaSuccess)                                                          \
+            return ::b200::set_err(B200_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__,     \
+                                   __LINE__, #kernel, cudaGetErrorString(e__));          \
+    } while (0)
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 int sm_count();
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda);

@@ -190,6 +190,10 @@ __global__ void __launch_bounds__(256, 2)
     for (int k1 = 1; k1 < 16; k1++)
         t2r[k1] = sT2[k1 * 16 + (tid & 15)];
 #endif
+    // programmatic dependent launch (B200_LAUNCH_PDL): the prologue above ran while the previous kernel in the
+    // stream drained; nothing below may start before that kernel has completed and flushed
+    pdl_wait();
+    pdl_launch_dependents();
     long long vec = blockIdx.x;
     if (tid == 0) {
         // NBUF input buffers: the copy of vector i + NBUF starts as soon as pass 1 of vector i
@@ -947,7 +951,7 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
     if (h->N == 4096) {
         long long g = n_vec < h->grid_4k ? n_vec : h->grid_4k;
         if (h->use_tma && (uintptr_t)d_in % 16 == 0)
-            B200_LAUNCH((fft4096_tma_kernel<FWD, OUT>), (unsigned)g, 256, f4k_tma_smem(OUT), s,
+            B200_LAUNCH_PDL((fft4096_tma_kernel<FWD, OUT>), (unsigned)g, 256, f4k_tma_smem(OUT), s,
                         (const float2*)d_in, d_out, n_vec, h->d_weff, h->d_tw1, h->d_tw2);
         else
             B200_LAUNCH((fft4096_kernel<FWD, OUT>), (unsigned)g, 256, 0, s, (const float2*)d_in, d_out,

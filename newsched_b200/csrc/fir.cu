@@ -58,6 +58,11 @@ __global__ void __launch_bounds__(256)
 __global__ void fir_hist_kernel(const float* __restrict__ x, const float* __restrict__ hist_old,
                                 float* __restrict__ hist_new, long long n_consumed, int Tm1, int VEC)
 {
+    // launched with programmatic stream serialization (B200_LAUNCH_PDL): the filter kernel of the NEXT work() call may
+    // start its prologue right away; this kernel waits for the filter kernel in front of it (which still reads
+    // hist_old's twin) before it touches anything
+    pdl_launch_dependents();
+    pdl_wait();
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Tm1)
         return;
@@ -712,8 +717,8 @@ int b200_fir_run(b200_fir* h, const void* d_in, void* d_out, int64_t n_in_items,
         return rc;
     if (h->T > 1 && n_cons > 0) {
         int Tm1 = h->T - 1;
-        B200_LAUNCH(fir_hist_kernel, (Tm1 + 255) / 256, 256, 0, cs(s), (const float*)d_in,
-                    h->d_hist[h->cur], h->d_hist[h->cur ^ 1], n_cons, Tm1, h->vec);
+        B200_LAUNCH_PDL(fir_hist_kernel, (Tm1 + 255) / 256, 256, 0, cs(s), (const float*)d_in,
+                        (const float*)h->d_hist[h->cur], h->d_hist[h->cur ^ 1], (long long)n_cons, Tm1, h->vec);
         h->cur ^= 1;
     }
     if (n_consumed)

@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(256, 2)
             bulk_copy_g2s(sIn, x + seg_start(b), OLS_N * 8, bar);
         }
     };
+    // programmatic dependent launch (B200_LAUNCH_PDL): the prologue above ran while the previous kernel in the
+    // stream drained; nothing below may start before that kernel has completed and flushed
+    pdl_wait();
+    pdl_launch_dependents();
     long long blk = blockIdx.x;
     if (tid == 0 && blk < g.n_blocks && tma_block(blk))
         issue(blk);
@@ -331,6 +335,10 @@ __global__ void __launch_bounds__(256, 2)
         for (int c = 0; c < 16; c++)
             tma_load_box2d(sP + c * 512, &tmap, 2 * pair, (int)(r + 256 * c), bar);
     };
+    // programmatic dependent launch (B200_LAUNCH_PDL): the prologue above ran while the previous kernel in the
+    // stream drained; nothing below may start before that kernel has completed and flushed
+    pdl_wait();
+    pdl_launch_dependents();
     long long blk = blockIdx.x;
     if (tid == 0 && blk < g.n_blocks && tma_block(blk))
         issue(blk, 0);
@@ -474,6 +482,10 @@ __global__ void __launch_bounds__(256, 2)
         bulk_copy_g2s(sP, x + first(b), OLS_N * 8, bar);
         bulk_copy_g2s(sP + OLS_N, x + first(b) + OLS_N, OLS_N * 8, bar);
     };
+    // programmatic dependent launch (B200_LAUNCH_PDL): the prologue above ran while the previous kernel in the
+    // stream drained; nothing below may start before that kernel has completed and flushed
+    pdl_wait();
+    pdl_launch_dependents();
     long long blk = blockIdx.x;
     if (tid == 0 && blk < g.n_blocks && tma_block(blk))
         issue(blk);
@@ -842,7 +854,7 @@ static int olsd_launch(ols_plan* p, const float* d_hist, const void* d_in, void*
         if (atoi(e) == 0)
             g.tma_ok = 0;
     const long long grid = g.n_blocks < p->grid ? g.n_blocks : p->grid;
-    B200_LAUNCH(fir_olsd_kernel, (unsigned)grid, 256, OLSD_SMEM, s, (const float2*)d_in, (const float2*)d_hist,
+    B200_LAUNCH_PDL(fir_olsd_kernel, (unsigned)grid, 256, OLSD_SMEM, s, (const float2*)d_in, (const float2*)d_hist,
                 (float2*)d_out, p->d_G, p->d_tw1, p->d_tw2, tmap, g);
     return B200_OK;
 }
@@ -866,7 +878,7 @@ static int ols2_launch(ols_plan* p, const float* d_hist, const void* d_in, void*
         g.c00 = 1, g.c01 = 0, g.c10 = 3, g.c11 = 1;
     }
     const long long grid = g.n_blocks < p->grid ? g.n_blocks : p->grid;
-    B200_LAUNCH(fir_ols2_kernel, (unsigned)grid, 256, OLSD_SMEM, s, (const float2*)d_in, (const float2*)d_hist,
+    B200_LAUNCH_PDL(fir_ols2_kernel, (unsigned)grid, 256, OLSD_SMEM, s, (const float2*)d_in, (const float2*)d_hist,
                 (float2*)d_out, p->d_H2, p->d_tw1, p->d_tw2, g);
     return B200_OK;
 }
@@ -893,11 +905,11 @@ int ols_launch(ols_plan* p, const float* d_hist, const void* d_in, void* d_out, 
         g.shift = part * OLS_PART;
         g.accumulate = part > 0;
         if (p->real)
-            B200_LAUNCH(fir_ols4096_kernel<true>, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
+            B200_LAUNCH_PDL(fir_ols4096_kernel<true>, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
                         (const float2*)d_hist, (float2*)d_out, p->d_H + (size_t)part * OLS_N, p->d_tw1,
                         p->d_tw2, g);
         else
-            B200_LAUNCH(fir_ols4096_kernel<false>, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
+            B200_LAUNCH_PDL(fir_ols4096_kernel<false>, (unsigned)grid, 256, OLS_SMEM, s, (const float2*)d_in,
                         (const float2*)d_hist, (float2*)d_out, p->d_H + (size_t)part * OLS_N, p->d_tw1,
                         p->d_tw2, g);
     }

@@ -837,8 +837,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
     if (a.ts_pdl) {
         // programmatic dependent launch: everything above (barriers, TMEM, the tap upload) overlapped the tail of
         // the previous kernel in the stream; nothing below may start before that kernel has completed and flushed
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        pdl_wait();
+        pdl_launch_dependents();
     }
 
     if (warp == 0) {
@@ -1302,22 +1302,7 @@ int tc_launch(tc_plan* p, const float* d_hist, const void* d_in, void* d_out, lo
             B200_LAUNCH(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
             return B200_OK;
         }
-        // programmatic dependent launch: this kernel's CTAs may become resident (and run their prologue) while the
-        // previous kernel in the stream drains; the kernel orders itself with griddepcontrol.wait
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(ts_tiles < sms ? ts_tiles : sms));
-        cfg.blockDim = dim3(TS_THREADS);
-        cfg.dynamicSmemBytes = p->ts_smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, fir_tc_ts_kernel, a);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        if (le != cudaSuccess)
-            return set_err(B200_ERR_CUDA, "fir(tensor core): launch fir_tc_ts_kernel -> %s", cudaGetErrorString(le));
+        B200_LAUNCH_PDL(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
         return B200_OK;
     }
     if (p->pipe) {

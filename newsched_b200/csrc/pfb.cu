@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(256, 2)
         return tma_ok && g0 >= 0 && g0 + (long long)rows * 64 <= n_in;
     };
     __syncthreads();
+    // programmatic dependent launch (B200_LAUNCH_PDL): the prologue above ran while the previous kernel in the
+    // stream drained; nothing below may start before that kernel has completed and flushed
+    pdl_wait();
+    pdl_launch_dependents();
     long long tile = blockIdx.x;
     if (tile < n_tiles && tma_tile(tile) && tid == 0) {
         mbar_arrive_expect_tx(bar, tile_bytes);
@@ -405,6 +409,10 @@ __global__ void __launch_bounds__(PFBT_THREADS, 2)
         }
     };
 
+    // programmatic dependent launch (B200_LAUNCH_PDL): the prologue above ran while the previous kernel in the
+    // stream drained; nothing below may start before that kernel has completed and flushed
+    pdl_wait();
+    pdl_launch_dependents();
     long long tile = blockIdx.x;
     const uint32_t planes_s = smem_u32(planes);
     if (warp == 8) {
@@ -1029,7 +1037,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
         long long g = tiles < h->grid ? tiles : h->grid;
 #define PFBT_GO(PT)                                                                               \
-    B200_LAUNCH(pfb64_tc_kernel<PT>, (unsigned)g, PFBT_THREADS, h->smem_tc, s, (const float2*)d_in,           \
+    B200_LAUNCH_PDL(pfb64_tc_kernel<PT>, (unsigned)g, PFBT_THREADS, h->smem_tc, s, (const float2*)d_in,           \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->d_dft, h->P4, h->P, n_frames, \
                 n_in, h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
         switch (h->P4) {
@@ -1043,7 +1051,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         long long tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
         long long g = tiles < h->grid ? tiles : h->grid;
 #define PFB64_GO(PT)                                                                              \
-    B200_LAUNCH(pfb64_kernel<PT>, (unsigned)g, 256, h->smem, s, (const float2*)d_in,                  \
+    B200_LAUNCH_PDL(pfb64_kernel<PT>, (unsigned)g, 256, h->smem, s, (const float2*)d_in,                  \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
                 h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
         switch (h->P4) {
