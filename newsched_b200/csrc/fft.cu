@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(256, 2)
         wt = make_float2(cs_ * odd_sign, (FWD ? -sn : sn) * odd_sign);
     }
     __syncthreads();
+    pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();
     long long vec = blockIdx.x;
     if (tid == 0 && vec < n_vec) {
         mbar_arrive_expect_tx(bar, 4096 * 8);
@@ -607,6 +609,8 @@ __global__ void __launch_bounds__(256, 2)
     __syncthreads();
     const long long n_blocks = (n_vec + G::V - 1) / G::V;
     auto tma_block = [&](long long b) { return tma_ok && (b + 1) * G::V <= n_vec; };
+    pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();
     long long blk = blockIdx.x;
     if (tid == 0 && blk < n_blocks && tma_block(blk)) {
         mbar_arrive_expect_tx(bar, 4096 * 8);
@@ -734,6 +738,8 @@ __global__ void __launch_bounds__(256, 2)
     __syncthreads();
     const long long n_blocks = (n_vec + G::V - 1) / G::V;
     auto tma_block = [&](long long b) { return tma_ok && (b + 1) * G::V <= n_vec; };
+    pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();
     long long blk = blockIdx.x;
     if (tid == 0 && blk < n_blocks && tma_block(blk)) {
         mbar_arrive_expect_tx(bar, 4096 * 8);
@@ -962,7 +968,7 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
         long long g = nb < h->grid_4k ? nb : h->grid_4k;
         const int tma_ok = (uintptr_t)d_in % 16 == 0;
 #define FFT_SM_GO(R)                                                                                     \
-    B200_LAUNCH((fft_small_kernel<R, FWD, OUT>), (unsigned)g, 256, fsm<R>::SMEM, s, (const float2*)d_in, \
+    B200_LAUNCH_PDL((fft_small_kernel<R, FWD, OUT>), (unsigned)g, 256, fsm<R>::SMEM, s, (const float2*)d_in, \
                 d_out, n_vec, h->d_weff, h->d_tw1, h->flip, tma_ok)
         switch (R0) {
         case 1: FFT_SM_GO(1); break;
@@ -977,7 +983,7 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
         long long g = nb < h->grid_4k ? nb : h->grid_4k;
         const int tma_ok = (uintptr_t)d_in % 16 == 0;
 #define FFT_R0_GO(R)                                                                                  \
-    B200_LAUNCH((fft_r0_kernel<R, FWD, OUT>), (unsigned)g, 256, fr0<R>::SMEM, s, (const float2*)d_in, \
+    B200_LAUNCH_PDL((fft_r0_kernel<R, FWD, OUT>), (unsigned)g, 256, fr0<R>::SMEM, s, (const float2*)d_in, \
                 d_out, n_vec, h->d_weff, h->d_tw1, h->d_tw2, tma_ok)
         switch (R0) {
         case 1: FFT_R0_GO(1); break;
@@ -993,7 +999,7 @@ static int fft_run_t(b200_fft* h, const void* d_in, void* d_out, long long n_vec
                     d_out, n_vec, h->d_weff, h->post, h->flip);
     } else if (h->N == 8192 && h->d_tw1 && (uintptr_t)d_in % 16 == 0 && (uintptr_t)d_out % 16 == 0) {
         long long g = n_vec < h->grid_4k ? n_vec : h->grid_4k;
-        B200_LAUNCH((fft8192_kernel<FWD, OUT>), (unsigned)g, 256, F8K_SMEM, s, (const float2*)d_in, d_out, n_vec,
+        B200_LAUNCH_PDL((fft8192_kernel<FWD, OUT>), (unsigned)g, 256, F8K_SMEM, s, (const float2*)d_in, d_out, n_vec,
                     h->d_weff, h->d_tw1, h->d_tw2, h->flip ? -1.f : 1.f);
     } else {
         long long blocks = (n_vec + h->vpb - 1) / h->vpb;

@@ -30,7 +30,12 @@
 namespace b200 {
 
 constexpr int OLS_N = 4096;
-constexpr size_t OLS_SMEM = OLS_N * 8 + 16 * F4K_STRIDE * 8 + 256 * 8 + 16;
+// + the spectrum table H (32 KiB), resident in shared memory for the lifetime of the CTA (B200_OLS_HSMEM): the
+// multiply step reads it with 16 conflict-free LDS.64 per thread instead of 16 L2-latency loads per block
+#ifndef B200_OLS_HSMEM
+#define B200_OLS_HSMEM 1
+#endif
+constexpr size_t OLS_SMEM = OLS_N * 8 + 16 * F4K_STRIDE * 8 + 256 * 8 + 16 + (B200_OLS_HSMEM ? OLS_N * 8 : 0);
 
 struct ols_geom {
     int Ov;  // samples of overlap discarded at the head of every block (>= T-1, even)
@@ -113,6 +118,9 @@ __global__ void __launch_bounds__(256, 2)
     float2* sA = sIn + OLS_N;
     float2* sT2 = sA + 16 * F4K_STRIDE;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sT2 + 256);
+#if B200_OLS_HSMEM
+    float2* sH = reinterpret_cast<float2*>(bar + 2);
+#endif
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -123,6 +131,11 @@ __global__ void __launch_bounds__(256, 2)
     for (int i = 0; i < 16; i++)
         t1[i] = __ldg(tw1 + i * 256 + tid);
     sT2[tid] = __ldg(tw2 + tid);
+#if B200_OLS_HSMEM
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        sH[i * 256 + tid] = __ldg(Htab + i * 256 + tid); // each thread reads back exactly what it wrote
+#endif
     __syncthreads();
     float2 t2r[16]; // this thread's pass-2 twiddles, register resident (see top of file)
 #pragma unroll
@@ -220,7 +233,11 @@ __global__ void __launch_bounds__(256, 2)
             // ---- spectrum multiply: thread holds X[tid + 256 k2] in v[pos16(k2)]
 #pragma unroll
             for (int k2 = 0; k2 < 16; k2++)
+#if B200_OLS_HSMEM
+                u[k2] = cmul(v[pos16(k2)], sH[k2 * 256 + tid]);
+#else
                 u[k2] = cmul(v[pos16(k2)], __ldg(Htab + k2 * 256 + tid));
+#endif
         }
         __syncthreads(); // pass-3 reads of sA done before the inverse transform overwrites it
         // ---- inverse transform straight from registers (u[k2] plays x[n2*256 + tid])

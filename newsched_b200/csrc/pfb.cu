@@ -603,6 +603,8 @@ __global__ void __launch_bounds__(256, (M >= 128 ? 1 : 2))
         return tma_ok && g0 >= 0 && g0 + (long long)rows * M <= n_in;
     };
     __syncthreads();
+    pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();
     long long tile = blockIdx.x;
     if (tile < n_tiles && tma_tile(tile) && tid == 0) {
         mbar_arrive_expect_tx(bar, tile_bytes);
@@ -780,6 +782,8 @@ __global__ void __launch_bounds__(256, 2)
         return tma_ok && g0 >= 0 && g0 + (long long)rows * M <= n_in;
     };
     __syncthreads();
+    pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();
     long long tile = blockIdx.x;
     if (tile < n_tiles && tma_tile(tile) && tid == 0) {
         mbar_arrive_expect_tx(bar, tile_bytes);
@@ -1069,7 +1073,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         long long tiles = (n_frames + TT - 1) / TT;
         long long g = tiles < h->grid ? tiles : h->grid;
 #define PFBS_GO(MM, PT)                                                                               \
-    B200_LAUNCH((pfbs_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
+    B200_LAUNCH_PDL((pfbs_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
                 h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), (int)((uintptr_t)d_out % 16 == 0))
         if (h->M == 8) {
@@ -1093,7 +1097,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
         long long tiles = (n_frames + TT - 1) / TT;
         long long g = tiles < h->grid ? tiles : h->grid;
 #define PFBM_GO(MM, PT)                                                                               \
-    B200_LAUNCH((pfbm_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
+    B200_LAUNCH_PDL((pfbm_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
                 h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
 #define PFBM_P(MM)                         \

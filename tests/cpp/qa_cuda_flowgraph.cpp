@@ -519,6 +519,41 @@ QA_TEST(Config4, PfbChannelizer64)
     EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
 }
 
+// config 4 as BASELINE.json words it ("filterbank + DFT as tensor-core GEMM"): the same flowgraph with the DFT across
+// branches on tcgen05 (algorithm 2); small rings, so the stream crosses many work() calls and 64-frame tiles
+QA_TEST(Config4, PfbChannelizer64TensorCoreDft)
+{
+    const int M = 64, P = 16;
+    auto in = noise((size_t)M * 5000, 11);
+    std::vector<float> taps(M * P);
+    for (int i = 0; i < M * P; i++) {
+        double t = (i - (M * P - 1) / 2.0) / M;
+        double s = std::fabs(t) < 1e-12 ? 1.0 : std::sin(M_PI * t) / (M_PI * t);
+        taps[i] = (float)(s * (0.54 - 0.46 * std::cos(2 * M_PI * i / (M * P - 1))) / M);
+    }
+    std::vector<gr_complex> exp(in.size());
+    orc_pfb_channelizer_f64((float*)exp.data(), (const float*)in.data(), (int64_t)in.size(), taps.data(), M, P, nullptr);
+    auto src = blocks::vector_source_c::make(in);
+    auto ch = cuda::pfb_channelizer_ccf::make(M, taps, 0, 0, 2);
+    auto snk = blocks::vector_sink_c::make(M);
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, ch, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 1u << 20));
+    fg->connect(ch, 0, snk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 1u << 20));
+    fg->set_scheduler(schedulers::scheduler_mt::make());
+    fg->validate();
+    fg->run();
+    EXPECT_EQ(snk->data().size(), exp.size());
+    EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+    // the tensor-core form needs 64 channels: anything else must fail loudly, not fall back
+    bool threw = false;
+    try {
+        cuda::pfb_channelizer_ccf::make(32, std::vector<float>(32 * 8, 0.1f), 0, 0, 2);
+    } catch (const std::exception&) {
+        threw = true;
+    }
+    EXPECT_TRUE(threw);
+}
+
 // two-input sync blocks: both inputs are clamped to the common minimum by sync_block::do_work
 QA_TEST(TwoInput, MultiplyAndAdd)
 {

@@ -41,6 +41,7 @@ def test_flowgraphs_on_gpu():
     for name in ("SchedulerMTTest.CudaCopyBasic", "SchedulerMTTest.CudaCopyMultiThreaded",
                  "SchedulerMTTest.CudaCopyPinnedBuffers",
                  "Config1.FirCcf64", "Config2.FftMag", "Config3.FirMulFftChain", "Config4.PfbChannelizer64",
+                 "Config4.PfbChannelizer64TensorCoreDft",
                  "Fusion.AdjacentBlocksCollapse", "TwoInput.MultiplyAndAdd",
                  "SchedulerMTTags.TagsAcrossDeviceBuffers"):
         assert f"[  OK  ] {name}" in out
