@@ -571,18 +571,22 @@ template <int M, int P4T>
 __global__ void __launch_bounds__(256, (M >= 128 ? 1 : 2))
     pfbm_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
                 const float* __restrict__ taps_rm /* [P4][M] */, int P4, int Ptrue, long long n_frames,
-                long long n_in, int ch_begin, int ch_count, int tma_ok)
+                long long n_in, int ch_begin, int ch_count, int tma_ok, int nbuf)
 {
+    // nbuf = 2 (when shared memory allows, see b200_pfb_create): two input tiles, the copy of tile i+1 is issued a
+    // whole tile ahead.  With one buffer it only had the DFT stage to hide behind: M = 128 (one CTA per SM) spent
+    // 17 % of its warp samples on the input mbarrier (ncu, round 2).
     constexpr int S = pfbm<M>::S, TT = pfbm<M>::TT, RS = pfbm<M>::RS;
     extern __shared__ __align__(128) float2 sm[];
     const int rows = TT + P4 - 1;
-    float2* X = sm;
-    float2* U = X + rows * M;
+    float2* X0 = sm;
+    float2* U = X0 + nbuf * rows * M;
     float* hT = reinterpret_cast<float*>(U + TT * RS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(hT + P4 * M);
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     for (int i = tid; i < P4 * M; i += 256)
@@ -606,16 +610,22 @@ __global__ void __launch_bounds__(256, (M >= 128 ? 1 : 2))
     pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
     pdl_launch_dependents();
     long long tile = blockIdx.x;
-    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
-        mbar_arrive_expect_tx(bar, tile_bytes);
-        bulk_copy_g2s(X, x + (tile * TT - (P4 - 1)) * M, tile_bytes, bar);
-    }
-    uint32_t phase = 0;
-    for (; tile < n_tiles; tile += gridDim.x) {
+    if (tid == 0)
+        for (int b = 0; b < nbuf; b++) {
+            const long long t = tile + (long long)b * gridDim.x;
+            if (t < n_tiles && tma_tile(t)) {
+                mbar_arrive_expect_tx(bar + b, tile_bytes);
+                bulk_copy_g2s(X0 + b * rows * M, x + (t * TT - (P4 - 1)) * M, tile_bytes, bar + b);
+            }
+        }
+    uint32_t phase = 0; // bit b: parity of the next completion of bar[b]
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, it++) {
         const long long f0 = tile * TT;
+        const int xb = nbuf == 2 ? (it & 1) : 0;
+        float2* X = X0 + xb * rows * M;
         if (tma_tile(tile)) {
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            mbar_wait(bar + xb, (phase >> xb) & 1u);
+            phase ^= 1u << xb;
         } else {
             const long long g0 = (f0 - (P4 - 1)) * M;
             for (int i0 = tid; i0 < rows * M; i0 += 256 * 8) {
@@ -678,10 +688,10 @@ __global__ void __launch_bounds__(256, (M >= 128 ? 1 : 2))
         }
         __syncthreads(); // U complete; X fully consumed
         {
-            const long long nxt = tile + gridDim.x;
+            const long long nxt = tile + (long long)nbuf * gridDim.x; // refill the buffer just consumed
             if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
-                mbar_arrive_expect_tx(bar, tile_bytes);
-                bulk_copy_g2s(X, x + (nxt * TT - (P4 - 1)) * M, tile_bytes, bar);
+                mbar_arrive_expect_tx(bar + xb, tile_bytes);
+                bulk_copy_g2s(X, x + (nxt * TT - (P4 - 1)) * M, tile_bytes, bar + xb);
             }
         }
         // ---- stage 1: radix 16 over i1 (rows are warp-local: a warp owns 32/S whole frames)
@@ -758,18 +768,26 @@ template <int M, int P4T>
 __global__ void __launch_bounds__(256, 2)
     pfbs_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
                 const float* __restrict__ taps_rm /* [P4][M] */, int P4, int Ptrue, long long n_frames,
-                long long n_in, int ch_begin, int ch_count, int tma_ok, int out16)
+                long long n_in, int ch_begin, int ch_count, int tma_ok, int out16, int nbuf)
 {
-    constexpr int TT = 4096 / M, US = TT + 1;
+    // Shared-memory layout (round 2, from the ncu capture of M = 8: 30 M bank conflicts, mio_throttle 4.2 warps per
+    // issue): a warp holds M branches x 32/M frame groups, and the groups' rows are 16 rows = a multiple of 128 bytes
+    // apart, so the filter loads of the groups hit the same banks (4-way for M = 8, 8-way for M = 4).  One spare
+    // row after every 16 rows of the input tile (the tile arrives as one bulk copy per 16-row block) and one spare
+    // slot after every 16 frames of a branch's outputs (row stride = 2 mod 16) make filter loads, output stores
+    // and the DFT's loads conflict-free.
+    constexpr int TT = 4096 / M, US = TT + TT / 16 + 2;
     extern __shared__ __align__(128) float2 sm[];
     const int rows = TT + P4 - 1;
-    float2* X = sm;
-    float2* U = X + rows * M;
+    const int prows = rows + (rows >> 4) + 1; // padded rows of one input tile
+    float2* X0 = sm;
+    float2* U = X0 + nbuf * prows * M;
     float* hT = reinterpret_cast<float*>(U + M * US);
     uint64_t* bar = reinterpret_cast<uint64_t*>(hT + P4 * M + ((P4 * M) & 1));
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     for (int i = tid; i < P4 * M; i += 256)
@@ -784,17 +802,30 @@ __global__ void __launch_bounds__(256, 2)
     __syncthreads();
     pdl_wait();              // programmatic dependent launch: everything above overlapped the previous kernel's tail
     pdl_launch_dependents();
+    auto issue = [&](long long t, int b) { // one elected thread: one bulk copy per 16-row block, padded destination
+        mbar_arrive_expect_tx(bar + b, tile_bytes);
+        const float2* src = x + (t * TT - (P4 - 1)) * M;
+        float2* dst = X0 + b * prows * M;
+        for (int r = 0; r < rows; r += 16) {
+            const int nr = rows - r < 16 ? rows - r : 16;
+            bulk_copy_g2s(dst + (r + (r >> 4)) * M, src + r * M, (uint32_t)(nr * M * 8), bar + b);
+        }
+    };
     long long tile = blockIdx.x;
-    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
-        mbar_arrive_expect_tx(bar, tile_bytes);
-        bulk_copy_g2s(X, x + (tile * TT - (P4 - 1)) * M, tile_bytes, bar);
-    }
-    uint32_t phase = 0;
-    for (; tile < n_tiles; tile += gridDim.x) {
+    if (tid == 0)
+        for (int b = 0; b < nbuf; b++) {
+            const long long t = tile + (long long)b * gridDim.x;
+            if (t < n_tiles && tma_tile(t))
+                issue(t, b);
+        }
+    uint32_t phase = 0; // bit b: parity of the next completion of bar[b]
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, it++) {
         const long long f0 = tile * TT;
+        const int xb = nbuf == 2 ? (it & 1) : 0;
+        float2* X = X0 + xb * prows * M;
         if (tma_tile(tile)) {
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            mbar_wait(bar + xb, (phase >> xb) & 1u);
+            phase ^= 1u << xb;
         } else {
             const long long g0 = (f0 - (P4 - 1)) * M;
             for (int i0 = tid; i0 < rows * M; i0 += 256 * 8) {
@@ -805,14 +836,16 @@ __global__ void __launch_bounds__(256, 2)
                         v[u] = pfb_fetch(x, halo, nh, g0 + i0 + u * 256, n_in);
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (i0 + u * 256 < rows * M)
-                        X[i0 + u * 256] = v[u];
+                    if (i0 + u * 256 < rows * M) {
+                        const int e = i0 + u * 256, r = e / M;
+                        X[e + (r >> 4) * M] = v[u];
+                    }
             }
             __syncthreads();
         }
         {
             const int i = tid % M, tg = tid / M; // 256 / M groups of 16 frames = TT frames
-            const float2* col = X + (M - 1 - i) + (tg * 16) * M;
+            const float2* col = X + (M - 1 - i) + (tg * 17) * M; // group tg starts at row 16 tg = padded row 17 tg
             float2 acc[16];
 #pragma unroll
             for (int j = 0; j < 16; j++)
@@ -824,7 +857,7 @@ __global__ void __launch_bounds__(256, 2)
                     hreg[r] = hT[r * M + i];
 #pragma unroll
                 for (int rho = 0; rho < 16 + P4T - 1; rho++) {
-                    const float2 v = col[rho * M];
+                    const float2 v = col[(rho + (rho >> 4)) * M];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int r = j + P4T - 1 - rho;
@@ -836,11 +869,11 @@ __global__ void __launch_bounds__(256, 2)
                 for (int rc = 0; rc < P4; rc += 4) {
                     const float h0 = hT[(rc + 0) * M + i], h1 = hT[(rc + 1) * M + i];
                     const float h2 = hT[(rc + 2) * M + i], h3 = hT[(rc + 3) * M + i];
-                    const float2* base = col + (P4 - 1 - rc - 3) * M;
+                    const int a0 = P4 - 1 - rc - 3;
                     float2 w[19];
 #pragma unroll
                     for (int q = 0; q < 19; q++)
-                        w[q] = base[q * M];
+                        w[q] = col[(a0 + q + ((a0 + q) >> 4)) * M];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         acc[j] = __ffma2_rn(w[j + 3], make_float2(h0, h0), acc[j]);
@@ -852,22 +885,20 @@ __global__ void __launch_bounds__(256, 2)
             }
 #pragma unroll
             for (int j = 0; j < 16; j++)
-                U[i * US + tg * 16 + j] = acc[j];
+                U[i * US + tg * 17 + j] = acc[j];
         }
         __syncthreads(); // U complete; X fully consumed
         {
-            const long long nxt = tile + gridDim.x;
-            if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
-                mbar_arrive_expect_tx(bar, tile_bytes);
-                bulk_copy_g2s(X, x + (nxt * TT - (P4 - 1)) * M, tile_bytes, bar);
-            }
+            const long long nxt = tile + (long long)nbuf * gridDim.x; // refill the buffer just consumed
+            if (tid == 0 && nxt < n_tiles && tma_tile(nxt))
+                issue(nxt, xb);
         }
 #pragma unroll 1
         for (int fr = tid; fr < TT; fr += 256) {
             float2 z[M];
 #pragma unroll
             for (int i = 0; i < M; i++)
-                z[i] = U[i * US + fr];
+                z[i] = U[i * US + fr + (fr >> 4)];
             if constexpr (M == 8)
                 idft8(z);
             else
@@ -996,6 +1027,18 @@ using namespace b200;
 #define PFB64_TC_DEFAULT 0
 #endif
 
+// shared memory of pfbs_kernel: one (padded) input tile, and everything else
+static inline size_t pfbs_xbytes(int M, int P4)
+{
+    const int rows = 4096 / M + P4 - 1;
+    return sizeof(float2) * (size_t)(rows + (rows >> 4) + 1) * M;
+}
+static inline size_t pfbs_rest(int M, int P4)
+{
+    const int TT = 4096 / M;
+    return sizeof(float2) * (size_t)M * (TT + TT / 16 + 2) + sizeof(float) * ((size_t)P4 * M + 1) + 32;
+}
+
 static inline uint16_t pfb_bf16_rn(float f)
 {
     uint32_t u;
@@ -1024,6 +1067,7 @@ struct b200_pfb {
     int tc_ok = 0;         // the tensor-core form exists for this (M, P)
     uint4* d_dft = nullptr; // [128 rows = (channel, re/im)][hi 128 | lo 128] bf16 DFT matrix
     size_t smem_tc = 0;
+    int nbuf = 1;          // input tiles in shared memory (pfbm_kernel)
     int fusedM = 0; // 1: M = 16 / 32 / 128 / 256 on pfbm_kernel; 2: M = 4 / 8 on pfbs_kernel (single pass both)
     // generic M >= 16: branch filters -> scratch -> the library's own reverse FFT of length M
     b200_fft* ifft = nullptr;
@@ -1075,7 +1119,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
 #define PFBS_GO(MM, PT)                                                                               \
     B200_LAUNCH_PDL((pfbs_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
-                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), (int)((uintptr_t)d_out % 16 == 0))
+                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), (int)((uintptr_t)d_out % 16 == 0), h->nbuf)
         if (h->M == 8) {
             switch (h->P4) {
             case 4: PFBS_GO(8, 4); break;
@@ -1099,7 +1143,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
 #define PFBM_GO(MM, PT)                                                                               \
     B200_LAUNCH_PDL((pfbm_kernel<MM, PT>), (unsigned)g, 256, h->smem, s, (const float2*)d_in,             \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
-                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
+                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), h->nbuf)
 #define PFBM_P(MM)                         \
     switch (h->P4) {                       \
     case 4: PFBM_GO(MM, 4); break;         \
@@ -1242,11 +1286,10 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
                 h->tc = atoi(e) != 0;
         }
     } else if ((M == 4 || M == 8) && !getenv("B200_PFB_TWOPASS") &&
-               sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)M * (4096 / M + 1)) +
-                       sizeof(float) * ((size_t)h->P4 * M + 1) + 16 <= 110 * 1024) {
+               pfbs_xbytes(M, h->P4) + pfbs_rest(M, h->P4) <= 110 * 1024) {
         h->fusedM = 2;
-        h->smem = sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)M * (4096 / M + 1)) +
-                  sizeof(float) * ((size_t)h->P4 * M + 1) + 16;
+        h->nbuf = (2 * pfbs_xbytes(M, h->P4) + pfbs_rest(M, h->P4) <= 113 * 1024 && !getenv("B200_PFB_ONEBUF")) ? 2 : 1;
+        h->smem = h->nbuf * pfbs_xbytes(M, h->P4) + pfbs_rest(M, h->P4);
 #define PFBS_ATTR(MM)                                                                                          \
     PFB_CUDA(cudaFuncSetAttribute(pfbs_kernel<MM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
     PFB_CUDA(cudaFuncSetAttribute(pfbs_kernel<MM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
@@ -1263,8 +1306,13 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
                sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)(4096 / M) * 17 * (M / 16)) +
                        sizeof(float) * (size_t)h->P4 * M + 16 <= 220 * 1024) {
         h->fusedM = 1;
-        h->smem = sizeof(float2) * ((size_t)(4096 / M + h->P4 - 1) * M + (size_t)(4096 / M) * 17 * (M / 16)) +
-                  sizeof(float) * (size_t)h->P4 * M + 16;
+        const size_t xbytes = sizeof(float2) * (size_t)(4096 / M + h->P4 - 1) * M;
+        const size_t rest = sizeof(float2) * (size_t)(4096 / M) * 17 * (M / 16) + sizeof(float) * (size_t)h->P4 * M + 16;
+        // a second input tile for M >= 128 (one CTA per SM: 321 -> 391 GS/s at M = 128 / P = 8, 335 -> 411 at M = 256 /
+        // P = 4).  M = 16 / 32 run two CTAs per SM and LOSE with it (M = 16 / P = 8: 399 -> 345 GS/s; the deeper read
+        // prefetch works against the write stream of these HBM-bound kernels), so they keep one.
+        h->nbuf = (M >= 128 && 2 * xbytes + rest <= 227 * 1024 && !getenv("B200_PFB_ONEBUF")) ? 2 : 1;
+        h->smem = h->nbuf * xbytes + rest;
 #define PFBM_ATTR(MM)                                                                                          \
     PFB_CUDA(cudaFuncSetAttribute(pfbm_kernel<MM, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \
     PFB_CUDA(cudaFuncSetAttribute(pfbm_kernel<MM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)); \

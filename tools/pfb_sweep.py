@@ -5,7 +5,7 @@ import newsched_b200 as nb
 n = 1 << 26
 g = torch.Generator(device="cuda").manual_seed(1)
 x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
-for M, P in ((64, 16), (64, 8), (64, 32), (64, 10), (16, 8), (32, 16), (128, 8), (256, 4), (8, 16), (4, 8)):
+for M, P in ((64, 16), (64, 8), (64, 32), (64, 10), (16, 8), (16, 16), (32, 16), (32, 8), (128, 8), (128, 16), (256, 4), (256, 8), (8, 16), (8, 8), (4, 8), (4, 16)):
     pt = sig.firwin(M * P, 1.0 / M).astype(np.float32)
     ch = nb.PfbChannelizer(pt, M)
     out = torch.empty((n // M, M), dtype=torch.complex64, device="cuda")

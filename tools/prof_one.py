@@ -40,6 +40,11 @@ elif what == "firdec64d5":
     op = nb.FirFilter((rng.uniform(-1, 1, 64) / 64).astype(np.float32), 5); out = torch.empty(n // 5, dtype=torch.complex64, device="cuda"); fn = lambda: op.work_segment(x, None, out)
 elif what == "rs32":
     op = nb.RationalResampler((rng.uniform(-1, 1, 192) / 64).astype(np.float32), 3, 2); out = torch.empty(n // 2 * 3, dtype=torch.complex64, device="cuda"); fn = lambda: op.work_segment(x, None, out)
+elif what.startswith("pfbm"):        # pfbm<M>x<P>, e.g. pfbm128x8, pfbm8x16
+    import scipy.signal as sig
+    Mm, Pp = (int(v) for v in what[4:].split("x"))
+    n = N * 32768; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+    op = nb.PfbChannelizer(sig.firwin(Mm * Pp, 1 / Mm).astype(np.float32), Mm); out = torch.empty_like(x).view(-1, Mm); fn = lambda: op.work_segment(x, None, out)
 elif what == "pfb16":
     import scipy.signal as sig
     n = N * 32768; x = torch.view_as_complex(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
