@@ -105,39 +105,44 @@ template <int P4T> // > 0: taps per branch known at compile time (fully unrolled
 __global__ void __launch_bounds__(256, 2)
     pfb64_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
                  const float* __restrict__ taps_rm /* [P4][64] */, int P4, int Ptrue,
-                 long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok)
+                 long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok, int nbuf)
 {
+    // nbuf = 2 (P4T > 0 and P <= 16, see b200_pfb_create): TWO input tiles, the copy of tile i+1 is issued a whole tile
+    // ahead of its use.  With one buffer the copy only had the DFT stage to hide behind and 10.5 % of all warp samples
+    // sat on the input mbarrier (ncu r02_pfb64_v4).  Two tiles + U are exactly the 115 712 bytes a CTA may use with two
+    // CTAs per SM, so the taps live in registers for the lifetime of the CTA (no shared copy) and the two mbarriers sit
+    // in the padding of U's first row (elements 64..67 of a row are never touched).
     extern __shared__ __align__(128) float2 sm[];
     const int rows = PFB64_TT + P4 - 1;
-    float2* X = sm;
-    float2* U = X + rows * 64;
-    float* hT = reinterpret_cast<float*>(U + PFB64_TT * PFB64_RS);
-    float2* tw = reinterpret_cast<float2*>(hT + P4 * 64);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 64);
+    float2* X0 = sm;
+    float2* U = X0 + nbuf * rows * 64;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(U + 64);
+    float* hT = reinterpret_cast<float*>(U + PFB64_TT * PFB64_RS); // only when P4T == 0 (taps not in registers)
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < P4 * 64; i += 256)
-        hT[i] = __ldg(taps_rm + i);
-    if (tid < 64) {
-        float s, c;
-        sincospif((float)tid / 32.0f, &s, &c); // e^{+j 2 pi tid/64}
-        tw[tid] = make_float2(c, s);
+    if (P4T == 0)
+        for (int i = tid; i < P4 * 64; i += 256)
+            hT[i] = __ldg(taps_rm + i);
+    float hreg[P4T > 0 ? P4T : 1];
+    if (P4T > 0) {
+#pragma unroll
+        for (int r = 0; r < P4T; r++)
+            hreg[r] = __ldg(taps_rm + r * 64 + (tid & 63));
     }
     const long long nh = (long long)(Ptrue - 1) * 64;
     const long long n_tiles = (n_frames + PFB64_TT - 1) / PFB64_TT;
-#if B200_PFB_TWREG
     // stage-1 twiddles W64^{i0 c1} depend on the thread only (i0 = tid & 3): register resident
     float2 twr[16];
-    {
-        __syncthreads();
 #pragma unroll
-        for (int c1 = 1; c1 < 16; c1++)
-            twr[c1] = tw[((tid & 3) * c1) & 63];
+    for (int c1 = 1; c1 < 16; c1++) {
+        float sn, cs_;
+        sincospif((float)(((tid & 3) * c1) & 63) / 32.0f, &sn, &cs_); // e^{+j 2 pi i0 c1 / 64}
+        twr[c1] = make_float2(cs_, sn);
     }
-#endif
     const uint32_t tile_bytes = (uint32_t)rows * 64u * 8u;
     // can tile `t` be staged by TMA?  (whole span inside [0, n_in), 16-byte aligned source)
     auto tma_tile = [&](long long t) {
@@ -150,18 +155,25 @@ __global__ void __launch_bounds__(256, 2)
     pdl_wait();
     pdl_launch_dependents();
     long long tile = blockIdx.x;
-    if (tile < n_tiles && tma_tile(tile) && tid == 0) {
-        mbar_arrive_expect_tx(bar, tile_bytes);
-        bulk_copy_g2s(X, x + (tile * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
-    }
-    uint32_t phase = 0;
+    if (tid == 0)
+        for (int b = 0; b < nbuf; b++) {
+            const long long t = tile + (long long)b * gridDim.x;
+            if (t < n_tiles && tma_tile(t)) {
+                mbar_arrive_expect_tx(bar + b, tile_bytes);
+                bulk_copy_g2s(X0 + b * rows * 64, x + (t * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar + b);
+            }
+        }
+    uint32_t phase = 0; // bit b: parity of the next completion of bar[b]
+    int it = 0;
 
-    for (; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < n_tiles; tile += gridDim.x, it++) {
         const long long f0 = tile * PFB64_TT; // first frame of the tile
+        const int xb = nbuf == 2 ? (it & 1) : 0;
+        float2* X = X0 + xb * rows * 64;
         // rows: row j holds frame (f0 - (P4-1) + j), col = position within the frame
         if (tma_tile(tile)) {
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            mbar_wait(bar + xb, (phase >> xb) & 1u);
+            phase ^= 1u << xb;
         } else {
             const long long g0 = (f0 - (P4 - 1)) * 64;
             for (int i0 = tid; i0 < rows * 64; i0 += 256 * 8) {
@@ -189,10 +201,6 @@ __global__ void __launch_bounds__(256, 2)
             if (P4T > 0) {
                 // taps in registers, every input row read exactly once: row rho feeds the
                 // (frame j, tap r) pairs with j + P4-1 - r == rho
-                float hreg[P4T > 0 ? P4T : 1];
-#pragma unroll
-                for (int r = 0; r < P4T; r++)
-                    hreg[r] = hT[r * 64 + i];
 #pragma unroll
                 for (int rho = 0; rho < 16 + P4T - 1; rho++) {
                     const float2 v = col[rho * 64];
@@ -228,10 +236,10 @@ __global__ void __launch_bounds__(256, 2)
         }
         __syncthreads(); // U complete; X fully consumed
         {
-            const long long nxt = tile + gridDim.x;
+            const long long nxt = tile + (long long)nbuf * gridDim.x; // refill the buffer just consumed
             if (tid == 0 && nxt < n_tiles && tma_tile(nxt)) {
-                mbar_arrive_expect_tx(bar, tile_bytes);
-                bulk_copy_g2s(X, x + (nxt * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar);
+                mbar_arrive_expect_tx(bar + xb, tile_bytes);
+                bulk_copy_g2s(X, x + (nxt * PFB64_TT - (P4 - 1)) * 64, tile_bytes, bar + xb);
             }
         }
 
@@ -254,11 +262,7 @@ __global__ void __launch_bounds__(256, 2)
             row[i0] = v[0];
 #pragma unroll
             for (int c1 = 1; c1 < 16; c1++) {
-#if B200_PFB_TWREG
                 const float2 w = twr[c1];
-#else
-                const float2 w = tw[(i0 * c1) & 63];
-#endif
                 row[4 * c1 + i0] = cmulc(v[4 * (c1 & 3) + (c1 >> 2)], w.x, w.y);
             }
             __syncwarp();
@@ -1101,7 +1105,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
 #define PFB64_GO(PT)                                                                              \
     B200_LAUNCH_PDL(pfb64_kernel<PT>, (unsigned)g, 256, h->smem, s, (const float2*)d_in,                  \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->P4, h->P, n_frames, n_in,     \
-                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
+                h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), h->nbuf)
         switch (h->P4) {
         case 4: PFB64_GO(4); break;
         case 8: PFB64_GO(8); break;
@@ -1246,8 +1250,14 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
     }
     if (M == 64) {
         int rows = PFB64_TT + h->P4 - 1;
-        h->smem = sizeof(float2) * ((size_t)rows * 64 + (size_t)PFB64_TT * PFB64_RS + 64) +
-                  sizeof(float) * (size_t)h->P4 * 64 + 16;
+        const bool regtaps = h->P4 == 4 || h->P4 == 8 || h->P4 == 12 || h->P4 == 16 || h->P4 == 24 || h->P4 == 32;
+        const size_t xb64 = sizeof(float2) * (size_t)rows * 64, u64 = sizeof(float2) * (size_t)PFB64_TT * PFB64_RS;
+        const size_t taps64 = regtaps ? 0 : sizeof(float) * (size_t)h->P4 * 64;
+        // second input tile when two CTAs per SM still fit: (233472 - 2 * 1024) / 2 = 115712 bytes per CTA
+        // ... and only for 16 taps per channel: the shorter (HBM-bound) filters LOSE with the deeper read prefetch
+        // (P = 8: 413 -> 353 GS/s, P = 12: 400 -> 374), P = 16 gains 1.5 % (372.6 -> 378.3)
+        h->nbuf = (regtaps && h->P4 == 16 && 2 * xb64 + u64 <= 115712 && !getenv("B200_PFB_ONEBUF")) ? 2 : 1;
+        h->smem = h->nbuf * xb64 + u64 + taps64;
         if (h->smem > 220 * 1024) {
             b200_pfb_destroy(h);
             return set_err(B200_ERR_UNSUPPORTED, "pfb_create: taps_per_channel too large for M=64 tile");
