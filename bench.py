@@ -544,7 +544,24 @@ def run_b200(args):
         t = timed(torch, lambda: pfb.work_segment(x, None, yp), reps, 3, lambda: None) / reps
         gbs = SAMPLES * 16 / (t * 1e-3) / 1e9
         extras["pfb_channelizer_64ch_16tpc_1Gi"] = {"Msamples_s": SAMPLES / (t * 1e-3) / 1e6, "ms": t,
-                                                   "hbm_gbs": gbs, "frac_of_hbm": gbs / peak_gbs}
+                                                   "hbm_gbs": gbs, "frac_of_hbm": gbs / peak_gbs,
+                                                   "algorithm": pfb.algorithm, "form": "branch filters + 64-point DFT on the SIMT pipes"}
+        # configs[3] as BASELINE words it ("filterbank + DFT as tensor-core GEMM"): the DFT across branches as a
+        # bf16-split tcgen05 GEMM with the DFT matrix in tensor memory (algorithm 2), timed beside the SIMT form;
+        # the library selects the faster one
+        pfb_tc = nb.PfbChannelizer(pt, 64, algorithm=2)
+        ref_rows = yp[:4096].clone()
+        t2 = timed(torch, lambda: pfb_tc.work_segment(x, None, yp), reps, 3, lambda: None) / reps
+        torch.cuda.synchronize()
+        d = (yp[:4096] - ref_rows).abs().double().pow(2).sum().sqrt() / ref_rows.abs().double().pow(2).sum().sqrt()
+        gbs2 = SAMPLES * 16 / (t2 * 1e-3) / 1e9
+        tc_flop = 3 * 2 * 128 * 128 / 64.0       # executed tensor flop per input sample: 3 split products of a 128 x 128 real DFT per 64-sample frame
+        extras["pfb_channelizer_64ch_16tpc_1Gi_tensor_core_dft"] = {
+            "Msamples_s": SAMPLES / (t2 * 1e-3) / 1e6, "ms": t2, "hbm_gbs": gbs2, "frac_of_hbm": gbs2 / peak_gbs,
+            "algorithm": pfb_tc.algorithm, "form": "branch filters on the SIMT pipes, DFT across branches as a tcgen05 GEMM (A from TMEM)",
+            "executed_tensor_tflops": tc_flop * SAMPLES / (t2 * 1e-3) / 1e12,
+            "executed_frac_of_measured_bf16_peak": (tc_flop * SAMPLES / (t2 * 1e-3) / 1e12 / bf16_tf) if bf16_tf else None,
+            "rel_rms_vs_simt_form": float(d), "selected_by_default": bool(pfb.algorithm == 2)}
         del yc, y1, y3
     except Exception as e:  # pragma: no cover
         extras["error"] = repr(e)
@@ -769,7 +786,15 @@ def run_b200(args):
     if "pfb_channelizer_64ch_16tpc_1Gi" in extras:
         e4 = extras["pfb_channelizer_64ch_16tpc_1Gi"]
         kernels["config4_pfb_channelizer_64ch_1Gi"] = {"bound": "hbm", "achieved": e4["hbm_gbs"], "peak": peak_gbs,
-                                                       "frac": e4["frac_of_hbm"], "unit": "GB/s", "ms": e4["ms"]}
+                                                       "frac": e4["frac_of_hbm"], "unit": "GB/s", "ms": e4["ms"],
+                                                       "algorithm": e4.get("algorithm")}
+    if "pfb_channelizer_64ch_16tpc_1Gi_tensor_core_dft" in extras:
+        e4 = extras["pfb_channelizer_64ch_16tpc_1Gi_tensor_core_dft"]
+        kernels["config4_pfb_channelizer_64ch_1Gi_tensor_core_dft"] = {
+            "bound": "hbm", "achieved": e4["hbm_gbs"], "peak": peak_gbs, "frac": e4["frac_of_hbm"], "unit": "GB/s",
+            "ms": e4["ms"], "algorithm": 2, "executed_tflops": e4["executed_tensor_tflops"], "executed_on": "tensor",
+            "executed_frac_of_measured_bf16_peak": e4["executed_frac_of_measured_bf16_peak"],
+            "selected_by_default": e4["selected_by_default"]}
 
     if rank == 0:
         line = {

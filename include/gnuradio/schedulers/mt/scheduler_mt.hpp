@@ -166,6 +166,9 @@ class thread_wrapper : public neighbor_interface
                 return executor_iteration_status::BLKD_OUT;
             work_output.emplace_back(space, first);
         }
+        std::vector<int> given_space;
+        for (auto& w : work_output)
+            given_space.push_back(w.n_items);
 
         work_return_code_t ret = b->do_work(work_input, work_output);
         if (ret != work_return_code_t::WORK_OK && ret != work_return_code_t::WORK_DONE)
@@ -214,12 +217,29 @@ class thread_wrapper : public neighbor_interface
             // because downstream has not drained yet: its space still grows, so that is BLKD_OUT,
             // not the end of the stream.
             if (all_upstream_done) {
+                // Order matters (this thread is the only writer of its output rings; the readers can only empty
+                // them).  (1) Anything still pending downstream: the space will grow, wait for it.  (2) The rings
+                // are empty -- and stay empty -- so the space seen NOW is all there will ever be: if it is more than
+                // this call was given (the reader drained the ring after write_info above), call again; only a call
+                // that had all of it and still produced nothing proves that nothing more can come out.  Checking
+                // the space first and "pending" second let the reader drain in between: the block retired with up
+                // to a ring of input unplaced (a 1-in-8 failure of SchedulerMTTest.OutputMultipleDrain).
                 bool output_pending = false;
                 for (auto& p : out_ports)
                     for (auto& buf : _bufman->get_output_buffers(p))
                         output_pending |= !buf->reader_done() && buf->items_pending() != 0;
                 if (output_pending)
                     return executor_iteration_status::BLKD_OUT;
+                for (size_t o = 0; o < out_ports.size(); o++) {
+                    int space = std::numeric_limits<int>::max();
+                    for (auto& buf : _bufman->get_output_buffers(out_ports[o])) {
+                        buffer_info_t wi;
+                        buf->write_info(wi);
+                        space = std::min(space, wi.n_items);
+                    }
+                    if (space > given_space[o])
+                        return executor_iteration_status::READY;
+                }
                 finish_block(bi);
                 return executor_iteration_status::DONE;
             }
