@@ -359,6 +359,12 @@ __global__ void __launch_bounds__(256, 2)
 // W8192^{tid + 256 i} = W8192^{tid} * W32^{i}: one per-thread register pair times compile-time
 // constants.  One HBM read and one HBM write per sample (the generic radix-2 kernel it replaces for
 // this size was latency-bound at 11 % of HBM).
+// B200_F8K_EARLY=1 (A/B, tools/f8k_ab.py): the even bins leave as 8-byte stores right after their transform, so that
+// their 32 registers are free during the odd transform.  Measured on the B200: 321 -> 256 GS/s (complex output), 358 ->
+// 330 (|.|): half-written 32-byte sectors cost more than the registers give.  Off.
+#ifndef B200_F8K_EARLY
+#define B200_F8K_EARLY 0
+#endif
 constexpr size_t F8K_SMEM = 8192 * 8 + 16 * F4K_STRIDE * 8 + 256 * 8 + 32;
 
 template <bool FWD, int I>
@@ -481,6 +487,24 @@ __global__ void __launch_bounds__(256, 2)
                 e[i] = row[i];
             dft16<FWD>(e); // X[2 (tid + 256 k2)] in e[pos16(k2)]
         }
+#if B200_F8K_EARLY
+        // A/B: the even bins leave as 8-byte stores now (the odd ones fill the other half of each 16-byte pair
+        // later; the pairs merge in L2), so e[] is dead during the odd transform: 32 registers back
+        if (OUT == B200_FFT_OUT_COMPLEX) {
+            float2* y = reinterpret_cast<float2*>(out) + vec * 8192;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++)
+                __stcs(y + 2 * (k2 * 256 + tid), e[pos16(k2)]);
+        } else {
+            float* y = reinterpret_cast<float*>(out) + vec * 8192;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                const float2 p = e[pos16(k2)];
+                const float pe = fmaf(p.x, p.x, p.y * p.y);
+                __stcs(y + 2 * (k2 * 256 + tid), OUT == B200_FFT_OUT_MAG ? sqrt_approx(pe) : pe);
+            }
+        }
+#endif
         __syncthreads(); // pass-3 reads of sA done
         // ---- odd bins: the b's come back from this thread's own slots
 #pragma unroll
@@ -516,6 +540,22 @@ __global__ void __launch_bounds__(256, 2)
                 v[i] = row[i];
             dft16<FWD>(v); // X[2 (tid + 256 k2) + 1] in v[pos16(k2)]
         }
+#if B200_F8K_EARLY
+        if (OUT == B200_FFT_OUT_COMPLEX) {
+            float2* y = reinterpret_cast<float2*>(out) + vec * 8192;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++)
+                __stcs(y + 2 * (k2 * 256 + tid) + 1, v[pos16(k2)]);
+        } else {
+            float* y = reinterpret_cast<float*>(out) + vec * 8192;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) {
+                const float2 q = v[pos16(k2)];
+                const float po = fmaf(q.x, q.x, q.y * q.y);
+                __stcs(y + 2 * (k2 * 256 + tid) + 1, OUT == B200_FFT_OUT_MAG ? sqrt_approx(po) : po);
+            }
+        }
+#else
         if (OUT == B200_FFT_OUT_COMPLEX) {
             float4* y = reinterpret_cast<float4*>(out) + vec * 4096;
 #pragma unroll
@@ -533,6 +573,7 @@ __global__ void __launch_bounds__(256, 2)
                                                                    : make_float2(pe, po));
             }
         }
+#endif
         __syncthreads(); // pass-3 reads done before the next vector's pass-1 writes
     }
 }
