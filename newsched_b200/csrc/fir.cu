@@ -445,7 +445,8 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         return set_err(B200_ERR_ARG, "fir_create: need n_taps >= 1, decimation >= 1, taps != NULL");
     if (p->algorithm == 2 && !tc_supported(p->n_taps, p->decimation, !p->is_complex))
         return set_err(B200_ERR_UNSUPPORTED,
-                       "fir_create: the tensor-core form needs a complex stream, decimation 1..8, <= 2048 taps per branch");
+                       "fir_create: the tensor-core form needs decimation 1..8 and <= 2048 taps per branch (complex stream), or "
+                       "decimation 1 and <= 449 taps (float stream)");
     b200_fir* h = new b200_fir();
     h->T = p->n_taps;
     h->D = p->decimation;
@@ -498,6 +499,17 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
         bool want2 = p->algorithm == 2;
         if (p->algorithm == 0 && h->vec == 2 && h->D == 1 && h->T >= 33 && h->T <= 384 && tc_supported(h->T, h->D, 0))
             want2 = true;
+        // float streams (fff): the same kernel with two 4096-sample runs per tile; crossovers measured with
+        // tools/real_tc_ab.py (B200_FIR_REAL_TC_MIN / _MAX override them)
+        if (p->algorithm == 0 && h->vec == 1 && h->D == 1 && tc_supported(h->T, h->D, 1)) {
+            int tmin = 33, tmax = 448;
+            if (const char* e = getenv("B200_FIR_REAL_TC_MIN"))
+                tmin = atoi(e);
+            if (const char* e = getenv("B200_FIR_REAL_TC_MAX"))
+                tmax = atoi(e);
+            if (h->T >= tmin && h->T <= tmax)
+                want2 = true;
+        }
         if (const char* e = getenv("B200_FIR_ALGO")) {
             if (p->algorithm == 0 && atoi(e) == 2 && tc_supported(h->T, h->D, h->vec == 1))
                 want2 = true;
@@ -517,7 +529,7 @@ int b200_fir_create(const b200_fir_params* p, b200_fir** out)
             h->algorithm = 2;
             h->tc_tf32 = 1;
         } else if (want2) {
-            int rc = tc_create(p->taps, h->T, h->D, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
+            int rc = tc_create(p->taps, h->T, h->D, h->vec == 1, h->ep.fuse, h->ep.kre, h->ep.kim, &h->tc);
             if (rc != B200_OK) {
                 b200_fir_destroy(h);
                 return rc;

@@ -69,6 +69,8 @@ struct tc_args {
     const uint32_t* gAt; // TMEM-resident form: tap matrix [128 lanes][16*ksteps / 2] bf16 pairs, K contiguous
     int ts_plane_elems, ts_plane_bytes, ts_stages, ts_stage_bytes;
     int ts_swap;     // diagnostic: swap the bf16 halves of every 32-bit TMEM column of A
+    int real;        // fff (float stream): a tile is 8192 real outputs = two 4096-sample runs riding through the two planes
+                     // ("re" = first run, "im" = second) of the complex kernel: same MMAs, twice the sample rate
     int ts_nohead;   // A/B: head tile through the element-wise path (B200_TC_TS_HEAD=0)
     int ts_pdl;      // launched with programmatic stream serialization: griddepcontrol.wait after the prologue
     int dbg;         // bottleneck attribution (B200_TC_DBG): 1 = skip conversion, 2 = skip epilogue, 4 = skip MMAs, 8 = skip input copies
@@ -749,21 +751,77 @@ constexpr uint32_t TS_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 // ONE bulk copy; edge tiles (history in front, ragged end) are read element-wise.  A ring hands out windows
 // that start on any item (8 bytes): when x is only 8-byte aligned the copy starts one sample early (`shift` = 1,
 // the bulk copy needs 16-byte alignment) and the converters skip that sample.
-__device__ __forceinline__ int ts_shift(const tc_args& a) { return (int)((reinterpret_cast<uintptr_t>(a.x) >> 3) & 1); }
-// head tile of a call: its first P samples are history (or zeros), the other 4096 are x[0 .. 4096).  The producer
+template <bool REAL>
+__device__ __forceinline__ int ts_shift(const tc_args& a)
+{
+    return REAL ? 0 : (int)((reinterpret_cast<uintptr_t>(a.x) >> 3) & 1);
+}
+// head tile of a call: its first P samples are history (or zeros), the others are x[0 .. tile).  The producer
 // warp copies the history part itself and sends the rest as a bulk copy, so the tile runs through the same staged
 // conversion as an interior one (the element-wise path costs ~3 us, on the CTA that has the most tiles).
+template <bool REAL>
 __device__ __forceinline__ bool ts_head_tile(const tc_args& a, long long j0)
 {
-    return j0 == -(long long)a.P && a.P > 0 && ts_shift(a) == 0 && a.ts_plane_elems - a.P <= a.n_in && !a.ts_nohead;
+    if (REAL)
+        return j0 == -(long long)a.P && a.P > 0 && 2 * TS_TILE <= a.n_in && !a.ts_nohead;
+    return j0 == -(long long)a.P && a.P > 0 && ts_shift<REAL>(a) == 0 && a.ts_plane_elems - a.P <= a.n_in && !a.ts_nohead;
 }
+// REAL: a tile's input is the 8192 + P floats from j0 on (run A: [j0, j0 + plane_elems), run B: 4096 further); the
+// bulk copies need a 16-byte aligned stream, j0 is a multiple of 16 samples
+template <bool REAL>
 __device__ __forceinline__ bool ts_fast_tile(const tc_args& a, long long j0)
 {
-    const int sh = ts_shift(a);
-    return (j0 - sh >= 0 && j0 + a.ts_plane_elems + sh <= a.n_in) || ts_head_tile(a, j0);
+    if (REAL) {
+        if (reinterpret_cast<uintptr_t>(a.x) & 15)
+            return false;
+        return (j0 >= 0 && j0 + 2 * TS_TILE + a.P <= a.n_in) || ts_head_tile<REAL>(a, j0);
+    }
+    const int sh = ts_shift<REAL>(a);
+    return (j0 - sh >= 0 && j0 + a.ts_plane_elems + sh <= a.n_in) || ts_head_tile<REAL>(a, j0);
 }
 
+// element-wise conversion of an edge tile of a REAL stream: plane "re" <- samples j0 + i, plane "im" <- j0 + 4096 + i
+template <int NCONV>
+__device__ __forceinline__ void tc_convert_real(const tc_args& a, uint8_t* planes, int plane_elems, int plane_bytes,
+                                                long long m0, int ctid)
+{
+    if (a.dbg & 1)
+        return;
+    const float* x = reinterpret_cast<const float*>(a.x);
+    const float* hist = reinterpret_cast<const float*>(a.hist);
+    const long long j0 = m0 - a.P;
+    auto fetch = [&](long long n) -> float {
+        if (n >= 0)
+            return n < a.n_in ? __ldg(x + n) : 0.f;
+        return (hist != nullptr && n >= -(long long)a.Tm1) ? __ldg(hist + (a.Tm1 + n)) : 0.f;
+    };
+#pragma unroll 1
+    for (int base = 0; base < plane_elems; base += NCONV * 4) {
+        float va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * NCONV + ctid;
+            va[u] = i < plane_elems ? fetch(j0 + i) : 0.f;
+            vb[u] = i < plane_elems ? fetch(j0 + TS_TILE + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * NCONV + ctid;
+            if (i < plane_elems) {
+                __nv_bfloat16 rh, rl, ih, il;
+                tc_split(va[u], rh, rl);
+                tc_split(vb[u], ih, il);
+                const uint32_t off = tc_plane_off((uint32_t)i);
+                *reinterpret_cast<__nv_bfloat16*>(planes + off) = rh;
+                *reinterpret_cast<__nv_bfloat16*>(planes + plane_bytes + off) = rl;
+                *reinterpret_cast<__nv_bfloat16*>(planes + 2 * plane_bytes + off) = ih;
+                *reinterpret_cast<__nv_bfloat16*>(planes + 3 * plane_bytes + off) = il;
+            }
+        }
+    }
+}
 
+template <bool REAL>
 __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args a)
 {
     extern __shared__ uint8_t tc_smem_raw[];
@@ -780,7 +838,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + TS_IN_STAGES);
 
     const int tid = threadIdx.x, warp = tc_warp_idx(), lane = tid & 31;
-    const long long n_tiles = (a.n_out + TS_TILE - 1) / TS_TILE;
+    constexpr int TILE_OUT = REAL ? 2 * TS_TILE : TS_TILE; // outputs (items) per tile
+    const long long n_tiles = (a.n_out + TILE_OUT - 1) / TILE_OUT;
     // CTA order reversed: the head tile (history in front of the call) goes to the LAST CTA, which has one tile
     // fewer than the first ones whenever the tiles do not divide evenly
     const long long bid = (long long)(gridDim.x - 1 - blockIdx.x);
@@ -872,12 +931,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
         // ================= input producer =================
         int nf = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const long long j0 = (bid + (long long)it * gridDim.x) * TS_TILE - a.P;
-            if (!ts_fast_tile(a, j0))
+            const long long j0 = (bid + (long long)it * gridDim.x) * TILE_OUT - a.P;
+            if (!ts_fast_tile<REAL>(a, j0))
                 continue;                                            // edge tile: the converters read it themselves
             const int slot = nf % TS_IN_STAGES;
             mbar_wait(&in_empty[slot], ((nf / TS_IN_STAGES) & 1) ^ 1);
-            if (j0 < 0) {
+            if (REAL) {
+                // float stream: 8192 + P samples per tile; the head tile's first P come from the history
+                float* st = reinterpret_cast<float*>(staging + (size_t)slot * a.ts_stage_bytes);
+                const float* xr = reinterpret_cast<const float*>(a.x);
+                const float* hr = reinterpret_cast<const float*>(a.hist);
+                if (j0 < 0) {
+                    for (int i = lane; i < a.P; i += 32) {
+                        const int n = i - a.P;
+                        st[i] = (hr != nullptr && n >= -a.Tm1) ? __ldg(hr + (a.Tm1 + n)) : 0.f;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)(2 * TS_TILE + (j0 < 0 ? 0 : a.P)) * 4u;
+                    mbar_arrive_expect_tx(&in_full[slot], bytes);
+                    bulk_copy_g2s(j0 < 0 ? st + a.P : st, j0 < 0 ? xr : xr + j0, bytes, &in_full[slot]);
+                }
+            } else if (j0 < 0) {
                 // head tile: history (or zeros) by this warp, x[0 .. 4096) as a bulk copy behind it; the mbarrier
                 // arrive below releases the generic stores to the converters
                 float2* st = reinterpret_cast<float2*>(staging + (size_t)slot * a.ts_stage_bytes);
@@ -892,7 +968,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
                     bulk_copy_g2s(st + a.P, a.x, bytes, &in_full[slot]);
                 }
             } else if (lane == 0) {
-                const int sh = ts_shift(a);
+                const int sh = ts_shift<REAL>(a);
                 const uint32_t bytes = (uint32_t)(a.ts_plane_elems + 2 * sh) * 8u;
                 if (a.dbg & 8) {
                     mbar_arrive(&in_full[slot]);
@@ -912,10 +988,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
         const uint32_t tl = d_base + ((uint32_t)(quarter * 32) << 16);
         for (int it = 0; it < my_tiles; it++) {
             const int acc = it & 1;
-            const long long m0 = (bid + (long long)it * gridDim.x) * TS_TILE;
+            const long long m0 = (bid + (long long)it * gridDim.x) * TILE_OUT;
             const long long left = a.n_out - m0;
-            const int count = left < TS_TILE ? (int)left : TS_TILE;
+            const int count = left < TILE_OUT ? (int)left : TILE_OUT;
             float2* dst = a.y + m0;
+            float* dstr = reinterpret_cast<float*>(a.y) + m0; // REAL: run A at dstr, run B 4096 floats further
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tc_fence_after();
             if (a.dbg & 2) {
@@ -939,11 +1016,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
                     const float sr = lower ? re[2 * j + 1] : re[2 * j], si = lower ? im[2 * j + 1] : im[2 * j];
                     const float rr = __shfl_xor_sync(0xffffffffu, sr, 16), ri = __shfl_xor_sync(0xffffffffu, si, 16);
                     float2 v = make_float2((lower ? re[2 * j] : re[2 * j + 1]) + rr, (lower ? im[2 * j] : im[2 * j + 1]) + ri);
-                    if (a.fuse)
-                        v = cmul_nofma(v, a.kre, a.kim);
                     const int o = (ch * 32 + 2 * j + (lower ? 0 : 1)) * 64 + c;
-                    if (o < count)
-                        __stcs(dst + o, v);
+                    if (REAL) {
+                        if (a.fuse) {
+                            v.x = __fmul_rn(v.x, a.kre);
+                            v.y = __fmul_rn(v.y, a.kre);
+                        }
+                        if (o < count)
+                            __stcs(dstr + o, v.x);
+                        if (TS_TILE + o < count)
+                            __stcs(dstr + TS_TILE + o, v.y);
+                    } else {
+                        if (a.fuse)
+                            v = cmul_nofma(v, a.kre, a.kim);
+                        if (o < count)
+                            __stcs(dst + o, v);
+                    }
                 }
             }
         }
@@ -952,21 +1040,25 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
         const int ctid = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
         int nf = 0;
         for (int it = 0; it < my_tiles; it++) {
-            const long long m0 = (bid + (long long)it * gridDim.x) * TS_TILE;
+            const long long m0 = (bid + (long long)it * gridDim.x) * TILE_OUT;
             const int ps = it % S;
             uint8_t* pl = planes + (size_t)ps * 4 * a.ts_plane_bytes;
             mbar_wait(&planes_empty[ps], ((it / S) & 1) ^ 1);
-            if (ts_fast_tile(a, m0 - a.P)) {
+            if (ts_fast_tile<REAL>(a, m0 - a.P)) {
                 const int slot = nf % TS_IN_STAGES;
                 mbar_wait(&in_full[slot], (nf / TS_IN_STAGES) & 1);
                 if (!(a.dbg & 1)) {
-                    const float2* src = reinterpret_cast<const float2*>(staging + (size_t)slot * a.ts_stage_bytes) + ts_shift(a);
+                    const float2* src = reinterpret_cast<const float2*>(staging + (size_t)slot * a.ts_stage_bytes) + ts_shift<REAL>(a);
                     const int npairs = a.ts_plane_elems >> 1;
-                    const bool al16 = ts_shift(a) == 0;
+                    const bool al16 = ts_shift<REAL>(a) == 0;
 #pragma unroll 4
                     for (int q = ctid; q < npairs; q += TS_CONV) {
                         float4 v;
-                        if (al16) {
+                        if (REAL) {
+                            // samples 2q, 2q+1 of run A and of run B (4096 floats = 2048 float2 further)
+                            const float2 ra = src[q], rb = src[TS_TILE / 2 + q];
+                            v = make_float4(ra.x, rb.x, ra.y, rb.y);
+                        } else if (al16) {
                             v = *reinterpret_cast<const float4*>(src + 2 * q);
                         } else {
                             const float2 s0 = src[2 * q], s1 = src[2 * q + 1];
@@ -989,7 +1081,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
                     mbar_arrive(&in_empty[slot]);                    // this warp has read its share of the slot
                 nf++;
             } else {
-                tc_convert<TS_CONV, 8>(a, pl, a.ts_plane_elems, a.ts_plane_bytes, m0, 0, ctid);
+                if (REAL)
+                    tc_convert_real<TS_CONV>(a, pl, a.ts_plane_elems, a.ts_plane_bytes, m0, ctid);
+                else
+                    tc_convert<TS_CONV, 8>(a, pl, a.ts_plane_elems, a.ts_plane_bytes, m0, 0, ctid);
             }
             fence_proxy_async();
             __syncwarp();
@@ -1014,6 +1109,7 @@ struct tc_plan {
     float kre = 1.f, kim = 0.f;
     int desc_mode = 0;
     size_t smem = 0;
+    int real = 0;          // float stream (fff): tap-stationary kernel only
     int ts = 0;            // 1: tap-stationary kernel (fir_tc_ts_kernel): D = 1, K <= 512
     int ts_plane_elems = 0, ts_plane_bytes = 0, ts_stages = 0, ts_stage_bytes = 0, ts_swap = 0;
     size_t ts_smem = 0;
@@ -1043,9 +1139,11 @@ static inline float tc_bf16_f(uint16_t b)
 
 bool tc_supported(int n_taps, int decimation, int real)
 {
-    if (real || n_taps < 1 || decimation < 1 || decimation > 8)
+    if (n_taps < 1 || decimation < 1 || decimation > 8)
         return false;
     const int tq = (n_taps + decimation - 1) / decimation;
+    if (real) // float streams: the tap-stationary kernel only (decimation 1, K = roundup16(T - 1) + 64 <= 512)
+        return decimation == 1 && (n_taps - 1 + 15) / 16 * 16 + TC_PH <= 2 * TS_A_COLS;
     return tq <= 2048;
 }
 
@@ -1109,14 +1207,15 @@ int tc_create_tf32(const float* taps, int n_taps, int fuse, float kre, float kim
     return B200_OK;
 }
 
-int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre, float kim, tc_plan** out)
+int tc_create(const float* taps, int n_taps, int decimation, int real, int fuse, float kre, float kim, tc_plan** out)
 {
     *out = nullptr;
-    if (!tc_supported(n_taps, decimation, 0))
+    if (!tc_supported(n_taps, decimation, real))
         return set_err(B200_ERR_UNSUPPORTED, "fir(tensor core): complex stream, decimation 1..8, <= 2048 taps per branch");
     tc_plan* p = new tc_plan();
     p->T = n_taps;
     p->D = decimation;
+    p->real = real;
     p->Tq = (n_taps + decimation - 1) / decimation;
     p->P = (p->Tq - 1 + 15) / 16 * 16;
     const int kneed = p->P + TC_PH;
@@ -1214,7 +1313,7 @@ int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre
         p->ts_smem = 1024 + (size_t)st * 4 * p->ts_plane_bytes + (size_t)TS_IN_STAGES * p->ts_stage_bytes + 256;
         p->ts = 1;
         if (const char* e = getenv("B200_TC_TS"))
-            p->ts = atoi(e) != 0;
+            p->ts = atoi(e) != 0 || p->real; // float streams exist in this kernel only
         if (const char* e = getenv("B200_TC_TS_SWAP"))
             p->ts_swap = atoi(e);
     }
@@ -1228,7 +1327,9 @@ int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre
         if (e == cudaSuccess)
             e = cudaMemcpy(p->d_at, at_rows.data(), at_rows.size() * 2, cudaMemcpyHostToDevice);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fir_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            e = cudaFuncSetAttribute(fir_tc_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fir_tc_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(fir_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1281,6 +1382,8 @@ int tc_launch(tc_plan* p, const float* d_hist, const void* d_in, void* d_out, lo
     a.desc_mode = p->desc_mode;
     if (const char* e = getenv("B200_TC_DBG"))
         a.dbg = atoi(e);
+    if (p->real && !p->ts)
+        return set_err(B200_ERR_UNSUPPORTED, "fir(tensor core): float streams need the tap-stationary kernel (<= 449 taps)");
     if (p->tf32) {
         const long long tf_tiles = (n_out + TF_TILE - 1) / TF_TILE;
         B200_LAUNCH(fir_tc_tf32_kernel, (unsigned)tf_tiles, TC_THREADS, p->smem, s, a);
@@ -1293,16 +1396,25 @@ int tc_launch(tc_plan* p, const float* d_hist, const void* d_in, void* d_out, lo
         a.ts_stages = p->ts_stages;
         a.ts_stage_bytes = p->ts_stage_bytes;
         a.ts_swap = p->ts_swap;
-        const long long ts_tiles = (n_out + TS_TILE - 1) / TS_TILE, sms = sm_count();
+        const long long tile_out = p->real ? 2 * TS_TILE : TS_TILE;
+        const long long ts_tiles = (n_out + tile_out - 1) / tile_out, sms = sm_count();
+        a.real = p->real;
         static const int no_head = [] { const char* e = getenv("B200_TC_TS_HEAD"); return e && atoi(e) == 0; }();
         static const int use_pdl = [] { const char* e = getenv("B200_TC_PDL"); return !e || atoi(e) != 0; }();
         a.ts_nohead = no_head;
         a.ts_pdl = use_pdl;
+        const unsigned grid = (unsigned)(ts_tiles < sms ? ts_tiles : sms);
         if (!use_pdl) {
-            B200_LAUNCH(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
+            if (p->real)
+                B200_LAUNCH(fir_tc_ts_kernel<true>, grid, TS_THREADS, p->ts_smem, s, a);
+            else
+                B200_LAUNCH(fir_tc_ts_kernel<false>, grid, TS_THREADS, p->ts_smem, s, a);
             return B200_OK;
         }
-        B200_LAUNCH_PDL(fir_tc_ts_kernel, (unsigned)(ts_tiles < sms ? ts_tiles : sms), TS_THREADS, p->ts_smem, s, a);
+        if (p->real)
+            B200_LAUNCH_PDL(fir_tc_ts_kernel<true>, grid, TS_THREADS, p->ts_smem, s, a);
+        else
+            B200_LAUNCH_PDL(fir_tc_ts_kernel<false>, grid, TS_THREADS, p->ts_smem, s, a);
         return B200_OK;
     }
     if (p->pipe) {

@@ -4,9 +4,10 @@
 
 namespace b200 {
 struct tc_plan;
-// complex stream, real taps; decimation 1..8; up to 2048 taps per polyphase branch
+// complex stream, real taps; decimation 1..8; up to 2048 taps per polyphase branch.  real = 1 (float stream):
+// decimation 1 and up to 449 taps (the tap-stationary kernel, two 4096-sample runs per tile)
 bool tc_supported(int n_taps, int decimation, int real);
-int tc_create(const float* taps, int n_taps, int decimation, int fuse, float kre, float kim, tc_plan** out);
+int tc_create(const float* taps, int n_taps, int decimation, int real, int fuse, float kre, float kim, tc_plan** out);
 // TF32 split, decimation 1: built to measure the second tensor-core precision (algorithm 6), not selected automatically
 int tc_create_tf32(const float* taps, int n_taps, int fuse, float kre, float kim, tc_plan** out);
 void tc_destroy(tc_plan* p);

@@ -659,9 +659,57 @@ def test_fir_tensor_core_form(cuda, T, D):
 def test_fir_tensor_core_form_rejects_what_it_cannot_do(cuda):
     import newsched_b200 as nb
     with pytest.raises(nb.B200Error):
-        nb.FirFilter(np.ones(64, np.float32), 1, is_complex=False, algorithm=2)    # real streams: SIMT forms
+        nb.FirFilter(np.ones(64, np.float32), 2, is_complex=False, algorithm=2)    # float streams: decimation 1 only
+    with pytest.raises(nb.B200Error):
+        nb.FirFilter(np.ones(450, np.float32), 1, is_complex=False, algorithm=2)   # ... and taps resident in TMEM (K <= 512)
     with pytest.raises(nb.B200Error):
         nb.FirFilter(np.ones(64, np.float32), 9, algorithm=2)                      # decimation > 8
+
+
+@pytest.mark.parametrize("T", [33, 64, 100, 256, 448, 5])
+def test_fir_fff_tensor_core_form(cuda, T):
+    """fir_filter_fff on the tensor cores: the tap-stationary block-Toeplitz kernel with two 4096-sample runs of the
+    float stream riding through its two planes.  Against the fp64 oracle: one shot, streamed in ragged chunks,
+    fused constant, a 4-byte-aligned stream (element-wise tiles), time segments with a halo, tiny inputs."""
+    import newsched_b200 as nb
+    rng = np.random.default_rng(900 + T)
+    taps = (rng.uniform(-1, 1, T) / T).astype(np.float32)
+    n = 8192 * 37 + 4097 + 13                         # whole tiles, a tile with only its first run complete, a ragged end
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    dx = dev(cuda, x)
+    ref = o.fir(x, taps, 1)
+    f = nb.FirFilter(taps, 1, is_complex=False, algorithm=2)
+    assert f.algorithm == 2
+    y, nc = f.work(dx)
+    assert nc == n and o.rel_rms(host(y), ref) < TOL_RMS
+    # streaming: the history carries over calls of any length (shorter than a tile, shorter than the history, one item)
+    g = nb.FirFilter(taps, 1, is_complex=False, algorithm=2)
+    outs, pos = [], 0
+    for m in (1, 7, T - 1 if T > 1 else 1, 4096, 8191, 8192, 8193, 100000, 10 ** 9):
+        if pos >= n:
+            break
+        yy, c = g.work(dx[pos:pos + m])
+        outs.append(host(yy))
+        pos += c
+    assert pos == n and o.rel_rms(np.concatenate(outs), ref) < TOL_RMS
+    # fused multiply_const (real constant)
+    yk, _ = nb.FirFilter(taps, 1, is_complex=False, algorithm=2, multiply_const=0.375).work(dx)
+    assert o.rel_rms(host(yk), ref * np.float32(0.375)) < TOL_RMS
+    # a stream that is only 4-byte aligned: same numbers through the element-wise tiles
+    xo = cuda.empty(n + 1, dtype=cuda.float32, device="cuda")
+    xo[1:] = dx
+    yo, _ = nb.FirFilter(taps, 1, is_complex=False, algorithm=2).work(xo[1:])
+    assert o.rel_rms(host(yo), ref) < TOL_RMS
+    # time segment with its halo == the same outputs of the stream
+    cut = 8192 * 11 + 16
+    if T > 1:
+        seg = nb.FirFilter(taps, 1, is_complex=False, algorithm=2).work_segment(dx[cut:], dx[cut - (T - 1):cut])
+        assert o.rel_rms(host(seg), ref[cut:]) < TOL_RMS
+    for m in (0, 1, 63, 64, 4095, 4096, 4097):
+        ys, c = nb.FirFilter(taps, 1, is_complex=False, algorithm=2).work(dx[:m])
+        assert c == m and ys.numel() == m
+        if m:
+            assert o.rel_rms(host(ys), ref[:m]) < TOL_RMS or np.abs(host(ys) - ref[:m]).max() < 1e-6
 
 
 def test_fir_auto_algorithm_choice(cuda):
@@ -670,7 +718,11 @@ def test_fir_auto_algorithm_choice(cuda):
     assert nb.FirFilter(np.ones(64, np.float32), 1).algorithm == 2     # config 1: block-Toeplitz GEMM on tcgen05
     assert nb.FirFilter(np.ones(384, np.float32), 1).algorithm == 2
     assert nb.FirFilter(np.ones(385, np.float32), 1).algorithm == 3    # beyond: overlap-save
-    assert nb.FirFilter(np.ones(64, np.float32), 1, is_complex=False).algorithm == 1   # real streams stay SIMT
+    assert nb.FirFilter(np.ones(32, np.float32), 1, is_complex=False).algorithm == 1   # float streams: the same rule ...
+    assert nb.FirFilter(np.ones(64, np.float32), 1, is_complex=False).algorithm == 2
+    assert nb.FirFilter(np.ones(448, np.float32), 1, is_complex=False).algorithm == 2  # ... while the taps fit TMEM
+    assert nb.FirFilter(np.ones(449, np.float32), 1, is_complex=False).algorithm == 3
+    assert nb.FirFilter(np.ones(64, np.float32), 4, is_complex=False).algorithm == 1   # decimating float streams stay SIMT
     assert nb.FirFilter(np.ones(64, np.float32), 1, algorithm=1).algorithm == 1        # and the SIMT forms stay selectable
     assert nb.FirFilter(np.ones(1024, np.float32), 4).algorithm == 3   # config 3: overlap-save
     assert nb.FirFilter(np.ones(1024, np.float32), 4, is_complex=False).algorithm == 3
