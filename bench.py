@@ -498,6 +498,19 @@ def run_b200(args):
         extras["fir_ccf_64taps_128Mi"] = fir_record(SAMPLES / (t * 1e-3) / 1e9, 64, 1, fir.algorithm, peak_gbs, fp32_tf,
                                                     bf16_tf, t)
         del y1b
+        # fir_filter_fff (float stream, 8 B per sample): 64 / 256 taps on the tensor cores (two 4096-sample runs per
+        # tile ride through the two planes of the complex kernel), the SIMT form beside it
+        xr = torch.view_as_real(x).reshape(-1)[:SAMPLES]
+        yr = torch.empty(SAMPLES, dtype=torch.float32, device=dev)
+        for Tr, algo_r in ((64, 0), (64, 1), (256, 0)):
+            tr = (rng.uniform(-1, 1, Tr) / Tr).astype(np.float32)
+            fir = nb.FirFilter(tr, 1, is_complex=False, algorithm=algo_r)
+            t = timed(torch, lambda: fir.work_segment(xr, None, yr), 5, 2, lambda: None) / 5
+            grs = SAMPLES / (t * 1e-3) / 1e9
+            extras[f"fir_fff_{Tr}taps_128Mi" + ("_simt_direct" if algo_r == 1 else "")] = {
+                "algorithm": fir.algorithm, "Mreal_samples_s": grs * 1e3, "ms": t, "bound": "hbm", "unit": "GB/s",
+                "achieved": grs * 8, "peak": peak_gbs, "frac": grs * 8 / peak_gbs, "algorithmic_bytes_per_sample": 8}
+        del yr
         # short decimating filters run folded into the TMA-staged SIMT kernel: HBM-bound (10 B per input at D = 4)
         for Td, Dd in ((32, 4), (64, 4), (64, 8)):
             taps = (rng.uniform(-1, 1, Td) / Td).astype(np.float32)
