@@ -751,10 +751,11 @@ constexpr uint32_t TS_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 // ONE bulk copy; edge tiles (history in front, ragged end) are read element-wise.  A ring hands out windows
 // that start on any item (8 bytes): when x is only 8-byte aligned the copy starts one sample early (`shift` = 1,
 // the bulk copy needs 16-byte alignment) and the converters skip that sample.
+// samples between the 16-byte boundary at or below x[0] and x[0]: 0 / 1 for a complex stream, 0 .. 3 for a float stream
 template <bool REAL>
 __device__ __forceinline__ int ts_shift(const tc_args& a)
 {
-    return REAL ? 0 : (int)((reinterpret_cast<uintptr_t>(a.x) >> 3) & 1);
+    return REAL ? (int)((reinterpret_cast<uintptr_t>(a.x) >> 2) & 3) : (int)((reinterpret_cast<uintptr_t>(a.x) >> 3) & 1);
 }
 // head tile of a call: its first P samples are history (or zeros), the others are x[0 .. tile).  The producer
 // warp copies the history part itself and sends the rest as a bulk copy, so the tile runs through the same staged
@@ -763,7 +764,7 @@ template <bool REAL>
 __device__ __forceinline__ bool ts_head_tile(const tc_args& a, long long j0)
 {
     if (REAL)
-        return j0 == -(long long)a.P && a.P > 0 && 2 * TS_TILE <= a.n_in && !a.ts_nohead;
+        return j0 == -(long long)a.P && a.P > 0 && ts_shift<REAL>(a) == 0 && 2 * TS_TILE <= a.n_in && !a.ts_nohead;
     return j0 == -(long long)a.P && a.P > 0 && ts_shift<REAL>(a) == 0 && a.ts_plane_elems - a.P <= a.n_in && !a.ts_nohead;
 }
 // REAL: a tile's input is the 8192 + P floats from j0 on (run A: [j0, j0 + plane_elems), run B: 4096 further); the
@@ -772,9 +773,10 @@ template <bool REAL>
 __device__ __forceinline__ bool ts_fast_tile(const tc_args& a, long long j0)
 {
     if (REAL) {
-        if (reinterpret_cast<uintptr_t>(a.x) & 15)
-            return false;
-        return (j0 >= 0 && j0 + 2 * TS_TILE + a.P <= a.n_in) || ts_head_tile<REAL>(a, j0);
+        // a ring hands out windows that start on any item (4 bytes): the copy then starts `sh` samples early and ends
+        // (4 - sh) % 4 samples late, so that both ends sit on 16-byte boundaries, and the converters skip the lead
+        const int sh = ts_shift<REAL>(a);
+        return (j0 - sh >= 0 && j0 + 2 * TS_TILE + a.P + ((4 - sh) & 3) <= a.n_in) || ts_head_tile<REAL>(a, j0);
     }
     const int sh = ts_shift<REAL>(a);
     return (j0 - sh >= 0 && j0 + a.ts_plane_elems + sh <= a.n_in) || ts_head_tile<REAL>(a, j0);
@@ -949,9 +951,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    const uint32_t bytes = (uint32_t)(2 * TS_TILE + (j0 < 0 ? 0 : a.P)) * 4u;
+                    const int sh = j0 < 0 ? 0 : ts_shift<REAL>(a);
+                    const uint32_t bytes = (uint32_t)(2 * TS_TILE + (j0 < 0 ? 0 : a.P) + sh + ((4 - sh) & 3)) * 4u;
                     mbar_arrive_expect_tx(&in_full[slot], bytes);
-                    bulk_copy_g2s(j0 < 0 ? st + a.P : st, j0 < 0 ? xr : xr + j0, bytes, &in_full[slot]);
+                    bulk_copy_g2s(j0 < 0 ? st + a.P : st, j0 < 0 ? xr : xr + j0 - sh, bytes, &in_full[slot]);
                 }
             } else if (j0 < 0) {
                 // head tile: history (or zeros) by this warp, x[0 .. 4096) as a bulk copy behind it; the mbarrier
@@ -1056,8 +1059,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fir_tc_ts_kernel(const tc_args 
                         float4 v;
                         if (REAL) {
                             // samples 2q, 2q+1 of run A and of run B (4096 floats = 2048 float2 further)
-                            const float2 ra = src[q], rb = src[TS_TILE / 2 + q];
-                            v = make_float4(ra.x, rb.x, ra.y, rb.y);
+                            if (al16) {
+                                const float2* s2 = reinterpret_cast<const float2*>(staging + (size_t)slot * a.ts_stage_bytes);
+                                const float2 ra = s2[q], rb = s2[TS_TILE / 2 + q];
+                                v = make_float4(ra.x, rb.x, ra.y, rb.y);
+                            } else {
+                                const float* s1 = reinterpret_cast<const float*>(staging + (size_t)slot * a.ts_stage_bytes) +
+                                                  ts_shift<REAL>(a);
+                                v = make_float4(s1[2 * q], s1[TS_TILE + 2 * q], s1[2 * q + 1], s1[TS_TILE + 2 * q + 1]);
+                            }
                         } else if (al16) {
                             v = *reinterpret_cast<const float4*>(src + 2 * q);
                         } else {
