@@ -596,6 +596,8 @@ def run_b200(args):
                     ("config1_fir_ccf_64taps_8Gi_stream", ["--config", "1", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_1Gi", ["--config", "3", "--samples", str(1 << 30)]),
                     ("config3_fir1024d4_mulc_fft_8Gi_stream", ["--config", "3", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
+                    ("config4_pfb_channelizer_64ch_8Gi_stream", ["--config", "4", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
+                    ("config4_pfb_channelizer_64ch_tensor_core_dft_8Gi_stream", ["--config", "4", "--fused", "2", "--samples", str(1 << 33), "--buffer_size", str(1 << 30)]),
                     ("config0_vector_source_fir64_vector_sink_16Mi", ["--config", "10", "--samples", str(1 << 24), "--buffer_size", str(1 << 25)]),
                     ("cuda_copy_x4_1Gi", ["--config", "0", "--samples", str(1 << 30)])):
                 best = None

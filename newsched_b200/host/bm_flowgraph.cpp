@@ -8,6 +8,7 @@
 //   --config 1  cuda::null_source -> fir_filter_ccf(ntaps) -> null_sink
 //   --config 2  cuda::null_source -> fft(veclen, Blackman-Harris)[+ fused |.|] -> null_sink
 //   --config 3  cuda::null_source -> fir_filter_ccf(1024 taps, decim 4)[+ fused k] -> fft -> null_sink
+//   --config 4  cuda::null_source -> pfb_channelizer_ccf(64 channels x 16 taps) -> null_sink   (--fused 2: tensor-core DFT)
 //   --config 0  cuda::null_source -> nblocks x cuda::copy -> null_sink       (bm_mt_cuda_copy shape)
 //   --config 5  BASELINE configs[4]: one stream cut into --gpus time segments, each resident on its GPU
 //               (cuda::vector_source), fir_filter_ccf(ntaps, default 4096) per GPU with the (ntaps-1)-sample
@@ -26,6 +27,7 @@
 #include <gnuradio/blocklib/cuda/fir_filter.hpp>
 #include <gnuradio/blocklib/cuda/multiply_const.hpp>
 #include <gnuradio/blocklib/cuda/null_source.hpp>
+#include <gnuradio/blocklib/cuda/pfb_channelizer.hpp>
 #include <gnuradio/blocklib/cuda/vector_source.hpp>
 #include <gnuradio/devicebuffer.hpp>
 #include <gnuradio/flowgraph.hpp>
@@ -174,6 +176,22 @@ int main(int argc, char** argv)
                     dev(fg->connect(seg_fir[g], 0, snk, 0));
                     chain = { resident[g], seg_fir[g], snk };
                     items = samples;
+                } else if (config == 4) {
+                    // BASELINE configs[3]: 64-channel polyphase channelizer (16 taps per channel); --fused 2 selects the
+                    // form with the DFT across branches as a tensor-core GEMM (b200_pfb_set_algorithm 2)
+                    auto src = cuda::null_source::make(sizeof(gr_complex), samples, opt.clear != 0);
+                    std::vector<float> taps(64 * 16);
+                    for (int i = 0; i < 64 * 16; i++) { // windowed-sinc prototype
+                        const double t = (i - (64 * 16 - 1) / 2.0) / 64;
+                        const double sc = std::fabs(t) < 1e-12 ? 1.0 : std::sin(M_PI * t) / (M_PI * t);
+                        taps[i] = (float)(sc * (0.54 - 0.46 * std::cos(2 * M_PI * i / (64 * 16 - 1))) / 64);
+                    }
+                    auto ch = cuda::pfb_channelizer_ccf::make(64, taps, 0, 0, opt.fused == 2 ? 2 : 1);
+                    snk = blocks::null_sink::make(64 * sizeof(gr_complex));
+                    dev(fg->connect(src, 0, ch, 0));
+                    dev(fg->connect(ch, 0, snk, 0));
+                    chain = { src, ch, snk };
+                    items = samples / 64;
                 } else if (config == 3) {
                     auto src = cuda::null_source::make(sizeof(gr_complex), samples, opt.clear != 0);
                     std::vector<float> taps(1024, 1.0f / 1024);
