@@ -324,6 +324,18 @@ constexpr int PFBT_PLANE = 2 * 64 * 128; // one plane (hi or lo) of a tile: 2 K-
 constexpr int PFBT_TMEM_COLS = 256;
 constexpr uint32_t PFBT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
+// shared-memory descriptor of an MN-major SWIZZLE_128B operand: atoms of 8 k-rows x 64 n-elements (1 KiB), SBO = stride
+// between the atoms along K; LBO (stride between 64-element groups along N) is not used with N = 64
+__device__ __forceinline__ uint64_t pfbt_desc_mn(uint32_t saddr)
+{
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 constexpr int PFBT_THREADS = 288; // 8 worker warps (filters, conversion, epilogue) + 1 issuer warp (TMA refills, MMAs)
 
 __device__ __forceinline__ void pfbt_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(PFBT_THREADS) : "memory"); }
@@ -334,8 +346,12 @@ template <int P4T>
 __global__ void __launch_bounds__(PFBT_THREADS, 2)
     pfb64_tc_kernel(const float2* __restrict__ x, const float2* __restrict__ halo, float2* __restrict__ out,
                     const float* __restrict__ taps_rm /* [P4][64] */, const uint4* __restrict__ gA /* [128][hi 128 | lo 128] bf16 */,
-                    int P4, int Ptrue, long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok)
+                    int P4, int Ptrue, long long n_frames, long long n_in, int ch_begin, int ch_count, int tma_ok, int mn)
 {
+    // mn = 1: the branch outputs are stored MN-major (frames contiguous, layout verified by tools/mn_probe.cu): a
+    // filter thread holds 16 consecutive frames of ONE branch, i.e. two 16-byte runs per (re | im, hi | lo) plane row --
+    // 8 STS.128 per thread and tile instead of the 32 STS.32 of the K-major layout (mn = 0, kept for the A/B).  K is then
+    // ordered planar (k = i: re of branch i, k = 64 + i: im), which the host-built DFT matrix gA matches.
     extern __shared__ uint8_t pfbt_raw[];
     uint8_t* planes = tc_align1024(pfbt_raw);                       // [hi, lo] planes of the tile being multiplied
     const int rows = PFB64_TT + P4 - 1;
@@ -442,12 +458,15 @@ __global__ void __launch_bounds__(PFBT_THREADS, 2)
             __syncwarp();
             const uint32_t d = tmem + 128 + st * 64;
 #pragma unroll
+            const uint32_t idesc = mn ? (PFBT_IDESC | (1u << 16)) : PFBT_IDESC; // bit 16: B is MN-major
             for (int ks = 0; ks < 8; ks++) {
-                const uint32_t boff = (ks >> 2) * 8192 + (ks & 3) * 32;
-                const uint64_t bh = tc_desc(planes_s + boff, 0), bl = tc_desc(planes_s + PFBT_PLANE + boff, 0);
-                tc_mma_bf16_ts_w(d, tmem + ks * 8, bh, PFBT_IDESC, ks != 0);   // F_hi u_hi
-                tc_mma_bf16_ts_w(d, tmem + 64 + ks * 8, bh, PFBT_IDESC, 1);    // F_lo u_hi
-                tc_mma_bf16_ts_w(d, tmem + ks * 8, bl, PFBT_IDESC, 1);         // F_hi u_lo
+                // K-major: K-step = 32 bytes inside the 128-byte rows of a K-atom; MN-major: two 8-row atoms of 1 KiB
+                const uint32_t boff = mn ? ks * 2048 : (ks >> 2) * 8192 + (ks & 3) * 32;
+                const uint64_t bh = mn ? pfbt_desc_mn(planes_s + boff) : tc_desc(planes_s + boff, 0);
+                const uint64_t bl = mn ? pfbt_desc_mn(planes_s + PFBT_PLANE + boff) : tc_desc(planes_s + PFBT_PLANE + boff, 0);
+                tc_mma_bf16_ts_w(d, tmem + ks * 8, bh, idesc, ks != 0);   // F_hi u_hi
+                tc_mma_bf16_ts_w(d, tmem + 64 + ks * 8, bh, idesc, 1);    // F_lo u_hi
+                tc_mma_bf16_ts_w(d, tmem + ks * 8, bl, idesc, 1);         // F_hi u_lo
             }
             tc_commit_w(smem_u32(bar + 2 + st));
         }
@@ -505,6 +524,33 @@ __global__ void __launch_bounds__(PFBT_THREADS, 2)
                 mbar_wait(bar + 2 + (st ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
                 tc_fence_after();
             }
+            if (mn) {
+                // MN-major planes: row k = i (re) / 64 + i (im) of atom k / 8, the thread's frames 16 tg .. 16 tg + 15 are
+                // the 16-byte chunks 2 tg and 2 tg + 1 of that row (XOR-swizzled by the row inside the atom).  The eight
+                // lanes of a quarter-warp sit on the eight rows of one atom: conflict-free 16-byte stores.
+                uint8_t* rowre = planes + (i >> 3) * 1024 + (i & 7) * 128;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float2 a0 = acc[8 * h + 2 * q], a1 = acc[8 * h + 2 * q + 1];
+                        const __nv_bfloat162 hr = __floats2bfloat162_rn(a0.x, a1.x), hi_ = __floats2bfloat162_rn(a0.y, a1.y);
+                        const float2 hrf = __bfloat1622float2(hr), hif = __bfloat1622float2(hi_);
+                        const __nv_bfloat162 lr = __floats2bfloat162_rn(a0.x - hrf.x, a1.x - hrf.y);
+                        const __nv_bfloat162 li = __floats2bfloat162_rn(a0.y - hif.x, a1.y - hif.y);
+                        rh[q] = *reinterpret_cast<const uint32_t*>(&hr);
+                        ih[q] = *reinterpret_cast<const uint32_t*>(&hi_);
+                        rl[q] = *reinterpret_cast<const uint32_t*>(&lr);
+                        il[q] = *reinterpret_cast<const uint32_t*>(&li);
+                    }
+                    const int off = ((2 * tg + h) ^ (i & 7)) << 4;
+                    *reinterpret_cast<uint4*>(rowre + off) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+                    *reinterpret_cast<uint4*>(rowre + PFBT_PLANE + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+                    *reinterpret_cast<uint4*>(rowre + 8192 + off) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+                    *reinterpret_cast<uint4*>(rowre + 8192 + PFBT_PLANE + off) = make_uint4(il[0], il[1], il[2], il[3]);
+                }
+            } else {
             // (re, im) of u_i[t] -> k = 2i, 2i + 1 of frame row t: bf16 hi and lo planes
             uint8_t* pl = planes + (i >> 5) * 8192 + (i & 3) * 4;
             const int chunk = (i & 31) >> 2;
@@ -517,6 +563,7 @@ __global__ void __launch_bounds__(PFBT_THREADS, 2)
                 const int off = n * 128 + ((chunk ^ (n & 7)) << 4);
                 *reinterpret_cast<__nv_bfloat162*>(pl + off) = hi;
                 *reinterpret_cast<__nv_bfloat162*>(pl + PFBT_PLANE + off) = lo;
+            }
             }
             fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
             tc_fence_before();
@@ -1071,6 +1118,7 @@ struct b200_pfb {
     int tc_ok = 0;         // the tensor-core form exists for this (M, P)
     uint4* d_dft = nullptr; // [128 rows = (channel, re/im)][hi 128 | lo 128] bf16 DFT matrix
     size_t smem_tc = 0;
+    int tc_mn = 1;         // pfb64_tc_kernel: branch outputs stored MN-major (16-byte stores), DFT matrix with planar K
     int nbuf = 1;          // input tiles in shared memory (pfbm_kernel)
     int fusedM = 0; // 1: M = 16 / 32 / 128 / 256 on pfbm_kernel; 2: M = 4 / 8 on pfbs_kernel (single pass both)
     // generic M >= 16: branch filters -> scratch -> the library's own reverse FFT of length M
@@ -1091,7 +1139,7 @@ static int pfb_launch(b200_pfb* h, const void* d_halo, const void* d_in, void* d
 #define PFBT_GO(PT)                                                                               \
     B200_LAUNCH_PDL(pfb64_tc_kernel<PT>, (unsigned)g, PFBT_THREADS, h->smem_tc, s, (const float2*)d_in,           \
                 (const float2*)d_halo, (float2*)d_out, h->d_taps_rm, h->d_dft, h->P4, h->P, n_frames, \
-                n_in, h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0))
+                n_in, h->ch_begin, h->ch_count, (int)((uintptr_t)d_in % 16 == 0), h->tc_mn)
         switch (h->P4) {
         case 4: PFBT_GO(4); break;
         case 8: PFBT_GO(8); break;
@@ -1271,11 +1319,15 @@ int b200_pfb_create(const b200_pfb_params* p, b200_pfb** out)
         PFB_CUDA(cudaFuncSetAttribute(pfb64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         h->grid = 2 * sm_count();
         if (h->P4 <= 16) {
-            // tensor-core DFT form: DFT matrix rows m = 2c + part, columns k = 2i + (re | im), bf16 hi | lo
+            // tensor-core DFT form: DFT matrix rows m = 2c + part; columns k = 2i + (re | im) for the K-major planes,
+            // k = i (re) / 64 + i (im) for the MN-major ones; bf16 hi | lo
+            h->tc_mn = 1;
+            if (const char* e = getenv("B200_PFBT_MN"))
+                h->tc_mn = atoi(e) != 0;
             std::vector<uint16_t> F((size_t)128 * 256);
             for (int m = 0; m < 128; m++)
                 for (int k = 0; k < 128; k++) {
-                    const int c = m >> 1, po = m & 1, i = k >> 1, pi = k & 1;
+                    const int c = m >> 1, po = m & 1, i = h->tc_mn ? (k & 63) : (k >> 1), pi = h->tc_mn ? (k >> 6) : (k & 1);
                     const double th = 2.0 * M_PI * (double)((i * c) & 63) / 64.0;
                     const double v = po == pi ? std::cos(th) : (po ? std::sin(th) : -std::sin(th));
                     const float f = (float)v;
