@@ -35,6 +35,15 @@ def test_host_boundary_cpu():
         assert f"[  OK  ] {name}" in out
 
 
+def test_end_of_stream_drain_is_race_free():
+    """The end-of-stream decision for a 0/0 work() call raced with a draining reader (1 failing run in 8 before the
+    fix in scheduler_mt.hpp): the interpolating-block QA, many times over."""
+    exe = _build("qa_host_cpu")
+    for _ in range(25):
+        p = subprocess.run([exe, "OutputMultipleDrain"], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0 and " 0 failed" in p.stdout, p.stdout[-2000:] + p.stderr[-500:]
+
+
 @pytest.mark.gpu
 def test_flowgraphs_on_gpu():
     out = _run(_build("qa_cuda_flowgraph"), 600)
