@@ -274,6 +274,30 @@ QA_TEST(Config1, FirFffDecim)
 }
 
 // interpolating FIR and rational resampler as rate-changing blocks on device edges
+// full-rate float stream, 64 taps: the tensor-core form of fir_filter_fff (two 4096-sample runs per tile) inside a
+// flowgraph; small rings, so work() windows start on arbitrary 4-byte boundaries and cross many tiles
+QA_TEST(Config1, FirFff64TensorCore)
+{
+    auto inc = noise(900007, 15);
+    std::vector<float> in(inc.size());
+    for (size_t i = 0; i < in.size(); i++)
+        in[i] = inc[i].imag();
+    auto taps = rtaps(64, 16);
+    auto src = blocks::vector_source_f::make(in);
+    auto fir = cuda::fir_filter_fff::make(1, taps);
+    auto snk = blocks::vector_sink_f::make();
+    auto fg = flowgraph::make();
+    fg->connect(src, 0, fir, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(H2D, 1u << 20));
+    fg->connect(fir, 0, snk, 0)->set_custom_buffer(DEVICE_BUFFER_ARGS_SIZED(D2H, 1u << 20));
+    fg->set_scheduler(schedulers::scheduler_mt::make());
+    fg->validate();
+    fg->run();
+    std::vector<float> exp(in.size());
+    orc_fir_fff_f64(exp.data(), in.data(), (int64_t)in.size(), taps.data(), 64, 1, nullptr);
+    EXPECT_EQ(snk->data().size(), exp.size());
+    EXPECT_TRUE(rel_rms(snk->data(), exp) < TOL);
+}
+
 QA_TEST(Resampler, InterpAndRational)
 {
     auto in = noise(300000, 11);

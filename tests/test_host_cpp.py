@@ -49,7 +49,7 @@ def test_flowgraphs_on_gpu():
     out = _run(_build("qa_cuda_flowgraph"), 600)
     for name in ("SchedulerMTTest.CudaCopyBasic", "SchedulerMTTest.CudaCopyMultiThreaded",
                  "SchedulerMTTest.CudaCopyPinnedBuffers",
-                 "Config1.FirCcf64", "Config2.FftMag", "Config3.FirMulFftChain", "Config4.PfbChannelizer64",
+                 "Config1.FirCcf64", "Config1.FirFff64TensorCore", "Config2.FftMag", "Config3.FirMulFftChain", "Config4.PfbChannelizer64",
                  "Config4.PfbChannelizer64TensorCoreDft",
                  "Fusion.AdjacentBlocksCollapse", "TwoInput.MultiplyAndAdd",
                  "SchedulerMTTags.TagsAcrossDeviceBuffers"):
